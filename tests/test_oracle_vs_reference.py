@@ -1,0 +1,113 @@
+"""Live comparison of the CPU oracle with the unmodified reference (imported through oracle/ref_shim.py).
+Skipped when /root/reference is not mounted (e.g. on the GPU box).  Tolerance 1e-5 max-norm, fp32."""
+import pytest
+import torch
+
+from golden_util import rel_err
+from oracle import perceiver_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+def _hot_path_io(perceiver_io_module):
+    """Hook the reference PerceiverIO's _encoder/_decoder to capture the hot path's inputs/outputs."""
+    rec = {}
+
+    def enc_hook(mod, args, kwargs, out):
+        rec["enc"] = (args, kwargs, out)
+
+    def dec_hook(mod, args, kwargs, out):
+        rec["dec"] = (args, kwargs, out)
+
+    h1 = perceiver_io_module._encoder.register_forward_hook(enc_hook, with_kwargs=True)
+    h2 = perceiver_io_module._decoder.register_forward_hook(dec_hook, with_kwargs=True)
+    return rec, (h1, h2)
+
+
+def _check_wrapper_hot_path(pio, rec, enc_cfg, dec_cfg):
+    p = {k: v for k, v in pio.state_dict().items()}
+    (inputs, latents), ekw, enc_out = rec["enc"]
+    got = O.encoder_forward(p, "_encoder.", inputs=inputs, latents=latents, input_mask=ekw.get("input_mask"), **enc_cfg)
+    emax, el2 = rel_err(got, enc_out)
+    assert emax < 1e-5, ("encoder", emax, el2)
+    (query, lat), dkw, dec_out = rec["dec"]
+    got = O.decoder_forward(p, "_decoder.", query=query, latents=lat, query_mask=dkw.get("query_mask"), **dec_cfg)
+    emax, el2 = rel_err(got, dec_out)
+    assert emax < 1e-5, ("decoder", emax, el2)
+
+
+def test_language_wrapper_hot_path():
+    ns = ref_shim.load_wrappers()
+    torch.manual_seed(0)
+    model = ref_shim.perturb_parameters(ns.language.LanguagePerceiver(num_self_attends_per_block=3).eval())
+    tokens = torch.randint(6, 262, (1, 2048))
+    mask = torch.zeros(1, 2048, dtype=torch.bool)
+    mask[:, :1500] = True
+    rec, hooks = _hot_path_io(model.perceiver)
+    with torch.inference_mode():
+        model(tokens, mask)
+    _check_wrapper_hot_path(model.perceiver, rec,
+                            dict(num_blocks=1, num_self_attends_per_block=3, num_cross_attend_heads=8,
+                                 num_self_attend_heads=8, use_query_residual=True),
+                            dict(num_heads=8, use_query_residual=False, final_project=False))
+
+
+def test_classification_wrapper_hot_path():
+    ns = ref_shim.load_wrappers()
+    torch.manual_seed(0)
+    model = ref_shim.perturb_parameters(
+        ns.classification.ClassificationPerceiver(num_self_attends_per_block=2, num_blocks=2).eval())
+    img = torch.randn(1, 3, 224, 224)
+    rec, hooks = _hot_path_io(model.perceiver)
+    with torch.inference_mode():
+        model(img)
+    _check_wrapper_hot_path(model.perceiver, rec,
+                            dict(num_blocks=2, num_self_attends_per_block=2, num_cross_attend_heads=1,
+                                 num_self_attend_heads=8, use_query_residual=True),
+                            dict(num_heads=1, use_query_residual=True, final_project=True))
+
+
+def test_flow_wrapper_hot_path_small_image():
+    ns = ref_shim.load_wrappers()
+    torch.manual_seed(0)
+    model = ref_shim.perturb_parameters(
+        ns.flow.FlowPerceiver(img_size=(64, 80), num_latents=256, num_self_attends_per_block=2).eval())
+    a, b = torch.randn(1, 3, 64, 80), torch.randn(1, 3, 64, 80)
+    rec, hooks = _hot_path_io(model.perceiver)
+    with torch.inference_mode():
+        model(a, b, test_mode=False)
+    _check_wrapper_hot_path(model.perceiver, rec,
+                            dict(num_blocks=1, num_self_attends_per_block=2, num_cross_attend_heads=1,
+                                 num_self_attend_heads=16, use_query_residual=True),
+                            dict(num_heads=1, use_query_residual=False, final_project=True))
+
+
+@pytest.mark.parametrize("heads,qk,v", [(1, None, None), (4, 32, 80)])
+def test_cross_attention_random(heads, qk, v):
+    ns = ref_shim.load_reference()
+    torch.manual_seed(1)
+    m = ref_shim.perturb_parameters(ns.primitives.CrossAttention(q_in_channels=48, kv_in_channels=33, num_heads=heads,
+                                                                 qk_channels=qk, v_channels=v).eval())
+    q, kv = torch.randn(3, 17, 48), torch.randn(3, 129, 33)
+    km = torch.rand(3, 129) > 0.3
+    km[2] = False  # a sample with every key masked: the whole output row block is wiped
+    mask = ns.primitives.make_cross_attention_mask(torch.ones(3, 17, dtype=torch.bool), km)
+    with torch.inference_mode():
+        want = m(q, kv, attention_mask=mask)
+    got = O.cross_attention(dict(m.state_dict()), "", heads, True, q, kv, O.make_cross_attention_mask(torch.ones(3, 17, dtype=torch.bool), km))
+    assert rel_err(got, want)[0] < 1e-5
+
+
+def test_key_shard_combine_identity():
+    """The (O, m, l) merge over key shards equals un-sharded attention, in fp64."""
+    torch.manual_seed(2)
+    q = torch.randn(2, 9, 2, 8, dtype=torch.float64) * 4
+    k = torch.randn(2, 50, 2, 8, dtype=torch.float64)
+    v = torch.randn(2, 50, 2, 5, dtype=torch.float64)
+    km = torch.rand(2, 50) > 0.4
+    km[:, 25:37] = False  # one shard holds only masked keys
+    full = O.attend(q, k, v, O.make_cross_attention_mask(torch.ones(2, 9, dtype=torch.bool), km))
+    parts = [O.attend_partial(q, k[:, s], v[:, s], km[:, s]) for s in (slice(0, 25), slice(25, 37), slice(37, 50))]
+    merged = O.combine_partials(parts).permute(0, 2, 1, 3).reshape(2, 9, 10)
+    assert float((merged - full).abs().max()) < 1e-12
