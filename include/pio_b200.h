@@ -1,0 +1,155 @@
+/*
+ * pio_b200.h — C ABI of the B200-native Perceiver IO attention stack (libpio_b200.so).
+ *
+ * The reference (JOBR0/PerceiverIO_Pytorch) has no FFI layer: its operator interface for this path is the
+ * nn.Module surface of perceiver_io/transformer_primitives.py (Attention :18-180, MLP :183-216,
+ * SelfAttention :219-297, CrossAttention :300-406) driven by PerceiverEncoder / PerceiverDecoder
+ * (perceiver_io/perceiver.py:98-107, :166-180).  Each entry point below names the reference lines whose
+ * arithmetic it replaces.  The Python host mirror (perceiverio_pytorch_b200/primitives.py, perceiver.py) keeps
+ * the reference's class names, constructor kwargs and state_dict layout and lowers every forward to these calls.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch); the library never allocates, frees or
+ *    retains them.  `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync, so
+ *    every call is CUDA-graph capturable.
+ *  - bf16 matrices are row-major with a leading dimension (in elements) that is a multiple of 8 (16 bytes, the
+ *    TMA global-stride rule) and a 16-byte aligned base.  Logical widths may be odd (261, 322, 1026): TMA
+ *    zero-fills out-of-bounds columns, so no padding content is ever read.
+ *  - Return value: 0 on success, negative pio_status otherwise; pio_last_error() gives a thread-local message.
+ *    Nothing throws, aborts or falls back to a CPU path.
+ */
+#ifndef PIO_B200_H_
+#define PIO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIO_ABI_VERSION 1
+
+typedef enum pio_status {
+  PIO_OK = 0,
+  PIO_ERR_INVALID_ARGUMENT = -1, /* bad shape / alignment / null pointer */
+  PIO_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels implement */
+  PIO_ERR_CUDA = -3,             /* CUDA runtime / driver / launch error */
+  PIO_ERR_ARCH = -4              /* device is not sm_100 */
+} pio_status;
+
+int pio_abi_version(void);
+const char* pio_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), PIO_ERR_ARCH otherwise. */
+int pio_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm + cast: y_bf16[r, 0:C] = (x[r] - mean) * rsqrt(var + eps) * gamma + beta, columns C..ldy-1 := 0.
+ * Replaces nn.LayerNorm at transformer_primitives.py:281 (layer_norm1), :292 / :401 (layer_norm2),
+ * :379-380 (layer_norm_kv, layer_norm_q).  gamma/beta may be NULL (plain normalisation); if `normalize` is 0
+ * the kernel only casts (used for fp32 activations that feed a GEMM without a LayerNorm).
+ * HBM-bound: 4*C bytes read + 2*ldy bytes written per row.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_layernorm_args {
+  const float* x;   /* [rows, C], row stride ldx (elements) */
+  int64_t ldx;
+  void* y;          /* bf16 [rows, ldy] */
+  int64_t ldy;
+  const float* gamma;
+  const float* beta;
+  int64_t rows;
+  int32_t C;
+  int32_t normalize;
+  float eps;
+} pio_layernorm_args;
+int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Batched GEMM with fused epilogue on tcgen05 tensor cores (TMA-staged operands, TMEM accumulators):
+ *   acc[z] = A[z] (M x K, bf16, K contiguous)  x  B[z]
+ *      B[z] is N x K with K contiguous (b_mn_major = 0: an nn.Linear weight [out, in] or K^T of attention), or
+ *      B[z] is K x N with N contiguous (b_mn_major = 1: the V operand of P.V)
+ *   v = alpha * acc + bias (per column: bias_mode 1, per row: bias_mode 2)
+ *   v = gelu_erf(v) if act == 1
+ *   v += residual[z][m, n]  (fp32)
+ *   out_f32[z][m, n] = v and/or out_bf16[z][m, n] = bf16(v)
+ * Replaces nn.Linear at transformer_primitives.py:93-95 (proj_q/k/v), :110 (final), :212-216 (fc1 + GELU, fc2),
+ * the residual adds at :287,:292,:397,:401, perceiver.py:179 (final_layer), and — for head sizes the streaming
+ * kernel does not cover — the two matmuls of Attention.attend (:138, :163).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_gemm_args {
+  const void* A; int64_t lda; int64_t strideA;
+  const void* B; int64_t ldb; int64_t strideB;
+  int32_t b_mn_major;
+  int32_t M, N, K, batch;
+  const float* bias; int32_t bias_mode;
+  int32_t act;
+  float alpha;
+  const float* residual; int64_t ldr; int64_t strideR;
+  float* out_f32; int64_t ldo32; int64_t strideO32;
+  void* out_bf16; int64_t ldo16; int64_t strideO16;
+  /* debug / tuning: 0 = default */
+  int32_t tile_n;       /* 64, 128, 256 or 0 = auto */
+  int32_t max_ctas;     /* 0 = number of SMs */
+} pio_gemm_args;
+int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Row softmax for the materialised attention path: P[b, i, :] = softmax(scale * S[b, i, :]) with masked keys
+ * excluded; rows with row_keep[b, i] == 0 are written as zeros.
+ * Replaces transformer_primitives.py:146-158 and the wipe at :168-175.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_softmax_args {
+  const float* S; int64_t lds; int64_t strideS;   /* [batch, rows, cols] */
+  void* P; int64_t ldp; int64_t strideP;          /* bf16 [batch, rows, ldp]; columns cols..ldp-1 := 0 */
+  const uint8_t* key_mask; int64_t stride_km;     /* [batch, cols] 1 = attend, or NULL */
+  const uint8_t* row_keep; int64_t stride_rk;     /* [batch, rows] 1 = keep, or NULL */
+  int32_t batch, rows, cols;
+  float scale;
+} pio_softmax_args;
+int pio_softmax_bf16(const pio_softmax_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Streaming (flash-style) attention on tcgen05: per (batch, head, 128-query tile[, key split]) the kernel
+ * streams key/value tiles with TMA, keeps S and O in TMEM, and applies an online softmax.
+ *   Q [B, Nq, H*dqk], K [B, Nk, H*dqk], V [B, Nk, H*dv]  (bf16, heads contiguous inside a row)
+ * Output, num_splits == 1:  O_bf16 [B, Nq, H*dv] normalised (rows with row_keep == 0 zeroed).
+ * Output, num_splits  > 1 or partial != 0: un-normalised fp32 partial O [splits, B, H, Nq, dv] plus running
+ *   max m and sum l [splits, B, H, Nq] (base-e logits), to be merged by pio_attention_combine — the same
+ *   contract the multi-GPU key-axis shard uses.
+ * Replaces Attention.attend, transformer_primitives.py:117-180, without materialising [B,H,Nq,Nk].
+ * Q may have batch stride 0 (the encoder's latent queries are a stride-0 broadcast, position_encoding.py:120).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_attention_args {
+  const void* Q; int64_t ldq; int64_t strideQ;
+  const void* K; int64_t ldk; int64_t strideK;
+  const void* V; int64_t ldv; int64_t strideV;
+  int32_t B, H, Nq, Nk, dqk, dv;
+  float scale;                                   /* 1/sqrt(dqk) */
+  const uint8_t* key_mask; int64_t stride_km;    /* [B, Nk] or NULL */
+  const uint8_t* row_keep; int64_t stride_rk;    /* [B, Nq] or NULL */
+  void* O; int64_t ldo; int64_t strideO;         /* bf16 [B, Nq, ldo] */
+  int32_t num_splits;                            /* key-axis splits inside this GPU (>= 1) */
+  int32_t partial;                               /* 1: always emit (O, m, l) partials */
+  float* O_part; float* m_part; float* l_part;
+} pio_attention_args;
+int pio_attention_fwd(const pio_attention_args* a, void* stream);
+/* 0 if pio_attention_fwd supports these head sizes, PIO_ERR_UNSUPPORTED otherwise (host picks the GEMM path). */
+int pio_attention_supported(int32_t dqk, int32_t dv);
+
+/* Merge `parts` partial results (from key splits and/or gathered from other ranks):
+ *   O[b, i, h*dv + :] = sum_p O_p * exp(m_p - M) / sum_p l_p * exp(m_p - M),  M = max_p m_p. */
+typedef struct pio_combine_args {
+  const float* O_part; const float* m_part; const float* l_part;   /* [parts, B, H, Nq, dv] / [parts, B, H, Nq] */
+  int32_t parts, B, H, Nq, dv;
+  const uint8_t* row_keep; int64_t stride_rk;
+  void* O; int64_t ldo; int64_t strideO;                          /* bf16 [B, Nq, ldo] */
+} pio_combine_args;
+int pio_attention_combine(const pio_combine_args* a, void* stream);
+
+/* Number of kernels launched by this library in the calling process (bench.py's gpu_launches). */
+int64_t pio_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIO_B200_H_ */

@@ -1,0 +1,115 @@
+"""ctypes binding of libpio_b200.so (the C ABI declared in include/pio_b200.h).
+
+The product path never falls back: if the library is missing it is built with nvcc (build.py); if that fails,
+or a call returns a non-zero status, a RuntimeError carrying pio_last_error() is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpio_b200.so")
+
+EXPORTED_SYMBOLS = (
+    "pio_abi_version", "pio_last_error", "pio_check_device", "pio_launch_count",
+    "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
+    "pio_attention_fwd", "pio_attention_supported", "pio_attention_combine",
+)
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
+                ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", vp), ("lda", i64), ("strideA", i64),
+                ("B", vp), ("ldb", i64), ("strideB", i64),
+                ("b_mn_major", i32),
+                ("M", i32), ("N", i32), ("K", i32), ("batch", i32),
+                ("bias", vp), ("bias_mode", i32),
+                ("act", i32),
+                ("alpha", f32),
+                ("residual", vp), ("ldr", i64), ("strideR", i64),
+                ("out_f32", vp), ("ldo32", i64), ("strideO32", i64),
+                ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
+                ("tile_n", i32), ("max_ctas", i32)]
+
+
+class SoftmaxArgs(C.Structure):
+    _fields_ = [("S", vp), ("lds", i64), ("strideS", i64),
+                ("P", vp), ("ldp", i64), ("strideP", i64),
+                ("key_mask", vp), ("stride_km", i64),
+                ("row_keep", vp), ("stride_rk", i64),
+                ("batch", i32), ("rows", i32), ("cols", i32),
+                ("scale", f32)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("Q", vp), ("ldq", i64), ("strideQ", i64),
+                ("K", vp), ("ldk", i64), ("strideK", i64),
+                ("V", vp), ("ldv", i64), ("strideV", i64),
+                ("B", i32), ("H", i32), ("Nq", i32), ("Nk", i32), ("dqk", i32), ("dv", i32),
+                ("scale", f32),
+                ("key_mask", vp), ("stride_km", i64),
+                ("row_keep", vp), ("stride_rk", i64),
+                ("O", vp), ("ldo", i64), ("strideO", i64),
+                ("num_splits", i32), ("partial", i32),
+                ("O_part", vp), ("m_part", vp), ("l_part", vp)]
+
+
+class CombineArgs(C.Structure):
+    _fields_ = [("O_part", vp), ("m_part", vp), ("l_part", vp),
+                ("parts", i32), ("B", i32), ("H", i32), ("Nq", i32), ("dv", i32),
+                ("row_keep", vp), ("stride_rk", i64),
+                ("O", vp), ("ldo", i64), ("strideO", i64)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{LIB_PATH} is missing; run `python -m perceiverio_pytorch_b200.build`")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(LIB_PATH)
+        lib.pio_abi_version.restype = C.c_int
+        lib.pio_last_error.restype = C.c_char_p
+        lib.pio_check_device.restype = C.c_int
+        lib.pio_launch_count.restype = C.c_int64
+        for name, argt in (("pio_layernorm_bf16", LayerNormArgs), ("pio_gemm_bf16", GemmArgs),
+                           ("pio_softmax_bf16", SoftmaxArgs), ("pio_attention_fwd", AttentionArgs),
+                           ("pio_attention_combine", CombineArgs)):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(argt), C.c_void_p]
+        lib.pio_attention_supported.restype = C.c_int
+        lib.pio_attention_supported.argtypes = [C.c_int32, C.c_int32]
+        if lib.pio_abi_version() != 1:
+            raise RuntimeError("libpio_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().pio_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().pio_launch_count())

@@ -1,0 +1,97 @@
+// Host plumbing: last-error storage, device info cache, TMA tensor-map encoding, ABI bookkeeping.
+#include "pio_host.h"
+
+#include <string.h>
+
+namespace pio {
+
+thread_local char g_last_error[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+int get_device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  static bool have[64] = {false};
+  int dev = 0;
+  PIO_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(PIO_ERR_CUDA, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[dev]) {
+    DeviceInfo d;
+    d.device = dev;
+    PIO_CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    PIO_CUDA_OK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    PIO_CUDA_OK(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    PIO_CUDA_OK(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache[dev] = d;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return PIO_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(PIO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(PIO_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu] strides [%llu,%llu] box [%u,%u,%u] "
+                "base %p",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0),
+                (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], rank > 1 ? box[1] : 0,
+                rank > 2 ? box[2] : 0, base);
+  }
+  return PIO_OK;
+}
+
+}  // namespace pio
+
+extern "C" {
+
+int pio_abi_version(void) { return PIO_ABI_VERSION; }
+const char* pio_last_error(void) { return pio::g_last_error; }
+int64_t pio_launch_count(void) { return pio::g_launch_count.load(); }
+
+int pio_check_device(void) {
+  pio::DeviceInfo d;
+  int rc = pio::get_device_info(&d);
+  if (rc != PIO_OK) return rc;
+  if (d.cc_major != 10)
+    return pio::fail(PIO_ERR_ARCH, "device %d is sm_%d%d; this library contains sm_100a code only", d.device,
+                     d.cc_major, d.cc_minor);
+  return PIO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Host-side plumbing shared by the C-ABI entry points: error reporting, driver entry points, TMA tensor maps.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/pio_b200.h"
+
+namespace pio {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<int64_t> g_launch_count;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PIO_CUDA_OK(expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return ::pio::fail(PIO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                                    \
+  } while (0)
+
+#define PIO_REQUIRE(cond, ...)                                          \
+  do {                                                                  \
+    if (!(cond)) return ::pio::fail(PIO_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0;
+  int cc_minor = 0;
+  int max_smem_optin = 0;
+};
+// Cached properties of the current device (one lookup per device per process).
+int get_device_info(DeviceInfo* out);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda, so the
+// library loads in the GPU-less build container for the symbol-export test).
+// Encodes a bf16 tensor of rank `rank` (dims[0] innermost) with SWIZZLE_128B and zero OOB fill.
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes /* rank-1 entries, for dims[1..] */, const uint32_t* box);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace pio

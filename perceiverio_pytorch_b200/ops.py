@@ -1,0 +1,155 @@
+"""Tensor-level wrappers over the C ABI (include/pio_b200.h).  PyTorch is used for device memory and streams only;
+all arithmetic on the hot path happens inside libpio_b200.so.  Every function raises if the tensors are not on a
+CUDA device — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("perceiverio_pytorch_b200: tensors must live on a CUDA (sm_100) device; "
+                               "there is no CPU path")
+
+
+def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
+                   normalize: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [rows, pad8(C)]."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    c = x.shape[-1]
+    x2 = x.reshape(-1, c) if x.dim() != 2 else x
+    rows = x2.shape[0]
+    ldy = pad8(c)
+    if out is None:
+        out = torch.empty((rows, ldy), dtype=BF16, device=x.device)
+    assert out.dtype == BF16 and out.shape[-1] == ldy and out.is_contiguous()
+    a = _lib.LayerNormArgs(_ptr(x2), x2.stride(0), _ptr(out), ldy, _ptr(gamma), _ptr(beta), rows, c,
+                           1 if normalize else 0, eps)
+    _lib.check(_lib.load().pio_layernorm_bf16(C.byref(a), _stream()), "pio_layernorm_bf16")
+    return out
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int = 1, b_mn_major: bool = False,
+         strideA: int = 0, strideB: int = 0, lda: Optional[int] = None, ldb: Optional[int] = None,
+         bias: Optional[torch.Tensor] = None, bias_mode: int = 1, act: int = 0, alpha: float = 1.0,
+         residual: Optional[torch.Tensor] = None, ldr: int = 0, strideR: int = 0,
+         out_f32: Optional[torch.Tensor] = None, ldo32: int = 0, strideO32: int = 0,
+         out_bf16: Optional[torch.Tensor] = None, ldo16: int = 0, strideO16: int = 0,
+         tile_n: int = 0, max_ctas: int = 0) -> None:
+    """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
+    _need_cuda(A, B, bias, residual, out_f32, out_bf16)
+    assert A.dtype == BF16 and B.dtype == BF16
+    lda = A.stride(-2) if lda is None else lda
+    ldb = B.stride(-2) if ldb is None else ldb
+    a = _lib.GemmArgs(_ptr(A), lda, strideA, _ptr(B), ldb, strideB, 1 if b_mn_major else 0,
+                      M, N, K, batch, _ptr(bias), bias_mode if bias is not None else 0, act, alpha,
+                      _ptr(residual), ldr, strideR, _ptr(out_f32), ldo32, strideO32,
+                      _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas)
+    _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
+
+
+def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torch.Tensor] = None, *,
+           act: int = 0, alpha: float = 1.0, residual: Optional[torch.Tensor] = None,
+           want_f32: bool = False, want_bf16: bool = True, bias_mode: int = 1):
+    """y = act(alpha * x @ w^T + bias) (+ residual).  x bf16 [M, ldx], w bf16 [N, ldw] (nn.Linear layout).
+    Returns (y_f32 [M, N] or None, y_bf16 [M, pad8(N)] or None)."""
+    m = x.shape[0]
+    y32 = torch.empty((m, N), dtype=torch.float32, device=x.device) if want_f32 else None
+    y16 = torch.empty((m, pad8(N)), dtype=BF16, device=x.device) if want_bf16 else None
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(-1) == 1
+    gemm(x, w, M=m, N=N, K=K, bias=bias, bias_mode=bias_mode, act=act, alpha=alpha,
+         residual=residual, ldr=residual.stride(0) if residual is not None else 0,
+         out_f32=y32, ldo32=N, out_bf16=y16, ldo16=pad8(N))
+    return y32, y16
+
+
+def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[torch.Tensor] = None,
+                 row_keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)]."""
+    _need_cuda(S, key_mask, row_keep)
+    b, rows, lds = S.shape
+    ldp = pad8(cols)
+    P = torch.empty((b, rows, ldp), dtype=BF16, device=S.device)
+    a = _lib.SoftmaxArgs(_ptr(S), lds, S.stride(0), _ptr(P), ldp, P.stride(0),
+                         _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
+                         _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
+                         b, rows, cols, scale)
+    _lib.check(_lib.load().pio_softmax_bf16(C.byref(a), _stream()), "pio_softmax_bf16")
+    return P
+
+
+def attention_supported(dqk: int, dv: int) -> bool:
+    return _lib.load().pio_attention_supported(dqk, dv) == 0
+
+
+def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, H: int, Nq: int, Nk: int,
+                  dqk: int, dv: int, strideQ: int, strideK: int, strideV: int,
+                  ldq: int, ldk: int, ldv: int, scale: Optional[float] = None,
+                  key_mask: Optional[torch.Tensor] = None, row_keep: Optional[torch.Tensor] = None,
+                  num_splits: int = 1, partial: bool = False, out: Optional[torch.Tensor] = None):
+    """Streaming attention.  Returns O bf16 [B, Nq, pad8(H*dv)] or, if partial, (O_part, m_part, l_part)."""
+    _need_cuda(Q, K, V, key_mask, row_keep)
+    scale = 1.0 / math.sqrt(dqk) if scale is None else scale
+    dev = Q.device
+    ldo = pad8(H * dv)
+    emit_partial = partial or num_splits > 1
+    O = out
+    if O is None and not partial:
+        O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+    Op = mp = lp = None
+    if emit_partial:
+        Op = torch.empty((num_splits, B, H, Nq, dv), dtype=torch.float32, device=dev)
+        mp = torch.empty((num_splits, B, H, Nq), dtype=torch.float32, device=dev)
+        lp = torch.empty((num_splits, B, H, Nq), dtype=torch.float32, device=dev)
+    a = _lib.AttentionArgs(_ptr(Q), ldq, strideQ, _ptr(K), ldk, strideK, _ptr(V), ldv, strideV,
+                           B, H, Nq, Nk, dqk, dv, scale,
+                           _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
+                           _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
+                           _ptr(O), ldo, (O.stride(0) if O is not None else 0),
+                           num_splits, 1 if partial else 0, _ptr(Op), _ptr(mp), _ptr(lp))
+    _lib.check(_lib.load().pio_attention_fwd(C.byref(a), _stream()), "pio_attention_fwd")
+    if partial:
+        return Op, mp, lp
+    if num_splits > 1:
+        attention_combine(Op, mp, lp, row_keep=row_keep, out=O)
+    return O
+
+
+def attention_combine(Op: torch.Tensor, mp: torch.Tensor, lp: torch.Tensor, *,
+                      row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Merge partials [parts, B, H, Nq, dv] -> O bf16 [B, Nq, pad8(H*dv)]."""
+    _need_cuda(Op, mp, lp, row_keep)
+    parts, b, h, nq, dv = Op.shape
+    assert Op.is_contiguous() and mp.is_contiguous() and lp.is_contiguous()
+    ldo = pad8(h * dv)
+    if out is None:
+        out = torch.empty((b, nq, ldo), dtype=BF16, device=Op.device)
+    a = _lib.CombineArgs(_ptr(Op), _ptr(mp), _ptr(lp), parts, b, h, nq, dv,
+                         _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
+                         _ptr(out), ldo, out.stride(0))
+    _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
+    return out
