@@ -135,6 +135,9 @@ typedef struct pio_attention_args {
 int pio_attention_fwd(const pio_attention_args* a, void* stream);
 /* 0 if pio_attention_fwd supports these head sizes, PIO_ERR_UNSUPPORTED otherwise (host picks the GEMM path). */
 int pio_attention_supported(int32_t dqk, int32_t dv);
+/* Key-tile width (64 or 128) the streaming kernel uses for these head sizes, or PIO_ERR_UNSUPPORTED; a key split
+ * must give every split at least one tile. */
+int pio_attention_key_tile(int32_t dqk, int32_t dv, int32_t same_kv);
 
 /* Merge `parts` partial results (from key splits and/or gathered from other ranks):
  *   O[b, i, h*dv + :] = sum_p O_p * exp(m_p - M) / sum_p l_p * exp(m_p - M),  M = max_p m_p. */

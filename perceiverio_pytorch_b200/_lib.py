@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libpio_b200.so")
 EXPORTED_SYMBOLS = (
     "pio_abi_version", "pio_last_error", "pio_check_device", "pio_launch_count",
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
-    "pio_attention_fwd", "pio_attention_supported", "pio_attention_combine",
+    "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -99,6 +99,8 @@ def load(build_if_missing: bool = True):
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
         lib.pio_attention_supported.restype = C.c_int
         lib.pio_attention_supported.argtypes = [C.c_int32, C.c_int32]
+        lib.pio_attention_key_tile.restype = C.c_int
+        lib.pio_attention_key_tile.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         if lib.pio_abi_version() != 1:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib

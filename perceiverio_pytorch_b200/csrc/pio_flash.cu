@@ -1,6 +1,503 @@
-// placeholder, replaced below
+// Streaming (flash-style) attention for sm_100a.
+//
+// One CTA = one 128-query tile of one (batch, head) [and one key split].  K/V tiles stream through a TMA ring
+// (SWIZZLE_128B, 64-column chunks); S = Q.K^T is accumulated by tcgen05.mma into a double-buffered TMEM tile, the
+// softmax warps read it with tcgen05.ld, keep running max / sum in registers (fp32, log2 domain), write P as bf16 into
+// a swizzled smem tile, and O += P.V is accumulated in TMEM by a second tcgen05.mma whose B operand is the V tile read
+// MN-major — so when K and V are the same array (the folded single-head cross-attends) one TMA load
+// feeds both products.  O is rescaled lazily (only when the running max grows by more than 2^8).
+//
+// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
+// warps 4..7 softmax / correction / epilogue (thread = one query row = one TMEM lane).
+#include <math.h>
+
+#include "pio_common.cuh"
 #include "pio_host.h"
-extern "C" int pio_attention_supported(int32_t dqk, int32_t dv) { return PIO_ERR_UNSUPPORTED; }
-extern "C" int pio_attention_fwd(const pio_attention_args* a, void* stream) {
-  return pio::fail(PIO_ERR_UNSUPPORTED, "pio_attention_fwd: not built yet");
+
+namespace pio {
+
+struct FlashParams {
+  int B, H, Nq, Nk, dqk, dv;
+  int q_bcast;            // Q has a single batch entry shared by every b
+  float scale_log2;       // scale * log2(e)
+  const uint8_t* key_mask; long long stride_km;
+  const uint8_t* row_keep; long long stride_rk;
+  __nv_bfloat16* O; long long ldo, strideO;
+  int num_splits, tiles_per_split, partial;
+  float* O_part; float* m_part; float* l_part;
+};
+
+template <int NQC, int NVC, bool SAME>
+struct FlashCfg {
+  static constexpr int KV_CHUNKS = SAME ? NQC : (NQC + NVC);
+  // smem with BN = 128 and two stages
+  static constexpr int SMEM128 = NQC * 16384 + 2 * KV_CHUNKS * 16384 + 2 * 16384;
+  static constexpr int TMEM128 = 2 * 128 + NVC * 64;
+  static constexpr int BN = (SMEM128 <= 220 * 1024 && TMEM128 <= 512) ? 128 : 64;
+  static constexpr int CHUNK_BYTES = BN * 128;            // one 64-column chunk of a K/V tile
+  static constexpr int STAGE_BYTES = KV_CHUNKS * CHUNK_BYTES;
+  static constexpr int Q_BYTES = NQC * 16384;
+  static constexpr int P_BYTES = (BN / 64) * 16384;
+  static constexpr int AVAIL = 224 * 1024 - Q_BYTES - P_BYTES;
+  static constexpr int STAGES_RAW = AVAIL / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static constexpr int TMEM_NEED = 2 * BN + NVC * 64;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int SMEM_USED = Q_BYTES + P_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  // request > half of the SM's shared memory so that exactly one CTA is resident per SM (TMEM is not oversubscribed)
+  static constexpr int SMEM_BYTES = SMEM_USED < 120 * 1024 ? 120 * 1024 : SMEM_USED;
+  static constexpr bool VALID = STAGES >= 2 && TMEM_NEED <= 512;
+};
+
+template <int NQC, int NVC, bool SAME>
+__global__ void __launch_bounds__(256, 1)
+pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
+  using Cfg = FlashCfg<NQC, NVC, SAME>;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + Cfg::Q_BYTES;
+  uint8_t* sKV = sP + Cfg::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* q_full = bars;                         // [1]
+  uint64_t* kv_full = bars + 1;                    // [STAGES]
+  uint64_t* kv_empty = kv_full + Cfg::STAGES;      // [STAGES]
+  uint64_t* s_full = kv_empty + Cfg::STAGES;       // [2]
+  uint64_t* p_full = s_full + 2;                   // [1] softmax -> MMA (128 arrivals)
+  uint64_t* pv_done = p_full + 1;                  // [1] MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int b = blockIdx.y / p.H;
+  const int h = blockIdx.y % p.H;
+  const int split = blockIdx.z;
+  const int total_tiles = (p.Nk + BN - 1) / BN;
+  const int tile_begin = split * p.tiles_per_split;
+  const int tile_end = min(total_tiles, tile_begin + p.tiles_per_split);
+  const int ntiles = tile_end - tile_begin;  // host guarantees >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    if (!SAME) tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 2 * BN;
+
+  // number of 16-wide k-steps of the QK^T contraction in chunk c, and N extent of the PV product
+  const int dqk_steps_total = (p.dqk + 15) / 16;
+  const int dv_n = ((p.dv + 15) / 16) * 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      const int bq = p.q_bcast ? 0 : b;
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < NQC; ++c) tma_load_3d(sQ + c * 16384, &tmap_q, q_full, h * p.dqk + c * 64, q0, bq);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int k0 = (tile_begin + j) * BN;
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        uint8_t* st = sKV + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < NQC; ++c)
+          tma_load_3d(st + c * Cfg::CHUNK_BYTES, &tmap_k, &kv_full[stage], h * p.dqk + c * 64, k0, b);
+        if constexpr (!SAME) {
+#pragma unroll
+          for (int c = 0; c < NVC; ++c)
+            tma_load_3d(st + (NQC + c) * Cfg::CHUNK_BYTES, &tmap_v, &kv_full[stage], h * p.dv + c * 64, k0, b);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_s = [&](int j, int stage) {
+        const uint32_t k_addr = smem_u32(sKV + stage * Cfg::STAGE_BYTES);
+        const uint32_t d = tmem_base + (j & 1) * BN;
+        for (int ks = 0; ks < dqk_steps_total; ++ks) {
+          const int c = ks >> 2, kk = ks & 3;
+          const uint64_t da = make_smem_desc_sw128(q_addr + c * 16384 + kk * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(k_addr + c * Cfg::CHUNK_BYTES + kk * 32, 16, 1024);
+          umma_ss(d, da, db, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      auto issue_pv = [&](int j, int stage) {
+        const uint32_t v_addr = smem_u32(sKV + stage * Cfg::STAGE_BYTES) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES);
+        for (int nb = 0; nb * 256 < dv_n; ++nb) {
+          const int n = min(256, dv_n - nb * 256);
+          const uint32_t idesc_pv = make_idesc_f16(128, n, 1, 0, /*B MN-major*/ 1);
+          for (int ks = 0; ks < BN / 16; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(v_addr + nb * 4 * Cfg::CHUNK_BYTES + ks * 2048,
+                                                     Cfg::CHUNK_BYTES, 1024);
+            umma_ss(tmem_o + nb * 256, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+          }
+        }
+      };
+      mbar_wait(q_full, 0);
+      int stage = 0;       // stage of tile j
+      uint32_t phase = 0;
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == Cfg::STAGES) { nstage = 0; nphase ^= 1u; }
+        if (j + 1 < ntiles) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(j + 1, nstage);
+        }
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        issue_pv(j, stage);
+        umma_commit(&kv_empty[stage]);
+        umma_commit(pv_done);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= softmax / correction / epilogue =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const int q = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint8_t* km = p.key_mask ? p.key_mask + (long long)b * p.stride_km : nullptr;
+    float m = -INFINITY;  // running max of scale_log2 * s
+    float l = 0.f;        // running sum of exp2(t - m)
+    for (int j = 0; j < ntiles; ++j) {
+      const int k0 = (tile_begin + j) * BN;
+      const uint32_t t_s = tmem_base + (j & 1) * BN + lane_off;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const bool tail = (k0 + BN > p.Nk) || (km != nullptr);
+      // ---- pass 1: row max ----
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tmem_wait_ld();
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = k0 + c * 32 + i;
+            const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
+            if (ok) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+          }
+        }
+      }
+      tmax *= p.scale_log2;  // scale > 0, so max commutes (an all-masked tile stays -inf)
+      // ---- running max update, lazy rescale ----
+      float m_use = m;
+      const bool grow = tmax > m + 8.0f;  // also true for the first valid tile (m == -inf)
+      float alpha = 1.0f;
+      if (grow) {
+        alpha = (m == -INFINITY) ? 0.0f : exp2f(m - tmax);
+        m_use = tmax;
+      }
+      const bool any_grow = __any_sync(0xffffffffu, grow && j > 0 && m != -INFINITY);
+      if (j > 0) {
+        // P buffer and O are free once PV_{j-1} has completed
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (any_grow) {
+        for (int c = 0; c < dv_n; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_o + lane_off + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st32(tmem_o + lane_off + c, r);
+        }
+        tmem_wait_st();
+      }
+      l *= alpha;
+      m = m_use;
+      const float msub = (m == -INFINITY) ? 0.0f : m;
+      // ---- pass 2: p = exp2(t - m), row sum, bf16 P tile into swizzled smem ----
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tmem_wait_ld();
+        float pv[32];
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -msub));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = k0 + c * 32 + i;
+            const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
+            pv[i] = ok ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -msub)) : 0.0f;
+          }
+        }
+        uint8_t* prow = sP + ((c * 32) >> 6) * 16384;
+        const int chunk0 = ((c * 32) & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(pv[8 * g], pv[8 * g + 1]);
+          w.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+          w.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
+          w.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+          *reinterpret_cast<uint4*>(prow + sw128_offset(row, chunk0 + g)) = w;
+        }
+        // the sum uses the bf16-rounded values that the tensor core will multiply, keeping P/l consistent
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lsum += __bfloat162float(__float2bfloat16_rn(pv[i]));
+      }
+      l += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue ----
+    mbar_wait(pv_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const bool keep = (q < p.Nq) && (p.row_keep == nullptr || p.row_keep[(long long)b * p.stride_rk + q] != 0);
+    const bool emit_partial = p.partial || p.num_splits > 1;
+    if (!emit_partial) {
+      const float inv = (keep && l > 0.f) ? 1.0f / l : 0.0f;
+      __nv_bfloat16* orow = p.O + (long long)b * p.strideO + (long long)q * p.ldo + (long long)h * p.dv;
+      for (int c = 0; c < dv_n; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_o + lane_off + c, r);
+        tmem_wait_ld();
+        if (q < p.Nq) {
+          __nv_bfloat16* op = orow + c;
+          if (c + 32 <= p.dv && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+              reinterpret_cast<uint4*>(op)[g] = w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i < p.dv) op[i] = __float2bfloat16_rn(__uint_as_float(r[i]) * inv);
+          }
+        }
+      }
+    } else {
+      const long long prow = (((long long)split * p.B + b) * p.H + h) * p.Nq + q;
+      if (q < p.Nq) {
+        p.m_part[prow] = (m == -INFINITY) ? -INFINITY : m * 0.69314718055994531f;  // back to natural-log units
+        p.l_part[prow] = l;
+      }
+      float* orow = p.O_part + prow * p.dv;
+      for (int c = 0; c < dv_n; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_o + lane_off + c, r);
+        tmem_wait_ld();
+        if (q < p.Nq) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.dv) orow[c + i] = (l > 0.f) ? __uint_as_float(r[i]) : 0.0f;
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int NQC, int NVC, bool SAME>
+static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream) {
+  using Cfg = FlashCfg<NQC, NVC, SAME>;
+  static_assert(Cfg::VALID, "flash configuration does not fit");
+  constexpr int BN = Cfg::BN;
+  CUtensorMap tq, tk, tv;
+  const int q_bcast = (a->strideQ == 0 && a->B > 1) ? 1 : 0;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->H * a->dqk, (uint64_t)a->Nq, (uint64_t)(q_bcast ? 1 : a->B)};
+    const uint64_t strides[2] = {(uint64_t)a->ldq * 2,
+                                 (uint64_t)((q_bcast || a->B == 1) ? a->ldq * (int64_t)a->Nq : a->strideQ) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = encode_tmap_bf16(&tq, a->Q, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->H * a->dqk, (uint64_t)a->Nk, (uint64_t)a->B};
+    const uint64_t strides[2] = {(uint64_t)a->ldk * 2, (uint64_t)(a->B == 1 ? a->ldk * (int64_t)a->Nk : a->strideK) * 2};
+    const uint32_t box[3] = {64, (uint32_t)BN, 1};
+    int rc = encode_tmap_bf16(&tk, a->K, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->H * a->dv, (uint64_t)a->Nk, (uint64_t)a->B};
+    const uint64_t strides[2] = {(uint64_t)a->ldv * 2, (uint64_t)(a->B == 1 ? a->ldv * (int64_t)a->Nk : a->strideV) * 2};
+    const uint32_t box[3] = {64, (uint32_t)BN, 1};
+    int rc = encode_tmap_bf16(&tv, a->V, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
+  FlashParams p;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.dqk = a->dqk; p.dv = a->dv;
+  p.q_bcast = q_bcast;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.key_mask = a->key_mask; p.stride_km = a->stride_km;
+  p.row_keep = a->row_keep; p.stride_rk = a->stride_rk;
+  p.O = reinterpret_cast<__nv_bfloat16*>(a->O); p.ldo = a->ldo; p.strideO = a->strideO;
+  const int total_tiles = (a->Nk + BN - 1) / BN;
+  int splits = a->num_splits < 1 ? 1 : a->num_splits;
+  if (splits > total_tiles) splits = total_tiles;
+  p.tiles_per_split = (total_tiles + splits - 1) / splits;
+  // the caller sized the partial buffers for a->num_splits; every split must own >= 1 tile
+  if (a->num_splits > 1 && (long long)(a->num_splits - 1) * p.tiles_per_split >= total_tiles)
+    return fail(PIO_ERR_INVALID_ARGUMENT,
+                "pio_attention_fwd: num_splits=%d leaves an empty split (Nk=%d, %d-key tiles: %d); use <= %d splits that "
+                "divide evenly", a->num_splits, a->Nk, BN, total_tiles, total_tiles);
+  p.num_splits = a->num_splits < 1 ? 1 : a->num_splits;
+  p.partial = a->partial;
+  p.O_part = a->O_part; p.m_part = a->m_part; p.l_part = a->l_part;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(pio_flash_kernel<NQC, NVC, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(flash<%d,%d,%d>) failed: %s", NQC, NVC, (int)SAME,
+                cudaGetErrorString(attr_err));
+  dim3 grid((a->Nq + 127) / 128, a->B * a->H, p.num_splits);
+  pio_flash_kernel<NQC, NVC, SAME><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
+}
+
+static bool flash_shape_ok(int dqk, int dv, bool same) {
+  const int nqc = (dqk + 63) / 64, nvc = (dv + 63) / 64;
+  if (same) return nqc >= 1 && nqc <= 6 && dqk == dv;
+  return nqc >= 1 && nqc <= 2 && nvc >= 1 && nvc <= 3;
+}
+
+}  // namespace pio
+
+extern "C" int pio_attention_supported(int32_t dqk, int32_t dv) {
+  return (pio::flash_shape_ok(dqk, dv, false) || pio::flash_shape_ok(dqk, dv, true)) ? PIO_OK : PIO_ERR_UNSUPPORTED;
+}
+
+// Tile width in keys the kernel uses for these head sizes (hosts use it to pick an even key split).
+extern "C" int pio_attention_key_tile(int32_t dqk, int32_t dv, int32_t same_kv) {
+  using namespace pio;
+  const int nqc = (dqk + 63) / 64, nvc = (dv + 63) / 64;
+  if (same_kv && flash_shape_ok(dqk, dv, true)) {
+    switch (nqc) {
+      case 1: return FlashCfg<1, 1, true>::BN;
+      case 2: return FlashCfg<2, 2, true>::BN;
+      case 3: return FlashCfg<3, 3, true>::BN;
+      case 4: return FlashCfg<4, 4, true>::BN;
+      case 5: return FlashCfg<5, 5, true>::BN;
+      case 6: return FlashCfg<6, 6, true>::BN;
+    }
+  }
+  if (flash_shape_ok(dqk, dv, false)) {
+    switch (nqc * 10 + nvc) {
+      case 11: return FlashCfg<1, 1, false>::BN;
+      case 12: return FlashCfg<1, 2, false>::BN;
+      case 13: return FlashCfg<1, 3, false>::BN;
+      case 21: return FlashCfg<2, 1, false>::BN;
+      case 22: return FlashCfg<2, 2, false>::BN;
+      case 23: return FlashCfg<2, 3, false>::BN;
+    }
+  }
+  return PIO_ERR_UNSUPPORTED;
+}
+
+extern "C" int pio_attention_fwd(const pio_attention_args* a, void* stream_) {
+  using namespace pio;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PIO_REQUIRE(a != nullptr, "pio_attention_fwd: null args");
+  PIO_REQUIRE(a->Q && a->K && a->V, "pio_attention_fwd: null operand");
+  PIO_REQUIRE(a->B > 0 && a->H > 0 && a->Nq > 0 && a->Nk > 0 && a->dqk > 0 && a->dv > 0, "pio_attention_fwd: bad shape");
+  PIO_REQUIRE(aligned16(a->Q) && aligned16(a->K) && aligned16(a->V), "pio_attention_fwd: operand base not 16-byte aligned");
+  PIO_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0, "pio_attention_fwd: leading dims must be multiples of 8");
+  PIO_REQUIRE(a->strideQ % 8 == 0 && a->strideK % 8 == 0 && a->strideV % 8 == 0,
+              "pio_attention_fwd: batch strides must be multiples of 8");
+  PIO_REQUIRE(a->H == 1 || (a->dqk % 16 == 0),
+              "pio_attention_fwd: multi-head needs dqk %% 16 == 0 (got %d); re-lay the heads out first", a->dqk);
+  const bool emit_partial = a->partial || a->num_splits > 1;
+  PIO_REQUIRE(emit_partial ? (a->O_part && a->m_part && a->l_part) : (a->O != nullptr),
+              "pio_attention_fwd: missing output buffer");
+  PIO_REQUIRE((long long)a->B * a->H < 65536 && a->num_splits < 65536, "pio_attention_fwd: grid too large");
+  DeviceInfo dev;
+  int rc = get_device_info(&dev);
+  if (rc != PIO_OK) return rc;
+  if (dev.cc_major != 10) return fail(PIO_ERR_ARCH, "pio_attention_fwd needs sm_100 (got sm_%d%d)", dev.cc_major, dev.cc_minor);
+  const bool same = (a->K == a->V) && (a->ldk == a->ldv) && (a->dqk == a->dv) && (a->strideK == a->strideV);
+  const int nqc = (a->dqk + 63) / 64, nvc = (a->dv + 63) / 64;
+  if (same && flash_shape_ok(a->dqk, a->dv, true)) {
+    switch (nqc) {
+      case 1: return launch_flash<1, 1, true>(a, dev, stream);
+      case 2: return launch_flash<2, 2, true>(a, dev, stream);
+      case 3: return launch_flash<3, 3, true>(a, dev, stream);
+      case 4: return launch_flash<4, 4, true>(a, dev, stream);
+      case 5: return launch_flash<5, 5, true>(a, dev, stream);
+      case 6: return launch_flash<6, 6, true>(a, dev, stream);
+    }
+  }
+  if (flash_shape_ok(a->dqk, a->dv, false)) {
+    switch (nqc * 10 + nvc) {
+      case 11: return launch_flash<1, 1, false>(a, dev, stream);
+      case 12: return launch_flash<1, 2, false>(a, dev, stream);
+      case 13: return launch_flash<1, 3, false>(a, dev, stream);
+      case 21: return launch_flash<2, 1, false>(a, dev, stream);
+      case 22: return launch_flash<2, 2, false>(a, dev, stream);
+      case 23: return launch_flash<2, 3, false>(a, dev, stream);
+    }
+  }
+  return fail(PIO_ERR_UNSUPPORTED, "pio_attention_fwd: head sizes dqk=%d dv=%d (same_kv=%d) not covered by the streaming kernel",
+              a->dqk, a->dv, (int)same);
 }

@@ -12,6 +12,7 @@ namespace pio {
 struct GemmEpilogue {
   int M, N, K, batch;
   int tiles_m, tiles_n;
+  int a_bcast, b_bcast;  // operand shared by every batch entry (batch stride 0)
   const float* bias;
   int bias_mode;
   int act;
@@ -97,13 +98,13 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * Cfg::BK, m0, z);
+          tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * Cfg::BK, m0, ep.a_bcast ? 0 : z);
           if constexpr (!B_MN) {
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * Cfg::BK, n0, z);
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * Cfg::BK, n0, ep.b_bcast ? 0 : z);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * (64 * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kc * Cfg::BK, z);
+              tma_load_3d(sb + j * (64 * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kc * Cfg::BK, ep.b_bcast ? 0 : z);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -179,6 +180,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + col0 + j);
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < ep.N) v[j] += __ldg(ep.bias + col0 + j);
           }
@@ -196,6 +198,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < ep.N) v[j] += __ldg(rp + j);
           }
@@ -207,6 +210,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int j = 0; j < 8; ++j)
               reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < ep.N) op[j] = v[j];
           }
@@ -224,6 +228,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               reinterpret_cast<uint4*>(op)[j] = q;
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < ep.N) op[j] = __float2bfloat16_rn(v[j]);
           }
@@ -248,28 +253,32 @@ template <int BN, bool B_MN>
 static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
+  const bool a_bcast = a->batch > 1 && a->strideA == 0;
+  const bool b_bcast = a->batch > 1 && a->strideB == 0;
+  const uint64_t a_batch = a_bcast ? 1 : a->batch, b_batch = b_bcast ? 1 : a->batch;
   {
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a->batch > 1 ? a->strideA : a->lda * (int64_t)a->M) * 2};
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, a_batch};
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a_batch > 1 ? a->strideA : a->lda * (int64_t)a->M) * 2};
     const uint32_t box[3] = {64, 128, 1};
     int rc = encode_tmap_bf16(&ta, a->A, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   }
   if (!B_MN) {
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(a->batch > 1 ? a->strideB : a->ldb * (int64_t)a->N) * 2};
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, b_batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(b_batch > 1 ? a->strideB : a->ldb * (int64_t)a->N) * 2};
     const uint32_t box[3] = {64, (uint32_t)BN, 1};
     int rc = encode_tmap_bf16(&tb, a->B, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   } else {
-    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(a->batch > 1 ? a->strideB : a->ldb * (int64_t)a->K) * 2};
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->K, b_batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(b_batch > 1 ? a->strideB : a->ldb * (int64_t)a->K) * 2};
     const uint32_t box[3] = {64, 64, 1};
     int rc = encode_tmap_bf16(&tb, a->B, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   }
   GemmEpilogue ep;
   ep.M = a->M; ep.N = a->N; ep.K = a->K; ep.batch = a->batch;
+  ep.a_bcast = a_bcast ? 1 : 0; ep.b_bcast = b_bcast ? 1 : 0;
   ep.tiles_m = (a->M + 127) / 128;
   ep.tiles_n = (a->N + BN - 1) / BN;
   ep.bias = a->bias; ep.bias_mode = a->bias ? a->bias_mode : 0;
