@@ -7,6 +7,7 @@ can be committed; they travel to the GPU box, the reference does not.
 """
 from __future__ import annotations
 
+import json
 import os
 import sys
 
@@ -21,7 +22,16 @@ from oracle import ref_shim  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def _build(cls, **kwargs):
+    """Construct a reference module and remember the constructor kwargs (stored in the fixture so the
+    B200 drop-in can be built with the very same call)."""
+    m = cls(**kwargs).eval()
+    m._ctor = dict(cls=cls.__name__, kwargs=kwargs)
+    return m
+
+
 def _save(name, module, meta, inputs, output):
+    meta = dict(meta, ctor=json.dumps(module._ctor))
     arrays = {f"param::{k}": v.detach().numpy() for k, v in module.state_dict().items()}
     arrays.update({f"input::{k}": (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
                    for k, v in inputs.items()})
@@ -40,14 +50,14 @@ def main():
     torch.manual_seed(0)
     with torch.inference_mode():
         # 1. single-head cross-attend with an odd channel count (the cls/flow encoder pattern)
-        m = ref_shim.perturb_parameters(P.CrossAttention(q_in_channels=64, kv_in_channels=37, num_heads=1).eval(), 1)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=64, kv_in_channels=37, num_heads=1), 1)
         q, kv = torch.randn(2, 48, 64), torch.randn(2, 300, 37)
         _save("xattn_h1_odd", m, dict(kind="cross", num_heads=1, use_query_residual=1),
               dict(q=q, kv=kv), m(q, kv))
 
         # 2. multi-head masked cross-attend, distinct qk / v widths (the language encoder pattern)
-        m = ref_shim.perturb_parameters(P.CrossAttention(q_in_channels=64, kv_in_channels=40, num_heads=4,
-                                                         qk_channels=32, v_channels=80).eval(), 2)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=64, kv_in_channels=40, num_heads=4,
+                                                         qk_channels=32, v_channels=80), 2)
         q, kv = torch.randn(2, 24, 64), torch.randn(2, 200, 40)
         kmask = torch.ones(2, 200, dtype=torch.bool)
         kmask[0, 150:] = False
@@ -58,9 +68,9 @@ def main():
 
         # 3. query-masked cross-attend without query residual (the language decoder pattern);
         #    sample 1 has every query masked -> rows become final.bias + MLP of it
-        m = ref_shim.perturb_parameters(P.CrossAttention(q_in_channels=48, kv_in_channels=64, num_heads=4,
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=48, kv_in_channels=64, num_heads=4,
                                                          qk_channels=32, v_channels=48,
-                                                         use_query_residual=False).eval(), 3)
+                                                         use_query_residual=False), 3)
         q, kv = torch.randn(2, 130, 48), torch.randn(2, 20, 64)
         qmask = torch.ones(2, 130, dtype=torch.bool)
         qmask[0, 100:] = False
@@ -70,22 +80,22 @@ def main():
               dict(q=q, kv=kv, query_mask=qmask), m(q, kv, attention_mask=mask))
 
         # 4. self-attention block, 8 heads, qk != v (language tower pattern)
-        m = ref_shim.perturb_parameters(P.SelfAttention(in_channels=64, widening_factor=1, num_heads=8,
-                                                        qk_channels=32, v_channels=64).eval(), 4)
+        m = ref_shim.perturb_parameters(_build(P.SelfAttention, in_channels=64, widening_factor=1, num_heads=8,
+                                                        qk_channels=32, v_channels=64), 4)
         x = torch.randn(2, 40, 64)
         _save("selfattn_h8", m, dict(kind="self", num_heads=8), dict(x=x), m(x))
 
         # 5. peaky softmax: query projection scaled x16 so the running max moves
-        m = ref_shim.perturb_parameters(P.CrossAttention(q_in_channels=32, kv_in_channels=24, num_heads=1).eval(), 5)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=32, kv_in_channels=24, num_heads=1), 5)
         m.attention.proj_q.weight.mul_(16.0)
         q, kv = torch.randn(1, 16, 32), 2.0 * torch.randn(1, 700, 24)
         _save("xattn_peaky", m, dict(kind="cross", num_heads=1, use_query_residual=1),
               dict(q=q, kv=kv), m(q, kv))
 
         # 6. whole encoder: masked input, 2 blocks x 2 shared self-attends
-        enc = ref_shim.perturb_parameters(R.PerceiverEncoder(num_input_channels=37, num_self_attends_per_block=2,
+        enc = ref_shim.perturb_parameters(_build(R.PerceiverEncoder, num_input_channels=37, num_self_attends_per_block=2,
                                                              num_blocks=2, num_latents=40, num_latent_channels=64,
-                                                             num_cross_attend_heads=1, num_self_attend_heads=4).eval(), 6)
+                                                             num_cross_attend_heads=1, num_self_attend_heads=4), 6)
         x = torch.randn(2, 260, 37)
         imask = torch.ones(2, 260, dtype=torch.bool)
         imask[1, 200:] = False
@@ -94,18 +104,18 @@ def main():
               dict(inputs=x, input_mask=imask), enc(x, enc.latents(x), input_mask=imask))
 
         # 7. whole decoder with final projection and a query residual
-        dec = ref_shim.perturb_parameters(R.PerceiverDecoder(query_channels=50, final_project_out_channels=10,
+        dec = ref_shim.perturb_parameters(_build(R.PerceiverDecoder, query_channels=50, final_project_out_channels=10,
                                                              num_latent_channels=64, use_query_residual=True,
-                                                             num_heads=1).eval(), 7)
+                                                             num_heads=1), 7)
         query, lat = torch.randn(2, 70, 50), torch.randn(2, 40, 64)
         _save("decoder_small", dec, dict(kind="decoder", num_heads=1, use_query_residual=1, final_project=1),
               dict(query=query, latents=lat), dec(query, lat))
 
         # 8. decoder without final projection, query mask (language decoder)
-        dec = ref_shim.perturb_parameters(R.PerceiverDecoder(query_channels=48, final_project_out_channels=48,
+        dec = ref_shim.perturb_parameters(_build(R.PerceiverDecoder, query_channels=48, final_project_out_channels=48,
                                                              num_latent_channels=64, qk_channels=32, v_channels=48,
                                                              use_query_residual=False, num_heads=4,
-                                                             final_project=False).eval(), 8)
+                                                             final_project=False), 8)
         query, lat = torch.randn(2, 33, 48), torch.randn(2, 40, 64)
         qmask = torch.ones(2, 33, dtype=torch.bool)
         qmask[0, 20:] = False

@@ -1,0 +1,307 @@
+"""Host-side lowering of the Perceiver IO blocks onto the C-ABI kernels.
+
+This is orchestration only: LayerNorm+cast, GEMM(+epilogue), streaming attention, softmax and combine launches on
+the caller's CUDA stream.  Activations between kernels are bf16 (MMA operands) while the residual stream, LayerNorm
+statistics, softmax statistics and all accumulators stay fp32.
+
+Weight preparation (bf16 copies, fused QKV matrices and the single-head "folded" products described in DESIGN.md)
+happens once per module and is cached as non-persistent derived state keyed on the parameters' versions.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops
+from .ops import BF16, pad8
+
+# Flags (module-level so tests / bench can flip them)
+ENABLE_FOLDING = True      # single-head cross-attention: K == V == LN(x)
+ENCODER_KEY_SPLITS = 0     # 0 = auto
+
+
+def _bf16_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N, K] -> bf16 [N, pad8(K)] (pad columns zero; never read by TMA anyway)."""
+    n, k = w.shape
+    out = torch.zeros((n, pad8(k)), dtype=BF16, device=w.device)
+    out[:, :k] = w.detach().to(BF16)
+    return out
+
+
+class PreparedAttention:
+    """Derived bf16 weights of one reference `Attention` module (+ fused / folded variants)."""
+
+    def __init__(self, att, *, self_attention: bool, allow_fold: bool):
+        wq, bq = att.proj_q.weight.detach(), att.proj_q.bias.detach()
+        wk, bk = att.proj_k.weight.detach(), att.proj_k.bias.detach()
+        wv, bv = att.proj_v.weight.detach(), att.proj_v.bias.detach()
+        wf = att.final.weight.detach()
+        bf = att.final.bias.detach() if att.final.bias is not None else None
+        self.H = att._num_heads
+        self.QK, self.Cq = wq.shape
+        self.Ck = wk.shape[1]
+        self.V = wv.shape[0]
+        self.O = wf.shape[0]
+        self.dqk = self.QK // self.H
+        self.dv = self.V // self.H
+        self.scale = 1.0 / math.sqrt(self.dqk)
+        self.folded = bool(allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck
+                           and ops.attention_supported(self.Ck, self.Ck) and self.Ck <= 384)
+        self.wf, self.bf = _bf16_weight(wf), (bf.float().contiguous() if bf is not None else None)
+        if self.folded:
+            # S = (LN(q) Wq^T + bq) Wk . LN(x)^T  (the q.bk term is constant per row and cancels in the softmax)
+            # out = (P . LN(x)) (Wf Wv)^T + (Wf bv + bf)          (rows of P sum to one)
+            wq64, wk64, wv64, wf64 = (t.double() for t in (wq, wk, wv, wf))
+            self.wq_fold = _bf16_weight((wk64.t() @ wq64).float())              # [Ck, Cq]
+            self.bq_fold = (wk64.t() @ bq.double()).float().contiguous()        # [Ck]
+            self.wo_fold = _bf16_weight((wf64 @ wv64).float())                  # [O, Ck]
+            bo = wf64 @ bv.double()
+            if bf is not None:
+                bo = bo + bf.double()
+            self.bo_fold = bo.float().contiguous()
+        elif self_attention:
+            self.wqkv = _bf16_weight(torch.cat([wq, wk, wv], 0))
+            self.bqkv = torch.cat([bq, bk, bv], 0).float().contiguous()
+        else:
+            self.wq, self.bq = _bf16_weight(wq), bq.float().contiguous()
+            self.kv_fused = (self.QK % 8 == 0)
+            if self.kv_fused:
+                self.wkv = _bf16_weight(torch.cat([wk, wv], 0))
+                self.bkv = torch.cat([bk, bv], 0).float().contiguous()
+            else:
+                self.wk, self.bk = _bf16_weight(wk), bk.float().contiguous()
+                self.wv, self.bv = _bf16_weight(wv), bv.float().contiguous()
+
+
+class PreparedMLP:
+    def __init__(self, mlp):
+        self.w1, self.b1 = _bf16_weight(mlp.fc1.weight.detach()), mlp.fc1.bias.detach().float().contiguous()
+        self.w2, self.b2 = _bf16_weight(mlp.fc2.weight.detach()), mlp.fc2.bias.detach().float().contiguous()
+        self.hidden, self.cin = mlp.fc1.weight.shape
+        self.cout = mlp.fc2.weight.shape[0]
+
+
+def _versions(module):
+    return tuple((p.data_ptr(), p._version, p.device) for p in module.parameters())
+
+
+def prepared(module, key, builder):
+    """Per-module cache of derived weights, rebuilt when any parameter changes (in-place update, load_state_dict,
+    .to(device))."""
+    cache = module.__dict__.setdefault("_pio_cache", {})
+    ver = _versions(module)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        with torch.no_grad():
+            hit = (ver, builder())
+        cache[key] = hit
+    return hit[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# attention cores
+# ---------------------------------------------------------------------------------------------------------------
+
+def _head_slice(t: torch.Tensor, B: int, N: int, ld: int, col0: int, d: int):
+    """Return (tensor, ld, col_offset) for columns [col0, col0+d) of a [B*N, ld] bf16 matrix such that the slice
+    base is 16-byte aligned; copies into a fresh padded buffer only when it is not."""
+    if (col0 * 2) % 16 == 0:
+        return t, ld, col0
+    out = torch.zeros((B * N, pad8(d)), dtype=BF16, device=t.device)
+    out[:, :d] = t.view(B * N, ld)[:, col0:col0 + d]
+    return out, pad8(d), 0
+
+
+def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv, scale,
+                            key_mask, row_keep, q_bcast):
+    """Attention through explicit S and P matrices (GEMM -> softmax -> GEMM), one head at a time.  Used when the
+    streaming kernel does not cover the head sizes (d > 384: the decoders, the multimodal encoder)."""
+    dev = q.device
+    ldo = pad8(H * dv)
+    O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+    lds = (Nk + 3) // 4 * 4
+    for h in range(H):
+        qh, ldqh, qo = _head_slice(q, 1 if q_bcast else B, Nq, ldq, qcol + h * dqk, dqk)
+        kh, ldkh, ko = _head_slice(k, B, Nk, ldk, kcol + h * dqk, dqk)
+        vh, ldvh, vo = _head_slice(v, B, Nk, ldv, vcol + h * dv, dv)
+        S = torch.empty((B, Nq, lds), dtype=torch.float32, device=dev)
+        ops.gemm(qh.view(-1)[qo:], kh.view(-1)[ko:], M=Nq, N=Nk, K=dqk, batch=B,
+                 strideA=0 if q_bcast else Nq * ldqh, strideB=Nk * ldkh, lda=ldqh, ldb=ldkh,
+                 out_f32=S, ldo32=lds, strideO32=Nq * lds)
+        P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)
+        del S
+        ldp = P.shape[-1]
+        oh = O.view(-1)[h * dv:]
+        ops.gemm(P, vh.view(-1)[vo:], M=Nq, N=dv, K=Nk, batch=B, b_mn_major=True,
+                 strideA=Nq * ldp, strideB=Nk * ldvh, lda=ldp, ldb=ldvh,
+                 out_bf16=oh, ldo16=ldo, strideO16=Nq * ldo)
+    return O
+
+
+def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv) -> int:
+    """Key-axis splits so that a small (batch x heads x query tiles) grid still fills the 148 SMs."""
+    if ENCODER_KEY_SPLITS > 0:
+        want = ENCODER_KEY_SPLITS
+    else:
+        ctas = B * H * ((Nq + 127) // 128)
+        if ctas >= 120 or Nk < 4096:
+            return 1
+        want = max(1, min(32, 148 // ctas))
+    bn = ops._lib.load().pio_attention_key_tile(dqk, dv, 1 if same_kv else 0)
+    tiles = (Nk + bn - 1) // bn
+    want = min(want, tiles)
+    while want > 1 and (want - 1) * ((tiles + want - 1) // want) >= tiles:
+        want -= 1
+    return want
+
+
+def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv, scale, key_mask=None,
+              row_keep=None, q_bcast=False, partial=False, num_splits=None):
+    """Dispatch between the streaming kernel and the materialised path.  q/k/v are flat bf16 [rows, ld] matrices;
+    *col give the first column of head 0.  Returns O bf16 [B, Nq, pad8(H*dv)] (or partials)."""
+    same_kv = (k.data_ptr() == v.data_ptr()) and kcol == vcol and ldk == ldv and dqk == dv
+    flash_ok = (ops.attention_supported(dqk, dv) and (H == 1 or dqk % 16 == 0)
+                and all((c * 2) % 16 == 0 for c in (qcol, kcol, vcol)))
+    if flash_ok and not same_kv and not ((dqk + 63) // 64 <= 2 and (dv + 63) // 64 <= 3):
+        flash_ok = False
+    if not flash_ok:
+        if partial:
+            raise RuntimeError("perceiverio_pytorch_b200: key-sharded attention needs head sizes covered by the "
+                               f"streaming kernel (got dqk={dqk}, dv={dv})")
+        return _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, B=B, H=H, Nq=Nq, Nk=Nk, dqk=dqk,
+                                       dv=dv, scale=scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast)
+    if num_splits is None:
+        num_splits = _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv)
+    qv, kv_, vv = q.view(-1)[qcol:], k.view(-1)[kcol:], v.view(-1)[vcol:]
+    if same_kv:
+        vv = kv_
+    return ops.attention_fwd(qv, kv_, vv, B=B, H=H, Nq=Nq, Nk=Nk, dqk=dqk, dv=dv,
+                             strideQ=0 if q_bcast else Nq * ldq, strideK=Nk * ldk, strideV=Nk * ldv,
+                             ldq=ldq, ldk=ldk, ldv=ldv, scale=scale, key_mask=key_mask, row_keep=row_keep,
+                             num_splits=num_splits, partial=partial)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# blocks
+# ---------------------------------------------------------------------------------------------------------------
+
+def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False):
+    """x + fc2(gelu(fc1(LN(x)))) on a flat fp32 [M, C] matrix.  Returns (fp32 [M, cout], bf16 copy or None)."""
+    xn = ops.layernorm_bf16(x_f32, ln_w, ln_b)
+    _, h = ops.linear(xn, pm.cin, pm.w1, pm.hidden, pm.b1, act=1)
+    y32, y16 = ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, residual=x_f32, want_f32=True,
+                          want_bf16=want_bf16_out)
+    return y32, y16
+
+
+def mlp_only(pm: PreparedMLP, x_bf16: torch.Tensor):
+    """fc2(gelu(fc1(x))) without LayerNorm / residual (the bare reference `MLP.forward`)."""
+    _, h = ops.linear(x_bf16, pm.cin, pm.w1, pm.hidden, pm.b1, act=1)
+    y32, _ = ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, want_f32=True, want_bf16=False)
+    return y32
+
+
+def self_attention_block(pa: PreparedAttention, pm: PreparedMLP, x: torch.Tensor, ln1, ln2,
+                         key_mask=None, row_keep=None) -> torch.Tensor:
+    """SelfAttention.forward (transformer_primitives.py:275-297) on x fp32 [B, N, C] (contiguous)."""
+    B, N, C = x.shape
+    x2 = x.reshape(B * N, C)
+    xn = ops.layernorm_bf16(x2, ln1.weight, ln1.bias)
+    nqkv = 2 * pa.QK + pa.V
+    _, qkv = ops.linear(xn, C, pa.wqkv, nqkv, pa.bqkv)
+    ld = pad8(nqkv)
+    o = attention(qkv, ld, 0, qkv, ld, pa.QK, qkv, ld, 2 * pa.QK, B=B, H=pa.H, Nq=N, Nk=N, dqk=pa.dqk, dv=pa.dv,
+                  scale=pa.scale, key_mask=key_mask, row_keep=row_keep)
+    x1, _ = ops.linear(o.view(B * N, -1), pa.V, pa.wf, pa.O, pa.bf, residual=x2, want_f32=True, want_bf16=False)
+    y, _ = mlp_block(pm, x1, ln2.weight, ln2.bias)
+    return y.view(B, N, -1)
+
+
+def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep,
+                         partial=False, num_splits=None):
+    """Projection(s) + attention for a cross-attend.  qn: bf16 [(1|B)*Nq, pad8(Cq)], kvn: bf16 [B*Nk, pad8(Ck)].
+    Returns the attention output O bf16 [B, Nq, ld] *before* the output projection, and its logical width."""
+    if pa.folded:
+        _, qf = ops.linear(qn, pa.Cq, pa.wq_fold, pa.Ck, pa.bq_fold)
+        ldq = pad8(pa.Ck)
+        ldk = kvn.shape[-1]
+        o = attention(qf, ldq, 0, kvn, ldk, 0, kvn, ldk, 0, B=B, H=1, Nq=Nq, Nk=Nk, dqk=pa.Ck, dv=pa.Ck,
+                      scale=pa.scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast, partial=partial,
+                      num_splits=num_splits)
+        return o, pa.Ck
+    _, q = ops.linear(qn, pa.Cq, pa.wq, pa.QK, pa.bq)
+    if pa.kv_fused:
+        n = pa.QK + pa.V
+        _, kv = ops.linear(kvn, pa.Ck, pa.wkv, n, pa.bkv)
+        ld = pad8(n)
+        k, ldk, kcol, v, ldv, vcol = kv, ld, 0, kv, ld, pa.QK
+    else:
+        _, k = ops.linear(kvn, pa.Ck, pa.wk, pa.QK, pa.bk)
+        _, v = ops.linear(kvn, pa.Ck, pa.wv, pa.V, pa.bv)
+        ldk, kcol, ldv, vcol = pad8(pa.QK), 0, pad8(pa.V), 0
+    o = attention(q, pad8(pa.QK), 0, k, ldk, kcol, v, ldv, vcol, B=B, H=pa.H, Nq=Nq, Nk=Nk, dqk=pa.dqk, dv=pa.dv,
+                  scale=pa.scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast, partial=partial,
+                  num_splits=num_splits)
+    return o, pa.V
+
+
+def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual):
+    """Output projection (+ query residual) of a cross-attend: returns fp32 [B*Nq, O]."""
+    if pa.folded:
+        w, b = pa.wo_fold, pa.bo_fold
+    else:
+        w, b = pa.wf, pa.bf
+    o2 = o.view(B * Nq, -1)
+    y = torch.empty((B * Nq, pa.O), dtype=torch.float32, device=o.device)
+    if residual is None:
+        ops.gemm(o2, w, M=B * Nq, N=pa.O, K=width, bias=b, out_f32=y, ldo32=pa.O)
+    else:
+        # residual is the un-normalised query [B, Nq, Cq], possibly a stride-0 batch broadcast
+        assert residual.stride(2) == 1
+        ops.gemm(o2, w, M=Nq, N=pa.O, K=width, batch=B, strideA=Nq * o2.shape[1], strideB=0, bias=b,
+                 residual=residual, ldr=residual.stride(1), strideR=residual.stride(0) if B > 1 else 0,
+                 out_f32=y, ldo32=pa.O, strideO32=Nq * pa.O)
+    return y
+
+
+def _as_u8(mask: Optional[torch.Tensor]):
+    if mask is None:
+        return None
+    return mask.to(torch.uint8).contiguous()
+
+
+def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torch.Tensor, inputs_kv: torch.Tensor,
+                          ln_q, ln_kv, ln2, *, use_query_residual: bool, key_mask=None, row_keep=None,
+                          want_bf16_out=False, shard=None):
+    """CrossAttention.forward (transformer_primitives.py:371-406).
+
+    inputs_q fp32 [B, Nq, Cq] (batch stride may be 0), inputs_kv fp32 [B, Nk, Ck].  `shard`, if given, is a
+    parallel.KeyShard describing a key-axis shard of inputs_kv across ranks."""
+    B, Nq, Cq = inputs_q.shape
+    Nk, Ck = inputs_kv.shape[1], inputs_kv.shape[2]
+    q_bcast = B > 1 and inputs_q.stride(0) == 0
+    if inputs_kv.stride(2) != 1 or inputs_kv.stride(0) != Nk * inputs_kv.stride(1):
+        inputs_kv = inputs_kv.contiguous()
+    kvn = ops.layernorm_bf16(inputs_kv.view(B * Nk, Ck) if inputs_kv.is_contiguous()
+                             else inputs_kv.reshape(B * Nk, Ck), ln_kv.weight, ln_kv.bias)
+    q_src = inputs_q[0] if q_bcast else (inputs_q if inputs_q.is_contiguous() else inputs_q.contiguous()).view(B * Nq, Cq)
+    if q_src.stride(-1) != 1:
+        q_src = q_src.contiguous()
+    qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias)
+    km, rk = _as_u8(key_mask), _as_u8(row_keep)
+    if shard is None:
+        o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk)
+    else:
+        parts = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=None,
+                                     partial=True, num_splits=shard.local_splits)
+        o = shard.combine(parts, row_keep=rk)
+        width = pa.Ck if pa.folded else pa.V
+    if use_query_residual:
+        res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
+    else:
+        res = None
+    x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res)
+    y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out)
+    return y32.view(B, Nq, -1), y16

@@ -1,0 +1,93 @@
+"""Plugging the B200 path into an unmodified checkout of JOBR0/PerceiverIO_Pytorch.
+
+Two routes, both leave `state_dict()` byte-identical:
+
+* `install_as_reference_primitives()` — before `perceiver_io.perceiver` is imported, register this package's
+  primitives module as `perceiver_io.transformer_primitives`; the reference's own `PerceiverEncoder` /
+  `PerceiverDecoder` (perceiver.py:10 imports CrossAttention, SelfAttention, make_cross_attention_mask from there)
+  then build themselves out of the B200 blocks.
+* `swap_hot_path(model)` — on an already constructed reference model (any wrapper or a bare `PerceiverIO`),
+  replace `_encoder` / `_decoder` by B200 modules that load the originals' parameters.
+"""
+from __future__ import annotations
+
+import sys
+
+import torch.nn as nn
+
+from . import perceiver as _perceiver
+from . import primitives as _primitives
+
+
+def install_as_reference_primitives() -> None:
+    if "perceiver_io.perceiver" in sys.modules:
+        raise RuntimeError("perceiver_io.perceiver is already imported; use swap_hot_path(model) instead")
+    sys.modules["perceiver_io.transformer_primitives"] = _primitives
+
+
+def _encoder_from_reference(enc: nn.Module) -> _perceiver.PerceiverEncoder:
+    ca = enc.cross_attend
+    sa0 = enc.self_attends[0]
+    att = ca.attention
+    new = _perceiver.PerceiverEncoder(
+        num_input_channels=att.proj_k.in_features,
+        num_self_attends_per_block=len(enc.self_attends),
+        num_blocks=enc._num_blocks,
+        num_latents=enc.latent_pos_enc.pos_embs.shape[0],
+        num_latent_channels=enc.latent_pos_enc.pos_embs.shape[1],
+        qk_channels=None, v_channels=None,
+        num_cross_attend_heads=att._num_heads,
+        num_self_attend_heads=sa0.attention._num_heads,
+        cross_attend_widening_factor=ca.mlp.fc1.out_features // ca.mlp.fc1.in_features,
+        self_attend_widening_factor=sa0.mlp.fc1.out_features // sa0.mlp.fc1.in_features,
+        use_query_residual=ca._use_query_residual)
+    # qk / v widths can differ between the cross-attend and the self-attends (they share the ctor kwarg in the
+    # reference but default differently), so rebuild the blocks from the actual parameter shapes
+    new.cross_attend = _cross_from_reference(ca)
+    new.self_attends = nn.ModuleList(_self_from_reference(s) for s in enc.self_attends)
+    new.load_state_dict(enc.state_dict(), strict=True)
+    return new.to(next(enc.parameters()).device).eval()
+
+
+def _cross_from_reference(ca: nn.Module) -> _primitives.CrossAttention:
+    att = ca.attention
+    return _primitives.CrossAttention(
+        q_in_channels=att.proj_q.in_features, kv_in_channels=att.proj_k.in_features,
+        widening_factor=ca.mlp.fc1.out_features // ca.mlp.fc1.in_features, num_heads=att._num_heads,
+        use_query_residual=ca._use_query_residual, qk_channels=att.proj_q.out_features,
+        v_channels=att.proj_v.out_features)
+
+
+def _self_from_reference(sa: nn.Module) -> _primitives.SelfAttention:
+    att = sa.attention
+    return _primitives.SelfAttention(
+        in_channels=att.proj_q.in_features, widening_factor=sa.mlp.fc1.out_features // sa.mlp.fc1.in_features,
+        num_heads=att._num_heads, qk_channels=att.proj_q.out_features, v_channels=att.proj_v.out_features)
+
+
+def _decoder_from_reference(dec: nn.Module) -> _perceiver.PerceiverDecoder:
+    ca = dec.decoding_cross_attn
+    att = ca.attention
+    new = _perceiver.PerceiverDecoder(
+        query_channels=dec.query_channels,
+        final_project_out_channels=dec._output_num_channels,
+        num_latent_channels=att.proj_k.in_features,
+        qk_channels=att.proj_q.out_features, v_channels=att.proj_v.out_features,
+        use_query_residual=dec._use_query_residual, num_heads=att._num_heads,
+        final_project=dec._final_project)
+    new.load_state_dict(dec.state_dict(), strict=True)
+    return new.to(next(dec.parameters()).device).eval()
+
+
+def swap_hot_path(model: nn.Module) -> nn.Module:
+    """Replace every reference PerceiverEncoder / PerceiverDecoder inside `model` by its B200 drop-in."""
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            cls = type(child).__name__
+            if isinstance(child, (_perceiver.PerceiverEncoder, _perceiver.PerceiverDecoder)):
+                continue
+            if cls == "PerceiverEncoder":
+                setattr(parent, name, _encoder_from_reference(child))
+            elif cls == "PerceiverDecoder":
+                setattr(parent, name, _decoder_from_reference(child))
+    return model

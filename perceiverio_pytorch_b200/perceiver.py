@@ -1,0 +1,132 @@
+"""Drop-in `PerceiverEncoder` / `PerceiverDecoder` (reference: perceiver_io/perceiver.py:13-107, :110-180).
+
+Same constructor kwargs, attribute / parameter names and forward signatures; this is where the hot path is
+orchestrated (cross-attend -> num_blocks x shared self-attends; decoder cross-attend -> final_layer) and where the
+multi-GPU partitioning of SURVEY.md §8(e) hooks in (`parallel.py`).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from .primitives import CrossAttention, SelfAttention, lecun_normal_, make_cross_attention_mask  # noqa: F401
+
+
+class TrainablePositionEncoding(nn.Module):
+    """The latent array holder: parameter `pos_embs` [index_dim, num_channels]
+    (reference: position_encoding.py:104-124, used at perceiver.py:64-67)."""
+
+    def __init__(self, index_dim, num_channels: int = 128, init_scale: float = 0.02):
+        super().__init__()
+        self.pos_embs = nn.Parameter(torch.zeros((index_dim, num_channels)))
+        nn.init.trunc_normal_(self.pos_embs, std=init_scale)
+        self._output_channels = num_channels
+
+    def forward(self, batch_size, pos=None):
+        del pos
+        pos_embs = self.pos_embs
+        if batch_size is not None:
+            pos_embs = torch.broadcast_to(self.pos_embs[None, :, :], (batch_size,) + self.pos_embs.shape)
+        return pos_embs
+
+    def n_output_channels(self):
+        return self._output_channels
+
+
+class PerceiverEncoder(nn.Module):
+    """The Perceiver encoder (reference: perceiver.py:13-107)."""
+
+    def __init__(self, num_input_channels: int, num_self_attends_per_block: int = 6, num_blocks: int = 8,
+                 num_latents: int = 512, num_latent_channels: int = 1024, qk_channels: int = None,
+                 v_channels: int = None, num_cross_attend_heads: int = 1, num_self_attend_heads: int = 8,
+                 cross_attend_widening_factor: int = 1, self_attend_widening_factor: int = 1,
+                 dropout_prob: float = 0.0, latent_pos_enc_init_scale: float = 0.02,
+                 cross_attention_shape_for_attn: str = "kv", use_query_residual: bool = True):
+        super().__init__()
+        if num_latent_channels % num_self_attend_heads != 0:
+            raise ValueError(f"num_z_channels ({num_latent_channels}) must be divisible by"
+                             f" num_self_attend_heads ({num_self_attend_heads}).")
+        if num_latent_channels % num_cross_attend_heads != 0:
+            raise ValueError(f"num_z_channels ({num_latent_channels}) must be divisible by"
+                             f" num_cross_attend_heads ({num_cross_attend_heads}).")
+        self._num_blocks = num_blocks
+        self.latent_pos_enc = TrainablePositionEncoding(index_dim=num_latents, num_channels=num_latent_channels,
+                                                        init_scale=latent_pos_enc_init_scale)
+        self.cross_attend = CrossAttention(q_in_channels=num_latent_channels, kv_in_channels=num_input_channels,
+                                           dropout_prob=dropout_prob, num_heads=num_cross_attend_heads,
+                                           widening_factor=cross_attend_widening_factor,
+                                           shape_for_attn=cross_attention_shape_for_attn, qk_channels=qk_channels,
+                                           v_channels=v_channels, use_query_residual=use_query_residual)
+        self.self_attends = nn.ModuleList()
+        for _ in range(num_self_attends_per_block):
+            self.self_attends.append(SelfAttention(in_channels=num_latent_channels, num_heads=num_self_attend_heads,
+                                                   dropout_prob=dropout_prob, qk_channels=qk_channels,
+                                                   v_channels=v_channels,
+                                                   widening_factor=self_attend_widening_factor))
+        self.key_shard = None  # set by parallel.shard_encoder_keys(): inputs hold this rank's slice of the key axis
+
+    def latents(self, inputs):
+        return self.latent_pos_enc(batch_size=inputs.shape[0])
+
+    def forward(self, inputs, latents, *, input_mask=None):
+        """inputs fp32 [B, Nk, C_in] (this rank's key slice when `key_shard` is set), latents [B, Nlat, C]."""
+        key_mask = None
+        row_keep = None
+        if input_mask is not None:
+            key_mask = input_mask.to(torch.bool)
+            any_key = key_mask.any(dim=1, keepdim=True)
+            if self.key_shard is not None:
+                any_key = self.key_shard.any_over_ranks(any_key)
+            row_keep = any_key.expand(latents.shape[0], latents.shape[1])
+        z, _ = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
+                                                   shard=self.key_shard)
+        for _ in range(self._num_blocks):
+            for self_attend in self.self_attends:
+                z = self_attend(z)
+        return z
+
+
+class PerceiverDecoder(nn.Module):
+    """Cross-attention-based decoder (reference: perceiver.py:110-180)."""
+
+    def __init__(self, query_channels: int, final_project_out_channels: int, num_latent_channels: int = 1024,
+                 qk_channels: int = None, v_channels: int = None, use_query_residual: bool = False,
+                 output_w_init: str = "lecun_normal", num_heads: int = 1, final_project: bool = True):
+        super().__init__()
+        self._output_num_channels = final_project_out_channels
+        self._output_w_init = output_w_init
+        self._use_query_residual = use_query_residual
+        self._qk_channels = qk_channels
+        self._v_channels = v_channels
+        self._final_project = final_project
+        self._num_heads = num_heads
+        self.query_channels = query_channels
+        self.decoding_cross_attn = CrossAttention(q_in_channels=query_channels, kv_in_channels=num_latent_channels,
+                                                  dropout_prob=0.0, num_heads=self._num_heads, widening_factor=1,
+                                                  shape_for_attn="kv", qk_channels=self._qk_channels,
+                                                  v_channels=self._v_channels,
+                                                  use_query_residual=self._use_query_residual)
+        if self._final_project:
+            self.final_layer = nn.Linear(query_channels, self._output_num_channels)
+            if self._output_w_init == "lecun_normal":
+                lecun_normal_(self.final_layer.weight)
+            elif self._output_w_init == "zeros":
+                nn.init.constant_(self.final_layer.weight, 0)
+            else:
+                raise ValueError(f"{self._output_w_init} not supported as output_w_init")
+            nn.init.constant_(self.final_layer.bias, 0)
+
+    def forward(self, query, latents, *, query_mask=None):
+        row_keep = query_mask.to(torch.bool) if query_mask is not None else None
+        y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
+                                                              want_bf16_out=self._final_project)
+        if not self._final_project:
+            return y32
+        B, Nq, C = y32.shape
+        w = engine.prepared(self.final_layer, "w", lambda: (engine._bf16_weight(self.final_layer.weight.detach()),
+                                                           self.final_layer.bias.detach().float().contiguous()))
+        out, _ = ops.linear(y16, C, w[0], self._output_num_channels, w[1], want_f32=True, want_bf16=False)
+        return out.view(B, Nq, -1)
