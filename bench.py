@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the Perceiver IO hot path (PerceiverEncoder + PerceiverDecoder forward) on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's sm_100a path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]): ClassificationPerceiver, ImageNet 224x224 Fourier-position pixels:
+encoder input [64, 50176, 261] fp32, 512 latents x 1024 channels, 8 blocks x 6 shared self-attends, decoder with
+1000 queries x 1024 channels and the 1024->1000 final projection; random-init weights (biases / LayerNorm affines
+perturbed), synthetic inputs.  A step is one forward of that hot path over one 64-sample batch per GPU (weak
+scaling: every rank processes its own batch, no data-path collective — SURVEY.md §8e "batch axis").
+
+Prints ONE JSON line (see README / DESIGN.md §measurement for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(
+    workload="ClassificationPerceiver ImageNet-pixels hot path: 50176x261 inputs -> 512x1024 latents, 8x6 self-attends, "
+             "1000-query decoder + final 1024->1000",
+    batch_per_gpu=64, num_inputs=50176, input_channels=261, num_latents=512, latent_channels=1024,
+    num_blocks=8, self_attends_per_block=6, num_queries=1000, num_classes=1000)
+
+ENC_KW = dict(num_input_channels=261, num_self_attends_per_block=6, num_blocks=8, num_latents=512,
+              num_latent_channels=1024, num_cross_attend_heads=1, num_self_attend_heads=8)
+DEC_KW = dict(query_channels=1024, final_project_out_channels=1000, num_latent_channels=1024, use_query_residual=True,
+              num_heads=1, final_project=True)
+
+
+def model_flops_per_sample() -> float:
+    """Reference-algorithm FLOPs of the hot path per sample (SURVEY.md §8d formula): 418.7 GFLOP."""
+    def blk(nq, nk, cq, ck, qk, v, o):
+        return 2 * nq * cq * qk + 2 * nk * ck * (qk + v) + 2 * nq * nk * (qk + v) + 2 * nq * v * o + 4 * nq * o * o
+    enc = blk(512, 50176, 1024, 261, 261, 261, 1024)
+    tower = 48 * blk(512, 512, 1024, 1024, 1024, 1024, 1024)
+    dec = blk(1000, 512, 1024, 1024, 1024, 1024, 1024) + 2 * 1000 * 1024 * 1000
+    return float(enc + tower + dec)
+
+
+def perturb(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, prm in module.named_parameters():
+            if name.endswith("bias"):
+                prm.copy_((0.1 if "layer_norm" in name else 0.02) * torch.randn(prm.shape, generator=g))
+            elif "layer_norm" in name:
+                prm.copy_(1.0 + 0.1 * torch.randn(prm.shape, generator=g))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class KernelTimer:
+    """CUDA-event timing of every C-ABI launch inside the timed region (on the launching stream)."""
+
+    def __init__(self):
+        self.records = []
+
+    def wrap(self, ops):
+        self._orig = {}
+        timer = self
+
+        def make(name, fn, flops_fn, bytes_fn):
+            def wrapped(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                e1.record()
+                timer.records.append((name, flops_fn(*a, **k), bytes_fn(*a, **k), e0, e1))
+                return out
+            return wrapped
+
+        def gemm_flops(A, B, **k):
+            return 2.0 * k["M"] * k["N"] * k["K"] * k.get("batch", 1)
+
+        def ln_bytes(x, g, b, **k):
+            rows = x.numel() // x.shape[-1]
+            return rows * (4.0 * x.shape[-1] + 2.0 * ((x.shape[-1] + 7) // 8 * 8))
+
+        def attn_flops(Q, K, V, **k):
+            return 2.0 * k["B"] * k["H"] * k["Nq"] * k["Nk"] * (k["dqk"] + k["dv"])
+
+        zero = lambda *a, **k: 0.0  # noqa: E731
+        for name, ff, bf in (("gemm", gemm_flops, zero), ("layernorm_bf16", zero, ln_bytes),
+                             ("attention_fwd", attn_flops, zero), ("softmax_bf16", zero, zero),
+                             ("attention_combine", zero, zero)):
+            self._orig[name] = getattr(ops, name)
+            setattr(ops, name, make(name, self._orig[name], ff, bf))
+
+    def unwrap(self, ops):
+        for name, fn in self._orig.items():
+            setattr(ops, name, fn)
+
+    def summary(self, steps):
+        agg = {}
+        for name, fl, by, e0, e1 in self.records:
+            a = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += fl
+            a["bytes"] += by
+            a["launches"] += 1
+        for a in agg.values():
+            a["ms_per_step"] = a["ms"] / steps
+            a["launches_per_step"] = a["launches"] / steps
+        return agg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                    tflops_burst=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port; the Python reference cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------------------------
+
+def cpu_forward_factory(batch):
+    from oracle import perceiver_oracle as O
+    import perceiverio_pytorch_b200 as pio
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(**ENC_KW).eval()
+    dec = pio.PerceiverDecoder(**DEC_KW).eval()
+    perturb(enc, 1)
+    perturb(dec, 2)
+    pe = {k: v.detach() for k, v in enc.state_dict().items()}
+    pd = {k: v.detach() for k, v in dec.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    inputs = torch.randn(batch, CFG["num_inputs"], CFG["input_channels"], generator=g)
+    query = 0.02 * torch.randn(1, CFG["num_queries"], 1024, generator=g).expand(batch, -1, -1)
+
+    def fwd():
+        with torch.inference_mode():
+            z = O.encoder_forward(pe, "", num_blocks=8, num_self_attends_per_block=6, num_cross_attend_heads=1,
+                                  num_self_attend_heads=8, inputs=inputs)
+            return O.decoder_forward(pd, "", num_heads=1, use_query_residual=True, final_project=True, query=query,
+                                     latents=z)
+    return fwd
+
+
+def time_cpu(batch, warmup, steps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    fwd = cpu_forward_factory(batch)
+    for _ in range(warmup):
+        fwd()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fwd()
+        ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1
+    sec = time_cpu(batch, args.warmup, args.steps)
+    v = batch / sec
+    sample = f"{batch} sample(s) of the 64-sample batch per step, fp32, torch CPU ops, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "samples/sec per forward", "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(CFG, sample=sample),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.check(_lib.load().pio_check_device(), "pio_check_device")
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(**ENC_KW).eval()
+    dec = pio.PerceiverDecoder(**DEC_KW).eval()
+    perturb(enc, 1)
+    perturb(dec, 2)
+    enc, dec = enc.to(dev), dec.to(dev)
+    g = torch.Generator().manual_seed(3 + rank)
+    host_inputs = torch.empty(B, CFG["num_inputs"], CFG["input_channels"]).normal_(generator=g).pin_memory()
+    inputs = host_inputs.to(dev)
+    # the decoder query of the classification recipe is a trainable [1000, 1024] array broadcast over the batch and
+    # materialised by torch.cat in PerceiverIO.decoder_query (perceiver.py:353-364): device-resident, like the weights
+    query = (0.02 * torch.randn(1, CFG["num_queries"], 1024, generator=torch.Generator().manual_seed(5))).to(dev) \
+        .expand(B, -1, -1).contiguous()
+    host_out = torch.empty(B, CFG["num_classes"]).pin_memory()
+
+    def step(x):
+        with torch.inference_mode():
+            z = enc(x, enc.latents(x))
+            return dec(query, z)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(inputs)
+    sync_all()
+
+    # ---- timed region 1: device-resident inputs, per-kernel CUDA events ----
+    timer = KernelTimer()
+    timer.wrap(ops)
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        out = step(inputs)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop()
+    timer.unwrap(ops)
+    kern = timer.summary(args.steps)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- timed region 2: end to end through the module API with host buffers ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    xdev = torch.empty_like(inputs)
+    for _ in range(1):
+        xdev.copy_(host_inputs, non_blocking=True)
+        host_out.copy_(step(xdev)[:, 0, :], non_blocking=True)
+    sync_all()
+    e0.record()
+    for _ in range(e2e_steps):
+        xdev.copy_(host_inputs, non_blocking=True)
+        o = step(xdev)
+        host_out.copy_(o[:, 0, :], non_blocking=True)   # what ClassificationPostprocessor keeps (postprocessors.py:187)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    gemm = kern.get("gemm", dict(ms=1e-9, flops=0.0, launches=1, ms_per_step=0.0, launches_per_step=0))
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    shares = {k: round(v["ms_per_step"] / ms_per_step, 4) for k, v in kern.items()}
+    detail = {}
+    for k, v in kern.items():
+        d = {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"]}
+        if v["flops"] > 0:
+            d["tflops"] = round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
+        if v["bytes"] > 0:
+            d["gbs"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+        detail[k] = d
+    mf = model_flops_per_sample()
+    result = {
+        "metric": "samples/sec per forward", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": dict(CFG, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world} (batch axis, no collective)",
+                       l2="inputs (3.35 GB fp32 per step) are larger than L2; no flush needed",
+                       precision="bf16 MMA operands, fp32 residual stream / LayerNorm / softmax statistics / accumulators"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": host_inputs.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                "note": "pinned host input -> H2D -> PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "pio_gemm_kernel (tcgen05 GEMM + fused epilogue), all launches of the step",
+                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                     "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"], "traffic": None,
+                     "share_of_step": shares.get("gemm")},
+        "model": {"flops_per_sample_reference_algorithm": mf,
+                  "tflops_reference_algorithm": mf * value / 1e12,
+                  "frac_of_sustained_peak": mf * value / 1e12 / (pk["tflops"] * world)},
+        "kernels": detail, "kernel_share_of_step": shares,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = 1
+            sec = time_cpu(cb, 1, 2)
+            result["cpu_baseline"] = {"value": cb / sec, "unit": "samples/s", "cores": torch.get_num_threads(),
+                                      "kind": "port",
+                                      "sample": f"{cb} sample of the 64-sample batch, fp32 oracle port of the reference "
+                                                f"forward, 1 warm-up + 2 timed runs, {sec:.2f} s per run"}
+        except Exception as ex:  # the baseline must never take the GPU number down
+            result["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                      "sample": f"failed: {ex}"}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
