@@ -112,61 +112,6 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class KernelTimer:
-    """CUDA-event timing of every C-ABI launch inside the timed region (on the launching stream)."""
-
-    def __init__(self):
-        self.records = []
-
-    def wrap(self, ops):
-        self._orig = {}
-        timer = self
-
-        def make(name, fn, flops_fn, bytes_fn):
-            def wrapped(*a, **k):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                out = fn(*a, **k)
-                e1.record()
-                timer.records.append((name, flops_fn(*a, **k), bytes_fn(*a, **k), e0, e1))
-                return out
-            return wrapped
-
-        def gemm_flops(A, B, **k):
-            return 2.0 * k["M"] * k["N"] * k["K"] * k.get("batch", 1)
-
-        def ln_bytes(x, g, b, **k):
-            rows = x.numel() // x.shape[-1]
-            return rows * (4.0 * x.shape[-1] + 2.0 * ((x.shape[-1] + 7) // 8 * 8))
-
-        def attn_flops(Q, K, V, **k):
-            return 2.0 * k["B"] * k["H"] * k["Nq"] * k["Nk"] * (k["dqk"] + k["dv"])
-
-        zero = lambda *a, **k: 0.0  # noqa: E731
-        for name, ff, bf in (("gemm", gemm_flops, zero), ("layernorm_bf16", zero, ln_bytes),
-                             ("attention_fwd", attn_flops, zero), ("softmax_bf16", zero, zero),
-                             ("attention_combine", zero, zero)):
-            self._orig[name] = getattr(ops, name)
-            setattr(ops, name, make(name, self._orig[name], ff, bf))
-
-    def unwrap(self, ops):
-        for name, fn in self._orig.items():
-            setattr(ops, name, fn)
-
-    def summary(self, steps):
-        agg = {}
-        for name, fl, by, e0, e1 in self.records:
-            a = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            a["ms"] += e0.elapsed_time(e1)
-            a["flops"] += fl
-            a["bytes"] += by
-            a["launches"] += 1
-        for a in agg.values():
-            a["ms_per_step"] = a["ms"] / steps
-            a["launches_per_step"] = a["launches"] / steps
-        return agg
-
-
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,10 +215,21 @@ def run_gpu_arm(args):
         .expand(B, -1, -1).contiguous()
     host_out = torch.empty(B, CFG["num_classes"]).pin_memory()
 
-    def step(x):
+    def step_eager(x):
         with torch.inference_mode():
             z = enc(x, enc.latents(x))
             return dec(query, z)
+
+    if args.no_graph:
+        step = step_eager
+    else:
+        # the whole forward (several hundred launches) is captured once; `inputs` is the graph's input buffer
+        from perceiverio_pytorch_b200.graph import GraphedForward
+        graphed = GraphedForward(step_eager, [inputs], warmup=2)
+        inputs = graphed.inputs[0]
+
+        def step(x):
+            return graphed(x)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -285,9 +241,7 @@ def run_gpu_arm(args):
         out = step(inputs)
     sync_all()
 
-    # ---- timed region 1: device-resident inputs, per-kernel CUDA events ----
-    timer = KernelTimer()
-    timer.wrap(ops)
+    # ---- timed region 1: device-resident inputs ----
     sampler = ClockSampler(local)
     sampler.start()
     n0 = _lib.launch_count()
@@ -299,10 +253,8 @@ def run_gpu_arm(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - n0
+    launches_eager_per_step = None
     clocks = sampler.stop()
-    timer.unwrap(ops)
-    kern = timer.summary(args.steps)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,9 +262,24 @@ def run_gpu_arm(args):
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
+    # ---- per-kernel device times: the same step launched eagerly with the library's own CUDA events around every
+    #      kernel launch (events cannot be read back from inside a replayed graph; the kernels, their arguments and
+    #      their order are identical to the captured ones) ----
+    prof_steps = max(1, min(args.steps, 3))
+    _lib.profile_read()
+    _lib.profile_enable(True)
+    n0 = _lib.launch_count()
+    for _ in range(prof_steps):
+        step_eager(inputs)
+    sync_all()
+    _lib.profile_enable(False)
+    launches = (_lib.launch_count() - n0) // prof_steps * args.steps
+    kern = {k: dict(v, ms_per_step=v["ms"] / prof_steps, launches_per_step=v["launches"] / prof_steps)
+            for k, v in _lib.profile_read().items() if v["launches"] > 0}
+
     # ---- timed region 2: end to end through the module API with host buffers ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    xdev = torch.empty_like(inputs)
+    xdev = inputs  # the (graph) input buffer: the H2D copy lands directly in it
     for _ in range(1):
         xdev.copy_(host_inputs, non_blocking=True)
         host_out.copy_(step(xdev)[:, 0, :], non_blocking=True)
@@ -359,7 +326,7 @@ def run_gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": host_inputs.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                 "note": "pinned host input -> H2D -> PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
         "roofline": {"bound": "tensor", "kernel": "pio_gemm_kernel (tcgen05 GEMM + fused epilogue), all launches of the step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"], "traffic": None,
@@ -368,6 +335,7 @@ def run_gpu_arm(args):
                   "tflops_reference_algorithm": mf * value / 1e12,
                   "frac_of_sustained_peak": mf * value / 1e12 / (pk["tflops"] * world)},
         "kernels": detail, "kernel_share_of_step": shares,
+        "kernel_timing": f"library-side CUDA events around each launch, {prof_steps} eager step(s) after the timed region",
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -394,6 +362,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -90,6 +90,7 @@ typedef struct pio_gemm_args {
   /* debug / tuning: 0 = default */
   int32_t tile_n;       /* 64, 128, 256 or 0 = auto */
   int32_t max_ctas;     /* 0 = number of SMs */
+  int32_t cluster_m;    /* CTAs per cluster along M sharing one multicast B tile: 1, 2, 4 or 0 = auto */
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 
@@ -140,14 +141,26 @@ int pio_attention_supported(int32_t dqk, int32_t dv);
 int pio_attention_key_tile(int32_t dqk, int32_t dv, int32_t same_kv);
 
 /* Merge `parts` partial results (from key splits and/or gathered from other ranks):
- *   O[b, i, h*dv + :] = sum_p O_p * exp(m_p - M) / sum_p l_p * exp(m_p - M),  M = max_p m_p. */
+ *   O[b, i, h*dv + :] = sum_p O_p * exp(m_p - M) / sum_p l_p * exp(m_p - M),  M = max_p m_p.
+ * Part p lives at O_part + p*part_stride_O, m_part/l_part + p*part_stride_ml (0 = densely packed).  Outputs: the
+ * normalised bf16 O (if O != NULL) and/or the merged, still un-normalised partial (O_out_part, m_out, l_out) that a
+ * rank contributes to the cross-GPU exchange of the key-sharded encoder. */
 typedef struct pio_combine_args {
-  const float* O_part; const float* m_part; const float* l_part;   /* [parts, B, H, Nq, dv] / [parts, B, H, Nq] */
+  const float* O_part; const float* m_part; const float* l_part;   /* [parts][B, H, Nq, dv] / [parts][B, H, Nq] */
+  int64_t part_stride_O, part_stride_ml;
   int32_t parts, B, H, Nq, dv;
   const uint8_t* row_keep; int64_t stride_rk;
-  void* O; int64_t ldo; int64_t strideO;                          /* bf16 [B, Nq, ldo] */
+  void* O; int64_t ldo; int64_t strideO;                          /* bf16 [B, Nq, ldo] or NULL */
+  float* O_out_part; float* m_out; float* l_out;                  /* fp32 [B, H, Nq, dv] / [B, H, Nq] or NULL */
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
+
+/* Per-launch device timing (bench.py's roofline): while enabled, every entry point brackets its kernel launch with
+ * CUDA events on the launching stream.  pio_profile_read drains the records into out[family*4 + {ms, flops, bytes,
+ * launches}] for the families {0 layernorm, 1 gemm, 2 softmax, 3 attention, 4 combine}.  Do not enable while a
+ * stream is being captured into a CUDA graph. */
+void pio_profile_enable(int on);
+int pio_profile_read(double* out, int n_families);
 
 /* Number of kernels launched by this library in the calling process (bench.py's gpu_launches). */
 int64_t pio_launch_count(void);

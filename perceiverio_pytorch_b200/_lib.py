@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libpio_b200.so")
 
 EXPORTED_SYMBOLS = (
     "pio_abi_version", "pio_last_error", "pio_check_device", "pio_launch_count",
+    "pio_profile_enable", "pio_profile_read",
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
 )
@@ -37,7 +38,7 @@ class GemmArgs(C.Structure):
                 ("residual", vp), ("ldr", i64), ("strideR", i64),
                 ("out_f32", vp), ("ldo32", i64), ("strideO32", i64),
                 ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
-                ("tile_n", i32), ("max_ctas", i32)]
+                ("tile_n", i32), ("max_ctas", i32), ("cluster_m", i32)]
 
 
 class SoftmaxArgs(C.Structure):
@@ -64,9 +65,11 @@ class AttentionArgs(C.Structure):
 
 class CombineArgs(C.Structure):
     _fields_ = [("O_part", vp), ("m_part", vp), ("l_part", vp),
+                ("part_stride_O", i64), ("part_stride_ml", i64),
                 ("parts", i32), ("B", i32), ("H", i32), ("Nq", i32), ("dv", i32),
                 ("row_keep", vp), ("stride_rk", i64),
-                ("O", vp), ("ldo", i64), ("strideO", i64)]
+                ("O", vp), ("ldo", i64), ("strideO", i64),
+                ("O_out_part", vp), ("m_out", vp), ("l_out", vp)]
 
 
 _lib = None
@@ -101,6 +104,10 @@ def load(build_if_missing: bool = True):
         lib.pio_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_key_tile.restype = C.c_int
         lib.pio_attention_key_tile.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        lib.pio_profile_enable.restype = None
+        lib.pio_profile_enable.argtypes = [C.c_int]
+        lib.pio_profile_read.restype = C.c_int
+        lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
         if lib.pio_abi_version() != 1:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
@@ -115,3 +122,19 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().pio_launch_count())
+
+
+KERNEL_FAMILIES = ("layernorm", "gemm", "softmax", "attention", "combine")
+
+
+def profile_enable(on: bool) -> None:
+    load().pio_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """Drain the library-side launch records: {family: dict(ms, flops, bytes, launches)}."""
+    n = len(KERNEL_FAMILIES)
+    buf = (C.c_double * (4 * n))()
+    check(load().pio_profile_read(buf, n), "pio_profile_read")
+    return {f: dict(ms=buf[4 * i], flops=buf[4 * i + 1], bytes=buf[4 * i + 2], launches=int(buf[4 * i + 3]))
+            for i, f in enumerate(KERNEL_FAMILIES)}

@@ -30,23 +30,24 @@ struct FlashParams {
 template <int NQC, int NVC, bool SAME>
 struct FlashCfg {
   static constexpr int KV_CHUNKS = SAME ? NQC : (NQC + NVC);
-  // smem with BN = 128 and two stages
-  static constexpr int SMEM128 = NQC * 16384 + 2 * KV_CHUNKS * 16384 + 2 * 16384;
+  static constexpr int SMEM_LIMIT = 232448 - 256;  // 227 KB minus the barrier block
+  // BN = 128 needs Q + two P buffers (2 x 32 KB) + two K/V stages in shared memory and 2 x 128 + dv columns of TMEM
+  static constexpr int SMEM128 = NQC * 16384 + 2 * 32768 + 2 * KV_CHUNKS * 16384;
   static constexpr int TMEM128 = 2 * 128 + NVC * 64;
-  static constexpr int BN = (SMEM128 <= 220 * 1024 && TMEM128 <= 512) ? 128 : 64;
+  static constexpr int BN = (SMEM128 <= SMEM_LIMIT && TMEM128 <= 512) ? 128 : 64;
   static constexpr int CHUNK_BYTES = BN * 128;            // one 64-column chunk of a K/V tile
   static constexpr int STAGE_BYTES = KV_CHUNKS * CHUNK_BYTES;
   static constexpr int Q_BYTES = NQC * 16384;
-  static constexpr int P_BYTES = (BN / 64) * 16384;
-  static constexpr int AVAIL = 224 * 1024 - Q_BYTES - P_BYTES;
+  static constexpr int P_BYTES = (BN / 64) * 16384;       // one P buffer; there are two
+  static constexpr int AVAIL = SMEM_LIMIT - Q_BYTES - 2 * P_BYTES;
   static constexpr int STAGES_RAW = AVAIL / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
   static constexpr int TMEM_NEED = 2 * BN + NVC * 64;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
-  static constexpr int SMEM_USED = Q_BYTES + P_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_USED = Q_BYTES + 2 * P_BYTES + STAGES * STAGE_BYTES + 256;
   // request > half of the SM's shared memory so that exactly one CTA is resident per SM (TMEM is not oversubscribed)
   static constexpr int SMEM_BYTES = SMEM_USED < 120 * 1024 ? 120 * 1024 : SMEM_USED;
-  static constexpr bool VALID = STAGES >= 2 && TMEM_NEED <= 512;
+  static constexpr bool VALID = STAGES >= 2 && TMEM_NEED <= 512 && SMEM_USED <= 232448;
 };
 
 template <int NQC, int NVC, bool SAME>
@@ -55,22 +56,25 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
   using Cfg = FlashCfg<NQC, NVC, SAME>;
   constexpr int BN = Cfg::BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory: the window starts 1024-aligned
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + Cfg::Q_BYTES;
-  uint8_t* sKV = sP + Cfg::P_BYTES;
+  uint8_t* sP = sQ + Cfg::Q_BYTES;                 // two P buffers (tile j uses buffer j & 1)
+  uint8_t* sKV = sP + 2 * Cfg::P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* q_full = bars;                         // [1]
   uint64_t* kv_full = bars + 1;                    // [STAGES]
   uint64_t* kv_empty = kv_full + Cfg::STAGES;      // [STAGES]
-  uint64_t* s_full = kv_empty + Cfg::STAGES;       // [2]
-  uint64_t* p_full = s_full + 2;                   // [1] softmax -> MMA (128 arrivals)
-  uint64_t* pv_done = p_full + 1;                  // [1] MMA -> softmax
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_full = kv_empty + Cfg::STAGES;       // [2]  S_j ready            (MMA -> softmax)
+  uint64_t* p_full = s_full + 2;                   // [2]  P_j written          (softmax -> MMA, 128 arrivals)
+  uint64_t* pv_done = p_full + 2;                  // [2]  O += P_j V_j retired (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("pio_flash_kernel: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   const int q0 = blockIdx.x * 128;
   const int b = blockIdx.y / p.H;
   const int h = blockIdx.y % p.H;
@@ -93,8 +97,10 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -139,30 +145,35 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer =================
+      // Descriptors differ only in their 14-bit start-address field, so each is one add away from a constant.
       constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
+      const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+      const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
+      const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sKV) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES), Cfg::CHUNK_BYTES, 1024);
       auto issue_s = [&](int j, int stage) {
-        const uint32_t k_addr = smem_u32(sKV + stage * Cfg::STAGE_BYTES);
         const uint32_t d = tmem_base + (j & 1) * BN;
-        for (int ks = 0; ks < dqk_steps_total; ++ks) {
-          const int c = ks >> 2, kk = ks & 3;
-          const uint64_t da = make_smem_desc_sw128(q_addr + c * 16384 + kk * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(k_addr + c * Cfg::CHUNK_BYTES + kk * 32, 16, 1024);
-          umma_ss(d, da, db, idesc_s, ks != 0 ? 1u : 0u);
+        const uint64_t dk = dk0 + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4 * NQC; ++ks) {
+          if (ks < dqk_steps_total) {
+            const int c = ks >> 2, kk = ks & 3;
+            umma_ss(d, dq0 + (uint64_t)((c * 16384 + kk * 32) >> 4), dk + (uint64_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4),
+                    idesc_s, ks != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&s_full[j & 1]);
       };
       auto issue_pv = [&](int j, int stage) {
-        const uint32_t v_addr = smem_u32(sKV + stage * Cfg::STAGE_BYTES) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES);
+        const uint64_t dvs = dv0 + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t dpj = dp0 + (uint64_t)(((j & 1) * Cfg::P_BYTES) >> 4);
         for (int nb = 0; nb * 256 < dv_n; ++nb) {
           const int n = min(256, dv_n - nb * 256);
           const uint32_t idesc_pv = make_idesc_f16(128, n, 1, 0, /*B MN-major*/ 1);
+#pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(v_addr + nb * 4 * Cfg::CHUNK_BYTES + ks * 2048,
-                                                     Cfg::CHUNK_BYTES, 1024);
-            umma_ss(tmem_o + nb * 256, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            umma_ss(tmem_o + nb * 256, dpj + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4),
+                    dvs + (uint64_t)((nb * 4 * Cfg::CHUNK_BYTES + ks * 2048) >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
           }
         }
       };
@@ -179,13 +190,13 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (j + 1 < ntiles) {
           mbar_wait(&kv_full[nstage], nphase);
           tc_fence_after();
-          issue_s(j + 1, nstage);
+          issue_s(j + 1, nstage);   // overwrites S_{j-1}: its readers arrived on p_full before PV_{j-1} was issued
         }
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
         issue_pv(j, stage);
         umma_commit(&kv_empty[stage]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[j & 1]);
         stage = nstage;
         phase = nphase;
       }
@@ -234,12 +245,14 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         m_use = tmax;
       }
       const bool any_grow = __any_sync(0xffffffffu, grow && j > 0 && m != -INFINITY);
-      if (j > 0) {
-        // P buffer and O are free once PV_{j-1} has completed
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
+      if (j >= 2) {
+        // P buffer j&1 was last read by PV_{j-2}
+        mbar_wait(&pv_done[j & 1], ((j >> 1) - 1) & 1);
       }
       if (any_grow) {
+        // O may only be rescaled once PV_{j-1} has retired (rare: the running max grew by more than 2^8)
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
         for (int c = 0; c < dv_n; c += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_o + lane_off + c, r);
@@ -272,7 +285,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             pv[i] = ok ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -msub)) : 0.0f;
           }
         }
-        uint8_t* prow = sP + ((c * 32) >> 6) * 16384;
+        uint8_t* prow = sP + (j & 1) * Cfg::P_BYTES + ((c * 32) >> 6) * 16384;
         const int chunk0 = ((c * 32) & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -282,18 +295,21 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           w.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
           w.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
           *reinterpret_cast<uint4*>(prow + sw128_offset(row, chunk0 + g)) = w;
+          // the row sum uses the bf16-rounded values the tensor core will multiply (P and l stay consistent); they
+          // are unpacked from the packed words with integer ops so the conversion pipe is only used once
+          lsum += (__uint_as_float(w.x << 16) + __uint_as_float(w.x & 0xffff0000u)) +
+                  (__uint_as_float(w.y << 16) + __uint_as_float(w.y & 0xffff0000u));
+          lsum += (__uint_as_float(w.z << 16) + __uint_as_float(w.z & 0xffff0000u)) +
+                  (__uint_as_float(w.w << 16) + __uint_as_float(w.w & 0xffff0000u));
         }
-        // the sum uses the bf16-rounded values that the tensor core will multiply, keeping P/l consistent
-#pragma unroll
-        for (int i = 0; i < 32; ++i) lsum += __bfloat162float(__float2bfloat16_rn(pv[i]));
       }
       l += lsum;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
     // ---- epilogue ----
-    mbar_wait(pv_done, (ntiles - 1) & 1);
+    mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     const bool keep = (q < p.Nq) && (p.row_keep == nullptr || p.row_keep[(long long)b * p.stride_rk + q] != 0);
     const bool emit_partial = p.partial || p.num_splits > 1;
@@ -411,7 +427,10 @@ static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cuda
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(flash<%d,%d,%d>) failed: %s", NQC, NVC, (int)SAME,
                 cudaGetErrorString(attr_err));
   dim3 grid((a->Nq + 127) / 128, a->B * a->H, p.num_splits);
-  pio_flash_kernel<NQC, NVC, SAME><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  {
+    ProfileScope prof(KF_FLASH, 2.0 * a->B * a->H * (double)a->Nq * a->Nk * (a->dqk + a->dv), 0.0, stream);
+    pio_flash_kernel<NQC, NVC, SAME><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;

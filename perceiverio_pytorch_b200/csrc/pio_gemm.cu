@@ -2,8 +2,15 @@
 // double-buffered fp32 accumulators in TMEM -> fused epilogue (alpha, bias, exact GELU, fp32 residual, fp32 and/or
 // bf16 stores).  One CTA per SM; tile 128 x BN x 64.
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
-// warps 4..7 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, i.e. accumulator rows).
+// L2 -> SM bandwidth is the binding resource of a 128 x 256 tile (48 KB of operands per 512 tensor cycles), so CTAs are
+// launched as clusters of CL along M that work on the same N tile in lockstep: each CTA fetches 1/CL of the B tile and
+// TMA-multicasts it into every CTA of the cluster, cutting the B traffic per CTA by CL.
+//
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
+// warps 4..11 = epilogue.  Epilogue warp w owns TMEM lanes 32*(w%4) .. +31 (accumulator rows) and the column half
+// (w-4)/4 of the tile.  fp32 inputs/outputs (residual stream) go through a per-warp 32x32 shared-memory transpose
+// so that every global access is a full 128-byte row segment; bf16-only outputs are stored straight from the
+// accumulator rows (64 contiguous bytes per thread and chunk).
 #include "pio_common.cuh"
 #include "pio_host.h"
 
@@ -12,6 +19,7 @@ namespace pio {
 struct GemmEpilogue {
   int M, N, K, batch;
   int tiles_m, tiles_n;
+  int m_groups;          // ceil(tiles_m / CL): M tiles are handed out to a cluster CL at a time
   int a_bcast, b_bcast;  // operand shared by every batch entry (batch stride 0)
   const float* bias;
   int bias_mode;
@@ -34,20 +42,48 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int XPOSE_PITCH = 33;  // floats; conflict-free for row-wise writes and transposed reads
+  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * XPOSE_PITCH * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XPOSE_BYTES + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU.  erf by Abramowitz-Stegun 7.1.26 (|abs error| < 1.5e-7, far below bf16 resolution of the stored
+// activation): two MUFU ops + 8 FMAs instead of libdevice erff's ~30 instructions.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2_approx(z * z * -1.4426950408889634f);   // exp(-z^2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return fmaf(0.5f * x, erf_v, 0.5f * x);
+}
 
-template <int BN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, bool B_MN, int CL>
+__global__ void __launch_bounds__(384, 1)
 pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte aligned bases.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  // SWIZZLE_128B tiles need 1024-byte aligned bases; the kernel has no static shared memory, so the dynamic window
+  // starts at the declared alignment.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* xpose = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::XPOSE_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;   // [2]       MMA -> epilogue
@@ -56,8 +92,18 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("pio_gemm_kernel: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   const int num_k_chunks = (ep.K + Cfg::BK - 1) / Cfg::BK;
-  const int total_tiles = ep.tiles_m * ep.tiles_n * ep.batch;
+  // cluster-level tile schedule: cluster c works on (n tile, M group, batch) triples; CTA `crank` of the cluster takes
+  // M tile group*CL + crank (possibly past the end: zero-filled loads, no stores)
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
+  const int total_tiles = ep.m_groups * ep.tiles_n * ep.batch;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -66,11 +112,11 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], Cfg::EPI_WARPS * 32);
     }
     fence_mbar_init();
   }
@@ -80,6 +126,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -88,10 +135,10 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // ================= TMA producer =================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int nt = t % ep.tiles_n;
-        const int mt = (t / ep.tiles_n) % ep.tiles_m;
-        const int z = t / (ep.tiles_n * ep.tiles_m);
+        const int mt = ((t / ep.tiles_n) % ep.m_groups) * CL + crank;
+        const int z = t / (ep.tiles_n * ep.m_groups);
         const int m0 = mt * Cfg::BM, n0 = nt * BN;
         for (int kc = 0; kc < num_k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -99,12 +146,28 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * Cfg::BK, m0, ep.a_bcast ? 0 : z);
-          if constexpr (!B_MN) {
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * Cfg::BK, n0, ep.b_bcast ? 0 : z);
-          } else {
+          const int zb = ep.b_bcast ? 0 : z;
+          if constexpr (CL == 1) {
+            if constexpr (!B_MN) {
+              tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * Cfg::BK, n0, zb);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * (64 * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kc * Cfg::BK, ep.b_bcast ? 0 : z);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(sb + j * (64 * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kc * Cfg::BK, zb);
+            }
+          } else {
+            // this CTA fetches its 1/CL slice of the B tile and multicasts it to the whole cluster
+            if constexpr (!B_MN) {
+              constexpr int SL = BN / CL;  // rows of B per CTA
+              tma_load_3d_mcast(sb + crank * (SL * 128), &tmap_b, &full_bar[stage], kc * Cfg::BK, n0 + crank * SL, zb,
+                                kMask);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                if (j % CL == crank)
+                  tma_load_3d_mcast(sb + j * (64 * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kc * Cfg::BK, zb,
+                                    kMask);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -117,7 +180,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -137,7 +200,9 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             else db = make_smem_desc_sw128(sb + ks * (16 * 128), 64 * 128, 1024);
             umma_ss(d_tmem, da, db, idesc, (kc | ks) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in every CTA that multicasts into it) once these MMAs have read it
+          if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], kMask);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -146,39 +211,72 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp >= 4) {
     // ================= Epilogue =================
     const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;                 // which half of the tile's columns
+    constexpr int HALF_COLS = BN / 2;
+    float* xp = xpose + (warp - 4) * (32 * Cfg::XPOSE_PITCH);
+    const bool via_smem = (ep.residual != nullptr) || (ep.out_f32 != nullptr);
+    const bool vec32 = ((ep.ldo32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15u) == 0) &&
+                       ((ep.strideO32 & 3) == 0);
+    const bool vecr = ((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15u) == 0) &&
+                      ((ep.strideR & 3) == 0);
+    const bool vec16 = ((ep.ldo16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7u) == 0) &&
+                       ((ep.strideO16 & 3) == 0);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int nt = t % ep.tiles_n;
-      const int mt = (t / ep.tiles_n) % ep.tiles_m;
-      const int z = t / (ep.tiles_n * ep.tiles_m);
+      const int mt = ((t / ep.tiles_n) % ep.m_groups) * CL + crank;
+      const int z = t / (ep.tiles_n * ep.m_groups);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row = mt * Cfg::BM + quarter * 32 + lane;
+      const int row_base = mt * Cfg::BM + quarter * 32;
+      const int row = row_base + lane;
       const bool row_ok = row < ep.M;
+      const float* res_z = ep.residual ? ep.residual + z * ep.strideR : nullptr;
+      if (res_z != nullptr && row_ok) {
+        // pull this warp's 32 x (BN/2) residual block towards L2 while the mainloop of the tile is still running
+        const float* rrow = res_z + static_cast<long long>(row) * ep.ldr + nt * BN + half * HALF_COLS;
+#pragma unroll
+        for (int cc = 0; cc < HALF_COLS; cc += 32)
+          if (nt * BN + half * HALF_COLS + cc < ep.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + cc));
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * BN + half * HALF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const float row_bias = (ep.bias_mode == 2 && row_ok) ? __ldg(ep.bias + row) : 0.0f;
-      const float* res_row = ep.residual ? ep.residual + z * ep.strideR + static_cast<long long>(row) * ep.ldr : nullptr;
-      float* o32_row = ep.out_f32 ? ep.out_f32 + z * ep.strideO32 + static_cast<long long>(row) * ep.ldo32 : nullptr;
-      __nv_bfloat16* o16_row =
-          ep.out_bf16 ? ep.out_bf16 + z * ep.strideO16 + static_cast<long long>(row) * ep.ldo16 : nullptr;
+      float* o32_z = ep.out_f32 ? ep.out_f32 + z * ep.strideO32 : nullptr;
+      __nv_bfloat16* o16_z = ep.out_bf16 ? ep.out_bf16 + z * ep.strideO16 : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = nt * BN + c * 32;
+      for (int c = 0; c < HALF_COLS / 32; ++c) {
+        const int col0 = nt * BN + half * HALF_COLS + c * 32;
         if (col0 >= ep.N) break;  // warp-uniform
+        const bool full = (col0 + 32 <= ep.N);
+        // residual for this chunk, in the transposed mapping (lane -> 4 columns of rows i*4 + lane/8): all eight
+        // 16-byte loads are issued up front so their HBM latency overlaps the TMEM read, the math and the transpose
+        const bool res_fast = via_smem && res_z != nullptr && vecr && full;
+        float4 resv[8];
+        if (res_fast) {
+          const float* rp0 = res_z + static_cast<long long>(row_base + (lane >> 3)) * ep.ldr + col0 + (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = row_base + i * 4 + (lane >> 3) < ep.M;
+            resv[i] = ok ? __ldg(reinterpret_cast<const float4*>(rp0 + static_cast<long long>(i * 4) * ep.ldr))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_wait_ld();
-        if (row_ok) {
-        const bool full = (col0 + 32 <= ep.N);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha + row_bias;
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ep.alpha, row_bias);
         if (ep.bias_mode == 1) {
-          if (full) {
+          if (full && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15u) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + col0 + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+              v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -189,51 +287,82 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (res_row) {
-          const float* rp = res_row + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+        if (!via_smem) {
+          // bf16-only output: 64 contiguous bytes per thread
+          if (row_ok) {
+            __nv_bfloat16* op = o16_z + static_cast<long long>(row) * ep.ldo16 + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+              for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                reinterpret_cast<uint4*>(op)[j] = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.N) op[j] = __float2bfloat16_rn(v[j]);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < ep.N) v[j] += __ldg(rp + j);
           }
-        }
-        if (o32_row) {
-          float* op = o32_row + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+        } else {
+          // transpose the warp's 32x32 block through shared memory: afterwards lane l holds 4 consecutive columns
+          // (l%8)*4.. of rows i*4 + l/8, so a warp instruction touches 4 rows x 128 contiguous bytes
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+          for (int j = 0; j < 32; ++j) xp[lane * Cfg::XPOSE_PITCH + j] = v[j];
+          __syncwarp();
+          const int cq = (lane & 7) * 4;
+          const int gcol = col0 + cq;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < ep.N) op[j] = v[j];
-          }
-        }
-        if (o16_row) {
-          __nv_bfloat16* op = o16_row + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-              q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              reinterpret_cast<uint4*>(op)[j] = q;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            const int grow = row_base + rr;
+            float4 w;
+            w.x = xp[rr * Cfg::XPOSE_PITCH + cq];
+            w.y = xp[rr * Cfg::XPOSE_PITCH + cq + 1];
+            w.z = xp[rr * Cfg::XPOSE_PITCH + cq + 2];
+            w.w = xp[rr * Cfg::XPOSE_PITCH + cq + 3];
+            if (grow < ep.M && gcol < ep.N) {
+              const bool quad = gcol + 4 <= ep.N;
+              if (res_fast) {
+                w.x += resv[i].x; w.y += resv[i].y; w.z += resv[i].z; w.w += resv[i].w;
+              } else if (res_z) {
+                const float* rp = res_z + static_cast<long long>(grow) * ep.ldr + gcol;
+                {
+                  w.x += __ldg(rp);
+                  if (gcol + 1 < ep.N) w.y += __ldg(rp + 1);
+                  if (gcol + 2 < ep.N) w.z += __ldg(rp + 2);
+                  if (gcol + 3 < ep.N) w.w += __ldg(rp + 3);
+                }
+              }
+              if (o32_z) {
+                float* op = o32_z + static_cast<long long>(grow) * ep.ldo32 + gcol;
+                if (quad && vec32) {
+                  *reinterpret_cast<float4*>(op) = w;
+                } else {
+                  op[0] = w.x;
+                  if (gcol + 1 < ep.N) op[1] = w.y;
+                  if (gcol + 2 < ep.N) op[2] = w.z;
+                  if (gcol + 3 < ep.N) op[3] = w.w;
+                }
+              }
+              if (o16_z) {
+                __nv_bfloat16* op = o16_z + static_cast<long long>(grow) * ep.ldo16 + gcol;
+                if (quad && vec16) {
+                  *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+                } else {
+                  op[0] = __float2bfloat16_rn(w.x);
+                  if (gcol + 1 < ep.N) op[1] = __float2bfloat16_rn(w.y);
+                  if (gcol + 2 < ep.N) op[2] = __float2bfloat16_rn(w.z);
+                  if (gcol + 3 < ep.N) op[3] = __float2bfloat16_rn(w.w);
+                }
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < ep.N) op[j] = __float2bfloat16_rn(v[j]);
           }
+          __syncwarp();
         }
-        }  // row_ok
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -243,13 +372,14 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into / arrive on it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool B_MN>
+template <int BN, bool B_MN, int CL>
 static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
@@ -266,7 +396,7 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   if (!B_MN) {
     const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, b_batch};
     const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(b_batch > 1 ? a->strideB : a->ldb * (int64_t)a->N) * 2};
-    const uint32_t box[3] = {64, (uint32_t)BN, 1};
+    const uint32_t box[3] = {64, (uint32_t)(BN / CL), 1};
     int rc = encode_tmap_bf16(&tb, a->B, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   } else {
@@ -281,6 +411,7 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   ep.a_bcast = a_bcast ? 1 : 0; ep.b_bcast = b_bcast ? 1 : 0;
   ep.tiles_m = (a->M + 127) / 128;
   ep.tiles_n = (a->N + BN - 1) / BN;
+  ep.m_groups = (ep.tiles_m + CL - 1) / CL;
   ep.bias = a->bias; ep.bias_mode = a->bias ? a->bias_mode : 0;
   ep.act = a->act; ep.alpha = a->alpha;
   ep.residual = a->residual; ep.ldr = a->ldr; ep.strideR = a->strideR;
@@ -290,17 +421,32 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(pio_gemm_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(pio_gemm_kernel<BN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(gemm<%d>) failed: %s", BN, cudaGetErrorString(attr_err));
 
-  const long long total = (long long)ep.tiles_m * ep.tiles_n * ep.batch;
-  int ctas = dev.sm_count;
-  if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
-  if (total < ctas) ctas = (int)total;
-  pio_gemm_kernel<BN, B_MN><<<ctas, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep);
+  const long long total = (long long)ep.m_groups * ep.tiles_n * ep.batch;  // cluster-level tiles
+  int clusters = dev.sm_count / CL;
+  if (a->max_ctas > 0 && a->max_ctas / CL < clusters) clusters = a->max_ctas / CL > 0 ? a->max_ctas / CL : 1;
+  if (total < clusters) clusters = (int)total;
+  {
+    ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, 0.0, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PIO_CUDA_OK(cudaLaunchKernelEx(&cfg, pio_gemm_kernel<BN, B_MN, CL>, ta, tb, ep));
+  }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;
@@ -330,18 +476,30 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   if (dev.cc_major != 10) return fail(PIO_ERR_ARCH, "pio_gemm_bf16 needs sm_100 (got sm_%d%d)", dev.cc_major, dev.cc_minor);
   int bn = a->tile_n;
   if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  // cluster width along M: multicast pays when there are at least two M tiles to pair up
+  int cl = a->cluster_m;
+  if (cl == 0) cl = (a->M > 128) ? 2 : 1;
+  PIO_REQUIRE(cl == 1 || cl == 2 || cl == 4, "pio_gemm_bf16: cluster_m must be 0, 1, 2 or 4 (got %d)", a->cluster_m);
+  if (cl == 4 && bn == 64 && a->b_mn_major) cl = 2;  // a 64-column MN-major tile is a single TMA box
+#define PIO_GEMM_DISPATCH(BN_, MN_)                                            \
+  switch (cl) {                                                                \
+    case 1: return launch_gemm<BN_, MN_, 1>(a, dev, stream);                   \
+    case 2: return launch_gemm<BN_, MN_, 2>(a, dev, stream);                   \
+    case 4: return launch_gemm<BN_, MN_, 4>(a, dev, stream);                   \
+  }
   if (a->b_mn_major) {
     switch (bn) {
-      case 256: return launch_gemm<256, true>(a, dev, stream);
-      case 128: return launch_gemm<128, true>(a, dev, stream);
-      case 64: return launch_gemm<64, true>(a, dev, stream);
+      case 256: PIO_GEMM_DISPATCH(256, true) break;
+      case 128: PIO_GEMM_DISPATCH(128, true) break;
+      case 64: if (cl == 4) cl = 2; PIO_GEMM_DISPATCH(64, true) break;
     }
   } else {
     switch (bn) {
-      case 256: return launch_gemm<256, false>(a, dev, stream);
-      case 128: return launch_gemm<128, false>(a, dev, stream);
-      case 64: return launch_gemm<64, false>(a, dev, stream);
+      case 256: PIO_GEMM_DISPATCH(256, false) break;
+      case 128: PIO_GEMM_DISPATCH(128, false) break;
+      case 64: PIO_GEMM_DISPATCH(64, false) break;
     }
   }
+#undef PIO_GEMM_DISPATCH
   return fail(PIO_ERR_INVALID_ARGUMENT, "pio_gemm_bf16: tile_n must be 0, 64, 128 or 256 (got %d)", a->tile_n);
 }

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <vector>
+
 namespace pio {
 
 thread_local char g_last_error[512] = "";
@@ -28,6 +30,30 @@ int get_device_info(DeviceInfo* out) {
   }
   *out = cache[dev];
   return PIO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// profiling
+// ---------------------------------------------------------------------------------------------------------
+struct ProfRecord { int family; double flops, bytes; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfileScope::ProfileScope(int family, double flops, double bytes, cudaStream_t stream)
+    : family_(family), flops_(flops), bytes_(bytes), stream_(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess) return;
+  on_ = true;
+  cudaEventRecord(e0_, stream_);
+}
+ProfileScope::~ProfileScope() {
+  if (!on_) return;
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess) return;
+  cudaEventRecord(e1, stream_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back({family_, flops_, bytes_, e0_, e1});
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -83,6 +109,30 @@ extern "C" {
 int pio_abi_version(void) { return PIO_ABI_VERSION; }
 const char* pio_last_error(void) { return pio::g_last_error; }
 int64_t pio_launch_count(void) { return pio::g_launch_count.load(); }
+
+void pio_profile_enable(int on) { pio::g_prof_on.store(on ? 1 : 0); }
+
+// Drains the recorded launches: out[f*4 + {0,1,2,3}] = {milliseconds, flops, bytes, launches} per kernel family
+// (pio::KernelFamily order: layernorm, gemm, softmax, attention, combine).  Synchronises on the recorded events.
+int pio_profile_read(double* out, int n_families) {
+  using namespace pio;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (int i = 0; i < n_families * 4; ++i) out[i] = 0.0;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.e1);
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.family < n_families) {
+      out[r.family * 4 + 0] += ms;
+      out[r.family * 4 + 1] += r.flops;
+      out[r.family * 4 + 2] += r.bytes;
+      out[r.family * 4 + 3] += 1.0;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return PIO_OK;
+}
 
 int pio_check_device(void) {
   pio::DeviceInfo d;

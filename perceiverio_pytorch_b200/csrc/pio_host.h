@@ -53,6 +53,20 @@ int get_device_info(DeviceInfo* out);
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 entries, for dims[1..] */, const uint32_t* box);
 
+// Optional per-launch profiling: when enabled (pio_profile_enable), every entry point brackets its kernel launch
+// with CUDA events recorded on the launching stream *inside* the library, so the interval contains the kernel and
+// nothing of the host-side Python gap.  Not usable during stream capture.
+enum KernelFamily { KF_LAYERNORM = 0, KF_GEMM = 1, KF_SOFTMAX = 2, KF_FLASH = 3, KF_COMBINE = 4, KF_COUNT = 5 };
+struct ProfileScope {
+  ProfileScope(int family, double flops, double bytes, cudaStream_t stream);
+  ~ProfileScope();
+  int family_;
+  double flops_, bytes_;
+  cudaStream_t stream_;
+  cudaEvent_t e0_ = nullptr;
+  bool on_ = false;
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace pio

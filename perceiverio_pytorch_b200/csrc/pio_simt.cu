@@ -17,48 +17,116 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// LayerNorm + cast.  One warp per row, the row lives in registers (C <= 32 * MAXV), two-pass statistics.
-// Lane l owns columns l, l+32, ... so that loads and bf16 stores are coalesced for any C (261, 322, 1026 ...).
+// LayerNorm + cast.  One warp per row, the row lives in registers, two-pass statistics (mean, then centred
+// variance).  Two layouts:
+//  * vector path (C % 4 == 0, 16-byte aligned rows: the 512/768/1024/1280-channel latent arrays): lane l owns the
+//    float4 at columns 4*(l + 32 i); 16-byte loads, 8-byte bf16x4 stores, <= 64 registers so 32 warps per SM keep
+//    >= 100 KB of loads in flight per SM;
+//  * scalar path (odd widths 261 / 322 / 1026): lane l owns columns l + 32 i (coalesced for any C and any row
+//    alignment) and each warp works on ROWS rows at once to double the loads in flight.
 // ------------------------------------------------------------------------------------------------------------
-template <int MAXV>
-__global__ void __launch_bounds__(256) pio_layernorm_kernel(const float* __restrict__ x, long long ldx,
+template <int NV>
+__global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __restrict__ x, long long ldx,
+                                                                __nv_bfloat16* __restrict__ y, long long ldy,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, long long rows, int C,
+                                                                int normalize, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int nvec = C >> 2;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < nvec) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (normalize) {
+    mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c2 * c2 + d * d);
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  }
+  uint2* yr = reinterpret_cast<uint2*>(y + row * ldy);
+  const int nvec_out = (int)(ldy >> 2);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec_out) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nvec) {
+        o.x = (v[i].x - mean) * rstd; o.y = (v[i].y - mean) * rstd;
+        o.z = (v[i].z - mean) * rstd; o.w = (v[i].w - mean) * rstd;
+        if (gamma) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+          o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+        }
+        if (beta) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+      }
+      yr[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+template <int MAXV, int ROWS>
+__global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restrict__ x, long long ldx,
                                                             __nv_bfloat16* __restrict__ y, long long ldy,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows, int C,
                                                             int normalize, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long warps_per_grid = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
-       row += warps_per_grid) {
-    const float* xr = x + row * ldx;
-    float v[MAXV];
-    float s = 0.f;
+  const long long row0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
+  float v[ROWS][MAXV];
+  float s[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const bool rok = row0 + r < rows;
+    const float* xr = x + (row0 + r) * ldx;
+    s[r] = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + 32 * i;
-      v[i] = (c < C) ? __ldg(xr + c) : 0.f;
-      s += v[i];
+      v[r][i] = (rok && c < C) ? __ldg(xr + c) : 0.f;
+      s[r] += v[r][i];
     }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= rows) break;  // warp-uniform
     float mean = 0.f, rstd = 1.f;
     if (normalize) {
-      mean = warp_sum(s) / (float)C;
+      mean = warp_sum(s[r]) / (float)C;
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = lane + 32 * i;
-        const float d = (c < C) ? v[i] - mean : 0.f;
+        const float d = (c < C) ? v[r][i] - mean : 0.f;
         q += d * d;
       }
       rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     }
-    __nv_bfloat16* yr = y + row * ldy;
+    __nv_bfloat16* yr = y + (row0 + r) * ldy;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < ldy) {
         float o = 0.f;
         if (c < C) {
-          o = (v[i] - mean) * rstd;
+          o = (v[r][i] - mean) * rstd;
           if (gamma) o = o * __ldg(gamma + c);
           if (beta) o += __ldg(beta + c);
         }
@@ -136,28 +204,50 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
   const int q = (int)(row % a.Nq);
   const int h = (int)((row / a.Nq) % a.H);
   const int b = (int)(row / ((long long)a.Nq * a.H));
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.O) + (long long)b * a.strideO + (long long)q * a.ldo +
-                     (long long)h * a.dv;
+  const long long so = a.part_stride_O ? a.part_stride_O : rows * a.dv;
+  const long long sm = a.part_stride_ml ? a.part_stride_ml : rows;
   const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + q] != 0 : true;
   float M = -INFINITY;
-  for (int p = 0; p < a.parts; ++p) M = fmaxf(M, __ldg(a.m_part + p * rows + row));
-  if (!keep || M == -INFINITY) {
-    for (int c = lane; c < a.dv; c += 32) o[c] = __float2bfloat16_rn(0.f);
-    return;
-  }
+  for (int p = 0; p < a.parts; ++p) M = fmaxf(M, __ldg(a.m_part + p * sm + row));
   float L = 0.f;
-  for (int p = 0; p < a.parts; ++p) {
-    const float mp = __ldg(a.m_part + p * rows + row);
-    if (mp != -INFINITY) L += __ldg(a.l_part + p * rows + row) * __expf(mp - M);
-  }
-  const float inv = 1.0f / L;
-  for (int c = lane; c < a.dv; c += 32) {
-    float acc = 0.f;
+  if (M != -INFINITY) {
     for (int p = 0; p < a.parts; ++p) {
-      const float mp = __ldg(a.m_part + p * rows + row);
-      if (mp != -INFINITY) acc += __ldg(a.O_part + (p * rows + row) * a.dv + c) * __expf(mp - M);
+      const float mp = __ldg(a.m_part + p * sm + row);
+      if (mp != -INFINITY) L += __ldg(a.l_part + p * sm + row) * __expf(mp - M);
     }
-    o[c] = __float2bfloat16_rn(acc * inv);
+  }
+  if (a.O_out_part) {  // merged, still un-normalised partial (referenced to M)
+    if (lane == 0) {
+      a.m_out[row] = M;
+      a.l_out[row] = L;
+    }
+    for (int c = lane; c < a.dv; c += 32) {
+      float acc = 0.f;
+      if (M != -INFINITY) {
+        for (int p = 0; p < a.parts; ++p) {
+          const float mp = __ldg(a.m_part + p * sm + row);
+          if (mp != -INFINITY) acc += __ldg(a.O_part + p * so + row * a.dv + c) * __expf(mp - M);
+        }
+      }
+      a.O_out_part[row * a.dv + c] = acc;
+    }
+  }
+  if (a.O) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.O) + (long long)b * a.strideO + (long long)q * a.ldo +
+                       (long long)h * a.dv;
+    if (!keep || M == -INFINITY || !(L > 0.f)) {
+      for (int c = lane; c < a.dv; c += 32) o[c] = __float2bfloat16_rn(0.f);
+      return;
+    }
+    const float inv = 1.0f / L;
+    for (int c = lane; c < a.dv; c += 32) {
+      float acc = 0.f;
+      for (int p = 0; p < a.parts; ++p) {
+        const float mp = __ldg(a.m_part + p * sm + row);
+        if (mp != -INFINITY) acc += __ldg(a.O_part + p * so + row * a.dv + c) * __expf(mp - M);
+      }
+      o[c] = __float2bfloat16_rn(acc * inv);
+    }
   }
 }
 
@@ -173,21 +263,38 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   DeviceInfo dev;
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
-  const int warps_per_block = 8;
-  long long blocks = (a->rows + warps_per_block - 1) / warps_per_block;
-  const long long max_blocks = (long long)dev.sm_count * 32;
-  if (blocks > max_blocks) blocks = max_blocks;
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a->y);
-#define PIO_LN_LAUNCH(MAXV)                                                                                      \
-  pio_layernorm_kernel<MAXV><<<(unsigned)blocks, 256, 0, stream>>>(a->x, a->ldx, y, a->ldy, a->gamma, a->beta, \
-                                                                   a->rows, a->C, a->normalize, a->eps)
-  const int need = (int)((a->ldy + 31) / 32);
-  if (need <= 4) PIO_LN_LAUNCH(4);
-  else if (need <= 12) PIO_LN_LAUNCH(12);
-  else if (need <= 24) PIO_LN_LAUNCH(24);
-  else if (need <= 40) PIO_LN_LAUNCH(40);
-  else PIO_LN_LAUNCH(64);
+  ProfileScope prof(KF_LAYERNORM, 0.0, (double)a->rows * (4.0 * a->C + 2.0 * a->ldy), stream);
+  const bool vec = (a->C % 4 == 0) && (a->ldx % 4 == 0) && aligned16(a->x) && aligned16(a->y) &&
+                   (!a->gamma || aligned16(a->gamma)) && (!a->beta || aligned16(a->beta));
+  if (vec) {
+    const long long blocks = (a->rows + 3) / 4;
+    PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
+    const int need = (int)((a->ldy / 4 + 31) / 32);
+#define PIO_LNV_LAUNCH(NV)                                                                                        \
+  pio_layernorm_vec_kernel<NV><<<(unsigned)blocks, 128, 0, stream>>>(a->x, a->ldx, y, a->ldy, a->gamma, a->beta, \
+                                                                     a->rows, a->C, a->normalize, a->eps)
+    if (need <= 2) PIO_LNV_LAUNCH(2);
+    else if (need <= 4) PIO_LNV_LAUNCH(4);
+    else if (need <= 8) PIO_LNV_LAUNCH(8);
+    else if (need <= 12) PIO_LNV_LAUNCH(12);
+    else PIO_LNV_LAUNCH(16);
+#undef PIO_LNV_LAUNCH
+  } else {
+    const int need = (int)((a->ldy + 31) / 32);
+    const int rows_per_warp = need <= 12 ? 2 : 1;
+    const long long blocks = (a->rows + 4 * rows_per_warp - 1) / (4 * rows_per_warp);
+    PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
+#define PIO_LN_LAUNCH(MAXV, ROWS)                                                                                      \
+  pio_layernorm_kernel<MAXV, ROWS><<<(unsigned)blocks, 128, 0, stream>>>(a->x, a->ldx, y, a->ldy, a->gamma, a->beta, \
+                                                                         a->rows, a->C, a->normalize, a->eps)
+    if (need <= 4) PIO_LN_LAUNCH(4, 2);
+    else if (need <= 12) PIO_LN_LAUNCH(12, 2);
+    else if (need <= 24) PIO_LN_LAUNCH(24, 1);
+    else if (need <= 40) PIO_LN_LAUNCH(40, 1);
+    else PIO_LN_LAUNCH(64, 1);
 #undef PIO_LN_LAUNCH
+  }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;
@@ -201,7 +308,10 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
               "pio_softmax_bf16: bad shape");
   const long long blocks = (long long)a->batch * a->rows;
   PIO_REQUIRE(blocks < (1ll << 31), "pio_softmax_bf16: too many rows");
-  pio_softmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+  {
+    ProfileScope prof(KF_SOFTMAX, 0.0, (double)blocks * (4.0 * a->cols + 2.0 * a->ldp), stream);
+    pio_softmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+  }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;
@@ -210,11 +320,15 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
 extern "C" int pio_attention_combine(const pio_combine_args* a, void* stream_) {
   using namespace pio;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PIO_REQUIRE(a && a->O_part && a->m_part && a->l_part && a->O, "pio_attention_combine: null pointer");
+  PIO_REQUIRE(a && a->O_part && a->m_part && a->l_part, "pio_attention_combine: null pointer");
+  PIO_REQUIRE(a->O || (a->O_out_part && a->m_out && a->l_out), "pio_attention_combine: no output");
   PIO_REQUIRE(a->parts > 0 && a->B > 0 && a->H > 0 && a->Nq > 0 && a->dv > 0, "pio_attention_combine: bad shape");
   const long long rows = (long long)a->B * a->H * a->Nq;
   const long long blocks = (rows + 7) / 8;
-  pio_combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+  {
+    ProfileScope prof(KF_COMBINE, 0.0, (double)rows * a->parts * (a->dv + 2) * 4.0 + (double)rows * a->dv * 2.0, stream);
+    pio_combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+  }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;

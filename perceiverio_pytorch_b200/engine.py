@@ -140,21 +140,29 @@ def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, N
     return O
 
 
-def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv) -> int:
-    """Key-axis splits so that a small (batch x heads x query tiles) grid still fills the 148 SMs."""
-    if ENCODER_KEY_SPLITS > 0:
-        want = ENCODER_KEY_SPLITS
-    else:
-        ctas = B * H * ((Nq + 127) // 128)
-        if ctas >= 120 or Nk < 4096:
-            return 1
-        want = max(1, min(32, 148 // ctas))
+def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv, sm_count: int = 148) -> int:
+    """Key-axis splits inside one GPU: fill the SMs when (batch x heads x query tiles) is small, and trim the
+    partial last wave otherwise (256 CTAs on 148 SMs waste 14 % of the machine; 4 x 256 waste 1 %)."""
     bn = ops._lib.load().pio_attention_key_tile(dqk, dv, 1 if same_kv else 0)
     tiles = (Nk + bn - 1) // bn
-    want = min(want, tiles)
-    while want > 1 and (want - 1) * ((tiles + want - 1) // want) >= tiles:
-        want -= 1
-    return want
+    if ENCODER_KEY_SPLITS > 0:
+        cands = [min(ENCODER_KEY_SPLITS, tiles)]
+    else:
+        if Nk < 4096:
+            return 1
+        cands = range(1, 33)
+    ctas = B * H * ((Nq + 127) // 128)
+    best, best_eff = 1, 0.0
+    for s in cands:
+        if s > tiles or tiles // s < 8:
+            continue
+        if s > 1 and (s - 1) * ((tiles + s - 1) // s) >= tiles:
+            continue  # would leave an empty split
+        waves = -(-ctas * s // sm_count)
+        eff = ctas * s / (waves * sm_count)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
 
 
 def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv, scale, key_mask=None,

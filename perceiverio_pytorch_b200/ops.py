@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+GEMM_CLUSTER_M = 0   # 0 = library default; tests / bench can force 1, 2 or 4
 
 
 def pad8(n: int) -> int:
@@ -58,7 +59,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          residual: Optional[torch.Tensor] = None, ldr: int = 0, strideR: int = 0,
          out_f32: Optional[torch.Tensor] = None, ldo32: int = 0, strideO32: int = 0,
          out_bf16: Optional[torch.Tensor] = None, ldo16: int = 0, strideO16: int = 0,
-         tile_n: int = 0, max_ctas: int = 0) -> None:
+         tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
     assert A.dtype == BF16 and B.dtype == BF16
@@ -67,7 +68,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
     a = _lib.GemmArgs(_ptr(A), lda, strideA, _ptr(B), ldb, strideB, 1 if b_mn_major else 0,
                       M, N, K, batch, _ptr(bias), bias_mode if bias is not None else 0, act, alpha,
                       _ptr(residual), ldr, strideR, _ptr(out_f32), ldo32, strideO32,
-                      _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas)
+                      _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas,
+                      GEMM_CLUSTER_M if cluster_m is None else cluster_m)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 
@@ -140,16 +142,22 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
 
 
 def attention_combine(Op: torch.Tensor, mp: torch.Tensor, lp: torch.Tensor, *,
-                      row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Merge partials [parts, B, H, Nq, dv] -> O bf16 [B, Nq, pad8(H*dv)]."""
+                      row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      part_stride_O: int = 0, part_stride_ml: int = 0, shape=None,
+                      merged_out=None, normalised: bool = True):
+    """Merge partials -> O bf16 [B, Nq, pad8(H*dv)] and/or a merged un-normalised partial.
+
+    Op/mp/lp are [parts, B, H, Nq, dv] / [parts, B, H, Nq] tensors, or flat buffers with explicit part strides and
+    `shape=(parts, B, H, Nq, dv)`.  `merged_out=(O, m, l)` (fp32 [B,H,Nq,dv] / [B,H,Nq]) receives the merged partial."""
     _need_cuda(Op, mp, lp, row_keep)
-    parts, b, h, nq, dv = Op.shape
-    assert Op.is_contiguous() and mp.is_contiguous() and lp.is_contiguous()
+    parts, b, h, nq, dv = Op.shape if shape is None else shape
     ldo = pad8(h * dv)
-    if out is None:
+    if out is None and normalised:
         out = torch.empty((b, nq, ldo), dtype=BF16, device=Op.device)
-    a = _lib.CombineArgs(_ptr(Op), _ptr(mp), _ptr(lp), parts, b, h, nq, dv,
+    mo = merged_out if merged_out is not None else (None, None, None)
+    a = _lib.CombineArgs(_ptr(Op), _ptr(mp), _ptr(lp), part_stride_O, part_stride_ml, parts, b, h, nq, dv,
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
-                         _ptr(out), ldo, out.stride(0))
+                         _ptr(out), ldo, out.stride(0) if out is not None else 0,
+                         _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]))
     _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
     return out

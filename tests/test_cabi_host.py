@@ -24,7 +24,7 @@ def _header():
 
 
 def test_library_exports_every_declared_symbol(lib):
-    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(pio_\w+)\s*\(", _header(), flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(pio_\w+)\s*\(", _header(), flags=re.M))
     from perceiverio_pytorch_b200 import _lib
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for sym in declared:

@@ -7,7 +7,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["env", "ln", "gemm_k", "gemm_mn", "gemm_epi", "softmax", "flash", "combine"]
+GROUPS = ["env", "ln", "gemm_k", "gemm_mn", "gemm_epi", "gemm_cluster", "softmax", "flash", "combine"]
 
 
 def _err(got, ref):
@@ -55,7 +55,7 @@ def group_ln():
     print("cast-only:", _err(y[:, :100].float(), x))
 
 
-def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha=1.0, residual=False, f32=True, bf16=False, verbose_map=False):
+def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha=1.0, residual=False, f32=True, bf16=False, verbose_map=False, cluster_m=None):
     import torch
     from perceiverio_pytorch_b200 import ops
     ld_k = ops.pad8(K)
@@ -96,7 +96,8 @@ def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha
     o16 = torch.zeros(batch, M, ld16, dtype=torch.bfloat16, device="cuda") if bf16 else None
     ops.gemm(A, Bm, M=M, N=N, K=K, batch=batch, b_mn_major=b_mn, strideA=M * ld_k, strideB=strideB, lda=ld_k, ldb=ldb,
              bias=bias, bias_mode=bias_mode, act=act, alpha=alpha, residual=res, ldr=N, strideR=M * N,
-             out_f32=o32, ldo32=N, strideO32=M * N, out_bf16=o16, ldo16=ld16, strideO16=M * ld16, tile_n=tile_n)
+             out_f32=o32, ldo32=N, strideO32=M * N, out_bf16=o16, ldo16=ld16, strideO16=M * ld16, tile_n=tile_n,
+             cluster_m=cluster_m)
     torch.cuda.synchronize()
     msgs = []
     ok = True
@@ -112,7 +113,7 @@ def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha
         good = e[1] < 1e-2
         ok &= good
         msgs.append(f"bf16 abs {e[0]:.3e} rel {e[1]:.3e}")
-    print(f"gemm M={M} N={N} K={K} b={batch} mn={int(b_mn)} tn={tile_n} bias={bias_mode} act={act} res={int(residual)}: "
+    print(f"gemm M={M} N={N} K={K} b={batch} mn={int(b_mn)} tn={tile_n} cl={cluster_m} bias={bias_mode} act={act} res={int(residual)}: "
           + "; ".join(msgs) + (" OK" if ok else " FAIL"), flush=True)
     return ok
 
@@ -148,6 +149,86 @@ def group_gemm_epi():
     _gemm_case(300, 322, 512, bias_mode=2, alpha=0.25, f32=True, bf16=True)
     _gemm_case(1000, 1000, 1024, bias_mode=1, f32=True)
     _gemm_case(100, 2, 322, bias_mode=1, f32=True)
+
+
+def group_gemm_cluster():
+    for cl in (1, 2, 4):
+        _gemm_case(256, 256, 64, cluster_m=cl, verbose_map=True)
+        _gemm_case(1000, 1000, 1024, cluster_m=cl, bias_mode=1, residual=True, bf16=True)
+        _gemm_case(333, 261, 261, cluster_m=cl)
+        _gemm_case(640, 64, 200, cluster_m=cl, tile_n=64)
+        _gemm_case(640, 128, 200, cluster_m=cl, tile_n=128, batch=3)
+        _gemm_case(700, 704, 1000, b_mn=True, cluster_m=cl)
+        _gemm_case(300, 64, 300, b_mn=True, cluster_m=cl, tile_n=64, batch=2)
+        _gemm_case(4096, 3072, 1024, cluster_m=cl)
+
+
+def _time(fn, iters=20):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def group_perf():
+    """Micro-benchmarks of the hot kernels at the ImageNet-recipe shapes (B=64)."""
+    import torch
+    from perceiverio_pytorch_b200 import ops
+    dev = "cuda"
+    M = 32768
+    x = torch.randn(M, 1024, device=dev)
+    g = torch.randn(1024, device=dev)
+    t = _time(lambda: ops.layernorm_bf16(x, g, g))
+    print(f"layernorm 32768x1024: {t * 1e3:.1f} us  {M * 1024 * 6 / t / 1e6:.0f} GB/s")
+    xi = torch.randn(8 * 50176, 261, device=dev)
+    gi = torch.randn(261, device=dev)
+    t = _time(lambda: ops.layernorm_bf16(xi, gi, gi), 5)
+    print(f"layernorm {xi.shape[0]}x261: {t * 1e3:.1f} us  {xi.shape[0] * (261 * 4 + 264 * 2) / t / 1e6:.0f} GB/s")
+    A = torch.randn(M, 1024, device=dev).to(torch.bfloat16)
+    res = torch.randn(M, 1024, device=dev)
+    bias = torch.randn(3072, device=dev)
+    for N in (1024, 3072):
+        W = torch.randn(N, 1024, device=dev).to(torch.bfloat16)
+        o16 = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        o32 = torch.empty(M, N, device=dev)
+        for cl in (1, 2, 4):
+            for tn in (256, 128):
+                t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, out_bf16=o16, ldo16=N, cluster_m=cl, tile_n=tn))
+                line = f"gemm {M}x{N}x1024 cl={cl} tn={tn}: bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+                if N == 1024:
+                    t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, residual=res, ldr=N, out_f32=o32, ldo32=N,
+                                               cluster_m=cl, tile_n=tn))
+                    line += f"; fp32 residual in/out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+                    t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, act=1, out_bf16=o16, ldo16=N,
+                                               cluster_m=cl, tile_n=tn))
+                    line += f"; gelu bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+                print(line, flush=True)
+    t = _time(lambda: torch.matmul(A, W.t()))
+    print(f"torch.matmul (cuBLAS) {M}x3072x1024: {2 * M * 3072 * 1024 / t / 1e9:.0f} TF/s")
+    # tower attention 64 x 8 heads x 512 x 512 x 128
+    qkv = torch.randn(64 * 512, 3072, device=dev).to(torch.bfloat16)
+    f = lambda: ops.attention_fwd(qkv, qkv[:, 1024:], qkv[:, 2048:], B=64, H=8, Nq=512, Nk=512, dqk=128, dv=128,
+                                  strideQ=512 * 3072, strideK=512 * 3072, strideV=512 * 3072, ldq=3072, ldk=3072, ldv=3072)
+    qv, kv_, vv = qkv.view(-1), qkv.view(-1)[1024:], qkv.view(-1)[2048:]
+    f = lambda: ops.attention_fwd(qv, kv_, vv, B=64, H=8, Nq=512, Nk=512, dqk=128, dv=128,
+                                  strideQ=512 * 3072, strideK=512 * 3072, strideV=512 * 3072, ldq=3072, ldk=3072, ldv=3072)
+    t = _time(f)
+    print(f"tower attention 64x8x512x512x128: {t * 1e3:.1f} us  {4 * 64 * 8 * 512 * 512 * 128 / t / 1e9:.0f} TF/s")
+    # encoder attention (folded): 64 x 512 x 50176 x 261
+    B = 16
+    kvn = torch.randn(B * 50176, 264, device=dev).to(torch.bfloat16)
+    qf = torch.randn(512, 264, device=dev).to(torch.bfloat16)
+    f = lambda: ops.attention_fwd(qf.view(-1), kvn.view(-1), kvn.view(-1), B=B, H=1, Nq=512, Nk=50176, dqk=261, dv=261,
+                                  strideQ=0, strideK=50176 * 264, strideV=50176 * 264, ldq=264, ldk=264, ldv=264)
+    t = _time(f, 5)
+    print(f"encoder attention {B}x512x50176x261: {t * 1e3:.1f} us  {4 * B * 512 * 50176 * 261 / t / 1e9:.0f} TF/s "
+          f"(K/V read once = {B * 50176 * 264 * 2 / t / 1e6:.0f} GB/s)")
 
 
 def group_softmax():
