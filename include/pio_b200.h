@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 1
+#define PIO_ABI_VERSION 2
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -64,7 +64,9 @@ typedef struct pio_layernorm_args {
 int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Batched GEMM with fused epilogue on tcgen05 tensor cores (TMA-staged operands, TMEM accumulators):
+ * Batched GEMM with fused epilogue on tcgen05 tensor cores (TMA-staged operands, TMEM accumulators).  Large
+ * problems run on CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, residual prefetched and results stored by
+ * TMA); small or oddly laid out ones on a single-CTA kernel with 128 x {64,128,256} tiles:
  *   acc[z] = A[z] (M x K, bf16, K contiguous)  x  B[z]
  *      B[z] is N x K with K contiguous (b_mn_major = 0: an nn.Linear weight [out, in] or K^T of attention), or
  *      B[z] is K x N with N contiguous (b_mn_major = 1: the V operand of P.V)
@@ -91,6 +93,9 @@ typedef struct pio_gemm_args {
   int32_t tile_n;       /* 64, 128, 256 or 0 = auto */
   int32_t max_ctas;     /* 0 = number of SMs */
   int32_t cluster_m;    /* CTAs per cluster along M sharing one multicast B tile: 1, 2, 4 or 0 = auto */
+  int32_t kernel;       /* 0 = auto, 1 = single-CTA kernel (128 x tile_n tiles), 2 = CTA-pair kernel (cta_group::2,
+                           256 x 256 tiles, TMA epilogue; needs K-major B, exactly one output and 16-byte aligned
+                           output / residual rows) */
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 

@@ -48,32 +48,6 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XPOSE_BYTES + 256 /*barriers*/;
 };
 
-// Exact (erf) GELU.  erf by Abramowitz-Stegun 7.1.26 (|abs error| < 1.5e-7, far below bf16 resolution of the stored
-// activation): two MUFU ops + 8 FMAs instead of libdevice erff's ~30 instructions.
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = ex2_approx(z * z * -1.4426950408889634f);   // exp(-z^2)
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return fmaf(0.5f * x, erf_v, 0.5f * x);
-}
-
 template <int BN, bool B_MN, int CL>
 __global__ void __launch_bounds__(384, 1)
 pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -474,6 +448,18 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
   if (dev.cc_major != 10) return fail(PIO_ERR_ARCH, "pio_gemm_bf16 needs sm_100 (got sm_%d%d)", dev.cc_major, dev.cc_minor);
+  PIO_REQUIRE(a->kernel >= 0 && a->kernel <= 2, "pio_gemm_bf16: kernel must be 0 (auto), 1 or 2 (got %d)", a->kernel);
+  {
+    // CTA-pair kernel: when explicitly requested, or when there are enough 256 x 256 tiles to occupy the SM pairs
+    const bool elig = gemm2_eligible(a) && (dev.sm_count % 2 == 0);
+    if (a->kernel == 2 && !elig)
+      return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the CTA-pair kernel needs K-major B, exactly one output and "
+                                       "16-byte aligned output / residual rows");
+    const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
+    const bool want = a->kernel == 2 ||
+                      (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && pair_tiles * 10 >= 8ll * (dev.sm_count / 2));
+    if (elig && want) return launch_gemm2(a, dev, stream);
+  }
   int bn = a->tile_n;
   if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   // cluster width along M: multicast pays when there are at least two M tiles to pair up

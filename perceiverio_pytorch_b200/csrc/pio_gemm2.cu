@@ -1,0 +1,436 @@
+// CTA-pair bf16 GEMM for sm_100a: the fast path of pio_gemm_bf16 for the big projection / MLP products.
+//
+// Two CTAs of a 2-wide cluster (one TPC) compute one 256 x 256 output tile with tcgen05.mma.cta_group::2 (M = 256):
+// each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 weight rows), so per 128-cycle MMA
+// step an SM reads 8 KB of operands from shared memory and receives 8 KB from TMA instead of 12 KB + 12 KB for a
+// single-CTA 128 x 256 tile.  Shared-memory bandwidth (128 B/clk/SM, shared by the tensor core's operand reads, the TMA
+// fills and the epilogue staging) is what caps the single-CTA kernel at ~62 % of the tensor peak.
+//
+// The epilogue never touches global memory with per-thread accesses: the fp32 residual tile is prefetched by TMA into
+// a per-warp shared-memory ring two chunks ahead (across tile boundaries, so HBM latency is hidden behind the
+// mainloop), and results leave through a swizzled per-warp staging slot and TMA stores, which also clip the M / N
+// tails.  Each epilogue warp runs its own pipeline (no CTA-wide barrier in the steady state).
+//
+// Roles (384 threads per CTA): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warp 3 idle, warps 4..11 epilogue: warp w owns TMEM lanes 32*(w%4).. (accumulator rows) and the
+// 128-column half (w-4)/4 of the tile.
+#include <stdlib.h>
+
+#include "pio_common.cuh"
+#include "pio_host.h"
+
+namespace pio {
+
+struct Gemm2Params {
+  int M, N, K, batch;
+  int tiles_n, m_pairs;          // 256-column tiles, 256-row CTA-pair tiles
+  int a_bcast, b_bcast, r_bcast; // operand shared by every batch entry
+  const float* bias;
+  int bias_mode;                 // 0 none, 1 per column, 2 per row
+  int act;
+  float alpha;
+  int has_residual;
+  int b_swap;                    // debug: which CTA of the pair stages which half of the B tile
+};
+
+enum { G2_BF16 = 0, G2_F32 = 1 };
+
+template <int KIND>
+struct Gemm2Cfg {
+  static constexpr int BM = 128;       // rows per CTA (256 per pair)
+  static constexpr int BN = 256;       // columns per pair tile
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (KIND == G2_BF16) ? 5 : 4;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int SLOT_BYTES = 4096;              // 32 rows x 128 B
+  static constexpr int RES_SLOTS = (KIND == G2_F32) ? 2 : 0;
+  static constexpr int OUT_SLOTS = (KIND == G2_F32) ? 1 : 2;
+  static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 512;                // two 256-column fp32 accumulators
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(384, 1)
+pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                 const Gemm2Params p) {
+  using Cfg = Gemm2Cfg<KIND>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* epi_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + Cfg::EPI_BYTES);
+  uint64_t* full_bar = bars;                        // [STAGES]  TMA (both CTAs) -> MMA; only the leader's are used
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;     // [STAGES]  MMA -> TMA producer of each CTA (multicast commit)
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;    // [2]       MMA -> epilogue of each CTA (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]       epilogue warps of both CTAs -> MMA (leader's)
+  uint64_t* res_full = tmem_empty + 2;              // [EPI_WARPS][2]  residual TMA -> epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::EPI_WARPS * 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("pio_gemm2_kernel: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  const uint32_t crank = cluster_ctarank();        // 0 = leader
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_tiles = p.m_pairs * p.tiles_n * p.batch;
+  const int num_k_chunks = (p.K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (KIND == G2_F32 && p.has_residual) tma_prefetch_desc(&tmap_res);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);   // one arrival per epilogue warp of either CTA
+    }
+    for (int i = 0; i < Cfg::EPI_WARPS * 2; ++i) mbar_init(&res_full[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (both CTAs) =================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < total_tiles; t += num_pairs) {
+        const int nt = t % p.tiles_n;
+        const int mp = (t / p.tiles_n) % p.m_pairs;
+        const int z = t / (p.tiles_n * p.m_pairs);
+        const int m0 = mp * 256 + (int)crank * Cfg::BM;
+        const int n0 = nt * Cfg::BN + (int)(crank ^ (uint32_t)p.b_swap) * (Cfg::BN / 2);
+        const int za = p.a_bcast ? 0 : z, zb = p.b_bcast ? 0 : z;
+        for (int kc = 0; kc < num_k_chunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          // both CTAs' bytes are credited to the leader's barrier, which expects the pair's total
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t leader_bar = mapa_u32(&full_bar[stage], 0);
+          tma_load_3d_2cta(sa, &tmap_a, leader_bar, kc * Cfg::BK, m0, za);
+          tma_load_3d_2cta(sb, &tmap_b, leader_bar, kc * Cfg::BK, n0, zb);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ================= MMA issuer (leader CTA) =================
+      constexpr uint32_t idesc = make_idesc_f16(256, Cfg::BN, /*bf16*/ 1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+        for (int kc = 0; kc < num_k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(sa + ks * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + ks * 32, 16, 1024);
+            umma_ss_2cta(d_tmem, da, db, idesc, (kc | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta_mcast(&empty_bar[stage], 0x3);   // frees the stage in both CTAs
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2cta_mcast(&tmem_full[acc], 0x3);       // accumulator halves complete in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= Epilogue (both CTAs) =================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* my = epi_base + ew * Cfg::WARP_EPI_BYTES;
+    uint8_t* my_out = my + Cfg::RES_SLOTS * Cfg::SLOT_BYTES;
+    uint64_t* my_res_full = res_full + ew * 2;
+    const bool has_res = (KIND == G2_F32) && p.has_residual;
+    constexpr int CHUNK_COLS = (KIND == G2_F32) ? 32 : 64;
+    constexpr int CHUNKS = 128 / CHUNK_COLS;           // chunks of this warp's column half per tile
+    const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
+
+    // residual prefetch cursor (lane 0): the stream of (tile, chunk) boxes this warp will consume, two ahead
+    int pf_t = pair_id, pf_c = 0;
+    uint32_t pf_idx = 0;
+    auto issue_res = [&]() {
+      if (pf_t >= total_tiles) return;
+      const int nt = pf_t % p.tiles_n;
+      const int mp = (pf_t / p.tiles_n) % p.m_pairs;
+      const int z = pf_t / (p.tiles_n * p.m_pairs);
+      const int row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
+      const int col = nt * Cfg::BN + half * 128 + pf_c * CHUNK_COLS;
+      const uint32_t slot = pf_idx & 1u;
+      mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
+      tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, p.r_bcast ? 0 : z);
+      ++pf_idx;
+      if (++pf_c == CHUNKS) { pf_c = 0; pf_t += num_pairs; }
+    };
+    if (has_res && lane == 0) {
+      issue_res();
+      issue_res();
+    }
+    uint32_t use_idx = 0;
+    int it = 0;
+    for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+      const int nt = t % p.tiles_n;
+      const int mp = (t / p.tiles_n) % p.m_pairs;
+      const int z = t / (p.tiles_n * p.m_pairs);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int row0 = mp * 256 + (int)crank * Cfg::BM + quarter * 32;   // first row of this warp's block
+      const int row = row0 + lane;
+      const float row_bias = (p.bias_mode == 2 && row < p.M) ? __ldg(p.bias + row) : 0.0f;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = nt * Cfg::BN + half * 128 + c * CHUNK_COLS;
+        float v[CHUNK_COLS];
+        {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * CHUNK_COLS, r);
+          if constexpr (CHUNK_COLS == 64) {
+            uint32_t r2[32];
+            tmem_ld32(t_row + c * CHUNK_COLS + 32, r2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[32 + j] = fmaf(__uint_as_float(r2[j]), p.alpha, row_bias);
+          } else {
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
+        }
+        if (c == CHUNKS - 1) {
+          // this warp has read its whole share of the accumulator: hand the TMEM buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+        }
+        if (p.bias_mode == 1) {
+          if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+              v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK_COLS; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < CHUNK_COLS; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if constexpr (KIND == G2_F32) {
+          if (has_res) {
+            const uint32_t slot = use_idx & 1u;
+            mbar_wait(&my_res_full[slot], (use_idx >> 1) & 1u);
+            const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rq = *reinterpret_cast<const float4*>(rs + sw128_offset(lane, j));
+              v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
+            }
+          }
+          // the staging slot is free once the previous chunk's TMA store has read it
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(my_out + sw128_offset(lane, j)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, my_out, col0, row0, z);
+            bulk_commit();
+            if (has_res) issue_res();   // refills the residual slot that was just consumed
+          }
+          ++use_idx;
+        } else {
+          uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(slot_out + sw128_offset(lane, j)) = q;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, slot_out, col0, row0, z);
+            bulk_commit();
+          }
+          ++use_idx;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();   // staging slots must outlive the stores that read them
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA exits (or frees TMEM) while its peer may still read its smem / signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int KIND>
+static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<KIND>;
+  CUtensorMap ta, tb, to, tr;
+  const bool a_bcast = a->batch > 1 && a->strideA == 0;
+  const bool b_bcast = a->batch > 1 && a->strideB == 0;
+  const bool r_bcast = a->batch > 1 && a->strideR == 0;
+  const uint64_t a_batch = a_bcast ? 1 : a->batch, b_batch = b_bcast ? 1 : a->batch;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, a_batch};
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a_batch > 1 ? a->strideA : a->lda * (int64_t)a->M) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = encode_tmap(&ta, a->A, false, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, b_batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)(b_batch > 1 ? a->strideB : a->ldb * (int64_t)a->N) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = encode_tmap(&tb, a->B, false, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
+  if (KIND == G2_F32) {
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldo32 * 4, (uint64_t)(a->batch > 1 ? a->strideO32 : a->ldo32 * (int64_t)a->M) * 4};
+    const uint32_t box[3] = {32, 32, 1};
+    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+    tr = to;
+    if (a->residual) {
+      const uint64_t rb = r_bcast ? 1 : a->batch;
+      const uint64_t rdims[3] = {(uint64_t)a->N, (uint64_t)a->M, rb};
+      const uint64_t rstrides[2] = {(uint64_t)a->ldr * 4, (uint64_t)(rb > 1 ? a->strideR : a->ldr * (int64_t)a->M) * 4};
+      rc = encode_tmap(&tr, a->residual, true, 3, rdims, rstrides, box);
+      if (rc != PIO_OK) return rc;
+    }
+  } else {
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldo16 * 2, (uint64_t)(a->batch > 1 ? a->strideO16 : a->ldo16 * (int64_t)a->M) * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    int rc = encode_tmap(&to, a->out_bf16, false, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+    tr = to;
+  }
+  Gemm2Params p;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+  p.tiles_n = (a->N + Cfg::BN - 1) / Cfg::BN;
+  p.m_pairs = (a->M + 255) / 256;
+  p.a_bcast = a_bcast; p.b_bcast = b_bcast; p.r_bcast = r_bcast;
+  p.bias = a->bias; p.bias_mode = a->bias ? a->bias_mode : 0;
+  p.act = a->act; p.alpha = a->alpha;
+  p.has_residual = a->residual != nullptr;
+  static const int b_swap = [] { const char* e = getenv("PIO_GEMM2_BSWAP"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.b_swap = b_swap;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(pio_gemm2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(gemm2<%d>) failed: %s", KIND, cudaGetErrorString(attr_err));
+
+  const long long total = (long long)p.m_pairs * p.tiles_n * p.batch;
+  int pairs = dev.sm_count / 2;
+  if (a->max_ctas > 0 && a->max_ctas / 2 < pairs) pairs = a->max_ctas / 2 > 0 ? a->max_ctas / 2 : 1;
+  if (total < pairs) pairs = (int)total;
+  {
+    const double bytes = (KIND == G2_F32 ? 4.0 * (a->residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
+    ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, bytes, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pairs * 2), 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PIO_CUDA_OK(cudaLaunchKernelEx(&cfg, pio_gemm2_kernel<KIND>, ta, tb, to, tr, p));
+  }
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
+}
+
+// Whether the CTA-pair kernel can run this problem (layout / alignment rules of its TMA epilogue).
+bool gemm2_eligible(const pio_gemm_args* a) {
+  if (a->b_mn_major) return false;
+  const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
+  if (f32 == b16) return false;                       // exactly one output
+  if (b16 && a->residual) return false;
+  if (f32) {
+    if (!aligned16(a->out_f32) || a->ldo32 % 4 != 0 || a->ldo32 < a->N) return false;
+    if (a->batch > 1 && (a->strideO32 % 4 != 0 || a->strideO32 <= 0)) return false;
+    if (a->residual) {
+      if (!aligned16(a->residual) || a->ldr % 4 != 0 || a->ldr < a->N) return false;
+      if (a->batch > 1 && a->strideR % 4 != 0) return false;
+    }
+  } else {
+    if (!aligned16(a->out_bf16) || a->ldo16 % 8 != 0 || a->ldo16 < a->N) return false;
+    if (a->batch > 1 && (a->strideO16 % 8 != 0 || a->strideO16 <= 0)) return false;
+  }
+  return true;
+}
+
+int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
+  if (a->out_f32) return launch_gemm2_kind<G2_F32>(a, dev, stream);
+  return launch_gemm2_kind<G2_BF16>(a, dev, stream);
+}
+
+}  // namespace pio

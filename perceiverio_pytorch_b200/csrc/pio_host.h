@@ -52,6 +52,9 @@ int get_device_info(DeviceInfo* out);
 // Encodes a bf16 tensor of rank `rank` (dims[0] innermost) with SWIZZLE_128B and zero OOB fill.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 entries, for dims[1..] */, const uint32_t* box);
+// Same for fp32 (is_f32) or bf16 elements; the box's inner extent must span exactly 128 bytes (SWIZZLE_128B).
+int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box);
 
 // Optional per-launch profiling: when enabled (pio_profile_enable), every entry point brackets its kernel launch
 // with CUDA events recorded on the launching stream *inside* the library, so the interval contains the kernel and
@@ -66,6 +69,10 @@ struct ProfileScope {
   cudaEvent_t e0_ = nullptr;
   bool on_ = false;
 };
+
+// CTA-pair GEMM (pio_gemm2.cu)
+bool gemm2_eligible(const pio_gemm_args* a);
+int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -14,6 +14,7 @@ from . import _lib
 
 BF16 = torch.bfloat16
 GEMM_CLUSTER_M = 0   # 0 = library default; tests / bench can force 1, 2 or 4
+GEMM_KERNEL = 0      # 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair (cta_group::2) kernel
 
 
 def pad8(n: int) -> int:
@@ -59,7 +60,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          residual: Optional[torch.Tensor] = None, ldr: int = 0, strideR: int = 0,
          out_f32: Optional[torch.Tensor] = None, ldo32: int = 0, strideO32: int = 0,
          out_bf16: Optional[torch.Tensor] = None, ldo16: int = 0, strideO16: int = 0,
-         tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None) -> None:
+         tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
     assert A.dtype == BF16 and B.dtype == BF16
@@ -69,7 +70,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       M, N, K, batch, _ptr(bias), bias_mode if bias is not None else 0, act, alpha,
                       _ptr(residual), ldr, strideR, _ptr(out_f32), ldo32, strideO32,
                       _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas,
-                      GEMM_CLUSTER_M if cluster_m is None else cluster_m)
+                      GEMM_CLUSTER_M if cluster_m is None else cluster_m,
+                      GEMM_KERNEL if kernel is None else kernel)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 

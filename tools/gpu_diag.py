@@ -7,7 +7,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["env", "ln", "gemm_k", "gemm_mn", "gemm_epi", "gemm_cluster", "softmax", "flash", "combine"]
+GROUPS = ["env", "ln", "gemm_k", "gemm_mn", "gemm_epi", "gemm_cluster", "gemm_pair", "softmax", "flash", "combine"]
 
 
 def _err(got, ref):
@@ -55,7 +55,7 @@ def group_ln():
     print("cast-only:", _err(y[:, :100].float(), x))
 
 
-def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha=1.0, residual=False, f32=True, bf16=False, verbose_map=False, cluster_m=None):
+def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha=1.0, residual=False, f32=True, bf16=False, verbose_map=False, cluster_m=None, kernel=None, res_bcast=False):
     import torch
     from perceiverio_pytorch_b200 import ops
     ld_k = ops.pad8(K)
@@ -89,15 +89,15 @@ def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha
         ref = torch.nn.functional.gelu(ref)
     res = None
     if residual:
-        res = torch.randn(batch, M, N, device="cuda")
+        res = torch.randn(1 if res_bcast else batch, M, N, device="cuda")
         ref = ref + res
     o32 = torch.full((batch, M, N), float("nan"), device="cuda") if f32 else None
     ld16 = ops.pad8(N)
     o16 = torch.zeros(batch, M, ld16, dtype=torch.bfloat16, device="cuda") if bf16 else None
     ops.gemm(A, Bm, M=M, N=N, K=K, batch=batch, b_mn_major=b_mn, strideA=M * ld_k, strideB=strideB, lda=ld_k, ldb=ldb,
-             bias=bias, bias_mode=bias_mode, act=act, alpha=alpha, residual=res, ldr=N, strideR=M * N,
+             bias=bias, bias_mode=bias_mode, act=act, alpha=alpha, residual=res, ldr=N, strideR=0 if res_bcast else M * N,
              out_f32=o32, ldo32=N, strideO32=M * N, out_bf16=o16, ldo16=ld16, strideO16=M * ld16, tile_n=tile_n,
-             cluster_m=cluster_m)
+             cluster_m=cluster_m, kernel=kernel)
     torch.cuda.synchronize()
     msgs = []
     ok = True
@@ -113,7 +113,7 @@ def _gemm_case(M, N, K, batch=1, b_mn=False, tile_n=0, bias_mode=0, act=0, alpha
         good = e[1] < 1e-2
         ok &= good
         msgs.append(f"bf16 abs {e[0]:.3e} rel {e[1]:.3e}")
-    print(f"gemm M={M} N={N} K={K} b={batch} mn={int(b_mn)} tn={tile_n} cl={cluster_m} bias={bias_mode} act={act} res={int(residual)}: "
+    print(f"gemm M={M} N={N} K={K} b={batch} mn={int(b_mn)} tn={tile_n} cl={cluster_m} kern={kernel} bias={bias_mode} act={act} res={int(residual)}: "
           + "; ".join(msgs) + (" OK" if ok else " FAIL"), flush=True)
     return ok
 
@@ -163,6 +163,24 @@ def group_gemm_cluster():
         _gemm_case(4096, 3072, 1024, cluster_m=cl)
 
 
+def group_gemm_pair():
+    """CTA-pair (cta_group::2) kernel, forced with kernel=2."""
+    _gemm_case(256, 256, 64, kernel=2, verbose_map=True)
+    _gemm_case(256, 256, 64, kernel=2, f32=False, bf16=True, verbose_map=True)
+    _gemm_case(256, 256, 256, kernel=2, verbose_map=True)
+    _gemm_case(512, 512, 1024, kernel=2, bias_mode=1, residual=True)
+    _gemm_case(512, 1024, 1024, kernel=2, bias_mode=1, act=1, f32=False, bf16=True)
+    _gemm_case(1000, 1000, 1024, kernel=2, bias_mode=1, residual=True)
+    _gemm_case(1000, 1000, 1024, kernel=2, bias_mode=1, f32=False, bf16=True)
+    _gemm_case(333, 264, 261, kernel=2, verbose_map=True)
+    _gemm_case(300, 328, 200, kernel=2, bias_mode=2, alpha=0.25, f32=False, bf16=True)
+    _gemm_case(512, 1024, 256, batch=5, kernel=2, bias_mode=1, residual=True, res_bcast=True)
+    _gemm_case(200, 304, 72, batch=3, kernel=2, bias_mode=1, residual=True)
+    _gemm_case(4096, 3072, 1024, kernel=2, f32=False, bf16=True)
+    _gemm_case(32768, 1024, 1024, kernel=2, bias_mode=1, residual=True)
+    _gemm_case(20000, 1024, 1024, kernel=2, bias_mode=1, act=1, f32=False, bf16=True)
+
+
 def _time(fn, iters=20):
     import torch
     fn()
@@ -209,6 +227,29 @@ def group_perf():
                                                cluster_m=cl, tile_n=tn))
                     line += f"; gelu bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
                 print(line, flush=True)
+    for N in (1024, 3072):
+        W = torch.randn(N, 1024, device=dev).to(torch.bfloat16)
+        o16 = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        o32 = torch.empty(M, N, device=dev)
+        t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, out_bf16=o16, ldo16=N, kernel=2))
+        line = f"gemm {M}x{N}x1024 pair: bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+        if N == 1024:
+            t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, residual=res, ldr=N, out_f32=o32, ldo32=N, kernel=2))
+            line += f"; fp32 residual in/out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+            t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, out_f32=o32, ldo32=N, kernel=2))
+            line += f"; fp32 out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+            t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, act=1, out_bf16=o16, ldo16=N, kernel=2))
+            line += f"; gelu bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
+        print(line, flush=True)
+    Ab = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    Wb = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    ob = torch.empty(8192, 8192, dtype=torch.bfloat16, device=dev)
+    for kern in (1, 2):
+        t = _time(lambda: ops.gemm(Ab, Wb, M=8192, N=8192, K=8192, out_bf16=ob, ldo16=8192, kernel=kern), 5)
+        print(f"gemm 8192^3 kernel={kern}: {2 * 8192 ** 3 / t / 1e9:.0f} TF/s", flush=True)
+    t = _time(lambda: torch.matmul(Ab, Wb.t()), 5)
+    print(f"torch.matmul (cuBLAS) 8192^3: {2 * 8192 ** 3 / t / 1e9:.0f} TF/s")
+    W = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
     t = _time(lambda: torch.matmul(A, W.t()))
     print(f"torch.matmul (cuBLAS) {M}x3072x1024: {2 * M * 3072 * 1024 / t / 1e9:.0f} TF/s")
     # tower attention 64 x 8 heads x 512 x 512 x 128
