@@ -278,17 +278,41 @@ def run_gpu_arm(args):
             for k, v in _lib.profile_read().items() if v["launches"] > 0}
 
     # ---- timed region 2: end to end through the module API with host buffers ----
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    xdev = inputs  # the (graph) input buffer: the H2D copy lands directly in it
-    for _ in range(1):
-        xdev.copy_(host_inputs, non_blocking=True)
-        host_out.copy_(step(xdev)[:, 0, :], non_blocking=True)
+    # Software-pipelined input feed, as a serving loop would run it: two device input buffers (each with its own
+    # captured graph); the H2D copy of step i+1 runs on a copy stream while step i computes.  Every step's H2D copy
+    # (3.35 GB from pinned memory) and D2H read of the logits are inside the timed region, including the
+    # un-overlapped first copy.
+    e2e_steps = max(2, args.e2e_steps)
+    if args.no_graph:
+        bufs = [inputs, inputs.clone()]
+        runners = [step_eager, step_eager]
+    else:
+        graphed2 = GraphedForward(step_eager, [inputs], warmup=1)
+        bufs = [graphed.inputs[0], graphed2.inputs[0]]
+        runners = [graphed, graphed2]
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def run_e2e(n):
+        for i in range(n):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[k])       # the graph that read this buffer has finished
+                bufs[k].copy_(host_inputs, non_blocking=True)
+                copied[k].record(copy_stream)
+            main_stream.wait_event(copied[k])
+            o = runners[k](bufs[k])
+            consumed[k].record(main_stream)
+            # what ClassificationPostprocessor keeps (postprocessors.py:187)
+            host_out.copy_(o[:, 0, :], non_blocking=True)
+
+    run_e2e(2)
     sync_all()
     e0.record()
-    for _ in range(e2e_steps):
-        xdev.copy_(host_inputs, non_blocking=True)
-        o = step(xdev)
-        host_out.copy_(o[:, 0, :], non_blocking=True)   # what ClassificationPostprocessor keeps (postprocessors.py:187)
+    run_e2e(e2e_steps)
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -325,9 +349,10 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": host_inputs.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-                "note": "pinned host input -> H2D -> PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H"},
+                "note": "pinned host input -> H2D (copy stream, double-buffered: overlaps the previous step's compute) -> "
+                        "PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H; PCIe-bound (3.35 GB per step)"},
         "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
-        "roofline": {"bound": "tensor", "kernel": "pio_gemm_kernel (tcgen05 GEMM + fused epilogue), all launches of the step",
+        "roofline": {"bound": "tensor", "kernel": "pio_gemm2_kernel / pio_gemm_kernel (tcgen05 GEMMs with fused epilogue), all GEMM launches of the step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"], "traffic": None,
                      "share_of_step": shares.get("gemm")},
@@ -360,7 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

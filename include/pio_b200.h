@@ -160,9 +160,25 @@ typedef struct pio_combine_args {
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 SIMT linear for very narrow outputs (N <= 16): y[m, :] = x[m, :] . W^T + bias, everything fp32.
+ * Replaces the decoder's `final_layer` (perceiver.py:179) when it projects to a handful of channels — the optical
+ * flow head is 322 -> 2 and carries most of the model's bf16 error budget, while being 0.01 % of
+ * the FLOPs.  HBM-bound: 4*K bytes read per row.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_linear_f32_args {
+  const float* x; int64_t ldx;      /* [M, K] */
+  const float* w; int64_t ldw;      /* [N, K] (nn.Linear layout) */
+  const float* bias;                /* [N] or NULL */
+  float* y; int64_t ldy;            /* [M, N] */
+  int64_t M;
+  int32_t N, K;
+} pio_linear_f32_args;
+int pio_linear_f32(const pio_linear_f32_args* a, void* stream);
+
 /* Per-launch device timing (bench.py's roofline): while enabled, every entry point brackets its kernel launch with
  * CUDA events on the launching stream.  pio_profile_read drains the records into out[family*4 + {ms, flops, bytes,
- * launches}] for the families {0 layernorm, 1 gemm, 2 softmax, 3 attention, 4 combine}.  Do not enable while a
+ * launches}] for the families {0 layernorm, 1 gemm, 2 softmax, 3 attention, 4 combine, 5 linear_f32}.  Do not enable while a
  * stream is being captured into a CUDA graph. */
 void pio_profile_enable(int on);
 int pio_profile_read(double* out, int n_families);

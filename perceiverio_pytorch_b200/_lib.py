@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     "pio_profile_enable", "pio_profile_read",
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
+    "pio_linear_f32",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -72,6 +73,11 @@ class CombineArgs(C.Structure):
                 ("O_out_part", vp), ("m_out", vp), ("l_out", vp)]
 
 
+class LinearF32Args(C.Structure):
+    _fields_ = [("x", vp), ("ldx", i64), ("w", vp), ("ldw", i64), ("bias", vp), ("y", vp), ("ldy", i64),
+                ("M", i64), ("N", i32), ("K", i32)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -96,7 +102,7 @@ def load(build_if_missing: bool = True):
         lib.pio_launch_count.restype = C.c_int64
         for name, argt in (("pio_layernorm_bf16", LayerNormArgs), ("pio_gemm_bf16", GemmArgs),
                            ("pio_softmax_bf16", SoftmaxArgs), ("pio_attention_fwd", AttentionArgs),
-                           ("pio_attention_combine", CombineArgs)):
+                           ("pio_attention_combine", CombineArgs), ("pio_linear_f32", LinearF32Args)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
@@ -124,7 +130,7 @@ def launch_count() -> int:
     return int(load().pio_launch_count())
 
 
-KERNEL_FAMILIES = ("layernorm", "gemm", "softmax", "attention", "combine")
+KERNEL_FAMILIES = ("layernorm", "gemm", "softmax", "attention", "combine", "linear_f32")
 
 
 def profile_enable(on: bool) -> None:

@@ -59,7 +59,7 @@ int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const
 // Optional per-launch profiling: when enabled (pio_profile_enable), every entry point brackets its kernel launch
 // with CUDA events recorded on the launching stream *inside* the library, so the interval contains the kernel and
 // nothing of the host-side Python gap.  Not usable during stream capture.
-enum KernelFamily { KF_LAYERNORM = 0, KF_GEMM = 1, KF_SOFTMAX = 2, KF_FLASH = 3, KF_COMBINE = 4, KF_COUNT = 5 };
+enum KernelFamily { KF_LAYERNORM = 0, KF_GEMM = 1, KF_SOFTMAX = 2, KF_FLASH = 3, KF_COMBINE = 4, KF_LINEAR_F32 = 5, KF_COUNT = 6 };
 struct ProfileScope {
   ProfileScope(int family, double flops, double bytes, cudaStream_t stream);
   ~ProfileScope();

@@ -251,7 +251,69 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// fp32 linear with a very narrow output (N <= 16): one warp per row, lane l owns columns l, l+32, ... of x (coalesced),
+// NOUT accumulators per lane, butterfly reduction.  W (N x K fp32, a few KB) is read through the read-only path.
+// ------------------------------------------------------------------------------------------------------------
+template <int NOUT>
+__global__ void __launch_bounds__(256) pio_linear_f32_kernel(pio_linear_f32_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.M) return;
+  const float* xr = a.x + row * a.ldx;
+  float acc[NOUT];
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += 128) {
+    float xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lane + 32 * i;
+      xv[i] = (k < a.K) ? __ldg(xr + k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lane + 32 * i;
+      if (k < a.K) {
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n)
+          if (n < a.N) acc[n] = fmaf(xv[i], __ldg(a.w + (long long)n * a.ldw + k), acc[n]);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane < a.N) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n)
+      if (n == lane) v = acc[n];
+    a.y[row * a.ldy + lane] = v + (a.bias ? __ldg(a.bias + lane) : 0.f);
+  }
+}
+
 }  // namespace pio
+
+extern "C" int pio_linear_f32(const pio_linear_f32_args* a, void* stream_) {
+  using namespace pio;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PIO_REQUIRE(a && a->x && a->w && a->y, "pio_linear_f32: null pointer");
+  PIO_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "pio_linear_f32: bad shape");
+  PIO_REQUIRE(a->ldx >= a->K && a->ldw >= a->K && a->ldy >= a->N, "pio_linear_f32: bad leading dimension");
+  if (a->N > 16) return fail(PIO_ERR_UNSUPPORTED, "pio_linear_f32 covers N <= 16 (got %d); use pio_gemm_bf16", a->N);
+  const long long blocks = (a->M + 7) / 8;
+  PIO_REQUIRE(blocks < (1ll << 31), "pio_linear_f32: too many rows");
+  {
+    ProfileScope prof(KF_LINEAR_F32, 2.0 * a->M * a->N * (double)a->K, (double)a->M * (4.0 * a->K + 4.0 * a->N), stream);
+    if (a->N <= 2) pio_linear_f32_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    else if (a->N <= 4) pio_linear_f32_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    else if (a->N <= 8) pio_linear_f32_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    else pio_linear_f32_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(*a);
+  }
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
+}
 
 extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   using namespace pio;

@@ -91,6 +91,18 @@ def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torc
     return y32, y16
 
 
+def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = x @ w^T + bias in fp32 on CUDA cores, for N <= 16 output channels (x fp32 [M, K], w fp32 [N, K])."""
+    _need_cuda(x, w, bias)
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.stride(-1) == 1 and w.stride(-1) == 1
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    a = _lib.LinearF32Args(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(y), n, m, n, k)
+    _lib.check(_lib.load().pio_linear_f32(C.byref(a), _stream()), "pio_linear_f32")
+    return y
+
+
 def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[torch.Tensor] = None,
                  row_keep: Optional[torch.Tensor] = None) -> torch.Tensor:
     """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)]."""

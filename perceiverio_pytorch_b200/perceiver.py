@@ -121,12 +121,19 @@ class PerceiverDecoder(nn.Module):
 
     def forward(self, query, latents, *, query_mask=None):
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
-        y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
-                                                              want_bf16_out=self._final_project)
+        y32, _ = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep)
         if not self._final_project:
             return y32
         B, Nq, C = y32.shape
+        n_out = self._output_num_channels
+        if n_out <= 16:
+            # a handful of output channels (optical flow: 322 -> 2): fp32 on CUDA cores.  The head is 0.01 % of the
+            # FLOPs but its bf16 rounding alone would cost 1.2e-2 of the 1e-2 error budget.
+            bias = self.final_layer.bias.detach() if self.final_layer.bias is not None else None
+            out = ops.linear_f32(y32.view(B * Nq, C), self.final_layer.weight.detach(), bias)
+            return out.view(B, Nq, -1)
         w = engine.prepared(self.final_layer, "w", lambda: (engine._bf16_weight(self.final_layer.weight.detach()),
                                                            self.final_layer.bias.detach().float().contiguous()))
-        out, _ = ops.linear(y16, C, w[0], self._output_num_channels, w[1], want_f32=True, want_bf16=False)
+        y16 = ops.layernorm_bf16(y32.view(B * Nq, C), None, None, normalize=False)
+        out, _ = ops.linear(y16, C, w[0], n_out, w[1], want_f32=True, want_bf16=False)
         return out.view(B, Nq, -1)

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 @pytest.mark.parametrize("struct,cname", [("LayerNormArgs", "pio_layernorm_args"), ("GemmArgs", "pio_gemm_args"),
                                           ("SoftmaxArgs", "pio_softmax_args"), ("AttentionArgs", "pio_attention_args"),
-                                          ("CombineArgs", "pio_combine_args")])
+                                          ("CombineArgs", "pio_combine_args"), ("LinearF32Args", "pio_linear_f32_args")])
 def test_ctypes_structs_follow_the_header(struct, cname):
     from perceiverio_pytorch_b200 import _lib
     body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), _header(), flags=re.S).group(1)

@@ -1,0 +1,198 @@
+"""Per-kernel numerics on the B200: every C-ABI entry point against a plain PyTorch fp32 evaluation of the same op
+(the floating-point kernels' own reference; the oracle covers the composed path in test_gpu_parity.py).
+Tolerances: fp32 outputs of bf16-operand products 2e-3 of the output range, bf16 outputs 1e-2 (bf16 rounding)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    d = (got.double() - ref.double()).abs().max()
+    return float(d / ref.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 261), (513, 1024), (77, 322), (300, 1280), (64, 32), (50, 1026)])
+def test_layernorm_cast(rows, c):
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(rows, c, device="cuda") * 2 + 0.5
+    g, b = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    y = ops.layernorm_bf16(x, g, b)
+    ref = torch.nn.functional.layer_norm(x, (c,), g, b, 1e-5)
+    assert _rel(y[:, :c].float(), ref) < 8e-3
+    if y.shape[1] > c:
+        assert float(y[:, c:].float().abs().max()) == 0.0   # pad columns are exact zeros
+
+
+def _gemm(M, N, K, *, batch=1, b_mn=False, bias_mode=0, act=0, alpha=1.0, residual=False, res_bcast=False,
+          out="f32", kernel=0, cluster_m=None, tile_n=0):
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(1)
+    ldk = ops.pad8(K)
+    A = torch.full((batch, M, ldk), 7.0, dtype=torch.bfloat16, device="cuda")   # pad = garbage that must not be read
+    A[:, :, :K] = torch.randn(batch, M, K, device="cuda").to(torch.bfloat16)
+    if not b_mn:
+        Bm = torch.full((batch, N, ldk), 5.0, dtype=torch.bfloat16, device="cuda")
+        Bm[:, :, :K] = torch.randn(batch, N, K, device="cuda").to(torch.bfloat16)
+        ref = A[:, :, :K].float() @ Bm[:, :, :K].float().transpose(1, 2)
+        ldb, strideB = ldk, N * ldk
+    else:
+        ldn = ops.pad8(N)
+        Bm = torch.full((batch, K, ldn), 5.0, dtype=torch.bfloat16, device="cuda")
+        Bm[:, :, :N] = torch.randn(batch, K, N, device="cuda").to(torch.bfloat16)
+        ref = A[:, :, :K].float() @ Bm[:, :, :N].float()
+        ldb, strideB = ldn, K * ldn
+    ref = ref * alpha
+    bias = None
+    if bias_mode == 1:
+        bias = torch.randn(N, device="cuda")
+        ref = ref + bias
+    elif bias_mode == 2:
+        bias = torch.randn(M, device="cuda")
+        ref = ref + bias[None, :, None]
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    res = None
+    if residual:
+        res = torch.randn(1 if res_bcast else batch, M, N, device="cuda")
+        ref = ref + res
+    ldo = (N + 3) // 4 * 4 if out == "f32" else ops.pad8(N)
+    o32 = torch.full((batch, M, ldo), float("nan"), device="cuda") if out == "f32" else None
+    o16 = torch.zeros(batch, M, ldo, dtype=torch.bfloat16, device="cuda") if out == "bf16" else None
+    ops.gemm(A, Bm, M=M, N=N, K=K, batch=batch, b_mn_major=b_mn, strideA=M * ldk, strideB=strideB, lda=ldk, ldb=ldb,
+             bias=bias, bias_mode=bias_mode, act=act, alpha=alpha, residual=res, ldr=N,
+             strideR=0 if res_bcast else M * N, out_f32=o32, ldo32=ldo, strideO32=M * ldo, out_bf16=o16, ldo16=ldo,
+             strideO16=M * ldo, tile_n=tile_n, cluster_m=cluster_m, kernel=kernel)
+    torch.cuda.synchronize()
+    if out == "f32":
+        got = o32[:, :, :N]
+        assert not bool(torch.isnan(got).any())
+        assert _rel(got, ref) < 2e-3
+    else:
+        assert _rel(o16[:, :, :N].float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("case", [
+    dict(M=256, N=256, K=64), dict(M=256, N=256, K=64, out="bf16"), dict(M=1000, N=1000, K=1024, bias_mode=1, residual=True),
+    dict(M=512, N=1024, K=1024, bias_mode=1, act=1, out="bf16"), dict(M=333, N=264, K=261),
+    dict(M=300, N=328, K=200, bias_mode=2, alpha=0.25, out="bf16"),
+    dict(M=512, N=1024, K=256, batch=5, bias_mode=1, residual=True, res_bcast=True),
+    dict(M=200, N=304, K=72, batch=3, bias_mode=1, residual=True), dict(M=4096, N=3072, K=1024, out="bf16"),
+])
+def test_gemm_both_kernels(kernel, case):
+    _gemm(kernel=kernel, **case)
+
+
+@pytest.mark.parametrize("case", [
+    dict(M=77, N=2, K=322), dict(M=333, N=261, K=261), dict(M=100, N=2, K=322, bias_mode=1),
+    dict(M=1000, N=1024, K=512, b_mn=True), dict(M=300, N=322, K=2048, b_mn=True, batch=2),
+    dict(M=640, N=64, K=200, cluster_m=2, tile_n=64), dict(M=700, N=704, K=1000, b_mn=True, cluster_m=2),
+    dict(M=130, N=261, K=1000, residual=True, bias_mode=1),          # unaligned fp32 rows: single-CTA kernel only
+])
+def test_gemm_single_cta_shapes(case):
+    _gemm(kernel=0, **case)
+
+
+def test_gemm_pair_kernel_rejects_unaligned_output():
+    from perceiverio_pytorch_b200 import ops
+    A = torch.zeros(256, 64, dtype=torch.bfloat16, device="cuda")
+    W = torch.zeros(261, 64, dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros(256, 261, device="cuda")
+    with pytest.raises(RuntimeError, match="CTA-pair"):
+        ops.gemm(A, W, M=256, N=261, K=64, out_f32=o, ldo32=261, kernel=2)
+
+
+@pytest.mark.parametrize("b,r,c", [(2, 40, 512), (1, 7, 52097), (3, 130, 785)])
+def test_softmax(b, r, c):
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(0)
+    S = torch.randn(b, r, c, device="cuda") * 3
+    km = (torch.rand(b, c, device="cuda") > 0.3).to(torch.uint8)
+    rk = (torch.rand(b, r, device="cuda") > 0.2).to(torch.uint8)
+    P = ops.softmax_bf16(S, c, 0.37, km, rk)
+    ref = torch.softmax(torch.where(km[:, None, :].bool(), S * 0.37, torch.tensor(float("-inf"), device="cuda")), -1)
+    ref = ref * rk[:, :, None]
+    assert _rel(P[:, :, :c].float(), ref) < 1e-2
+
+
+def _attn_ref(q, k, v, scale, km=None, rk=None):
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if km is not None:
+        s = torch.where(km[:, None, None, :].bool(), s, torch.tensor(float("-inf"), device=s.device))
+    p = torch.nan_to_num(torch.softmax(s, -1), nan=0.0)
+    o = torch.einsum("bhqk,bkhd->bqhd", p, v)
+    if rk is not None:
+        o = o * rk[:, :, None, None]
+    return o.reshape(o.shape[0], o.shape[1], -1)
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=1, H=1, Nq=128, Nk=1024, dqk=64, dv=64, qscale=4.0), dict(B=1, H=1, Nq=100, Nk=300, dqk=64, dv=64),
+    dict(B=2, H=8, Nq=512, Nk=512, dqk=128, dv=128), dict(B=2, H=8, Nq=256, Nk=256, dqk=32, dv=160),
+    dict(B=1, H=16, Nq=2048, Nk=2048, dqk=32, dv=32), dict(B=1, H=8, Nq=784, Nk=784, dqk=64, dv=64),
+    dict(B=2, H=8, Nq=256, Nk=2048, dqk=32, dv=160, mask=True), dict(B=2, H=8, Nq=2048, Nk=256, dqk=32, dv=96, mask=True),
+    dict(B=2, H=1, Nq=512, Nk=5000, dqk=261, dv=261, same_kv=True, q_bcast=True),
+    dict(B=2, H=1, Nq=512, Nk=5000, dqk=261, dv=261, same_kv=True, splits=3, qscale=3.0),
+    dict(B=1, H=1, Nq=2048, Nk=9000, dqk=322, dv=322, same_kv=True, splits=4, mask=True),
+])
+def test_streaming_attention(case):
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(2)
+    B, H, Nq, Nk, dqk, dv = (case[k] for k in ("B", "H", "Nq", "Nk", "dqk", "dv"))
+    same_kv, q_bcast, splits = case.get("same_kv", False), case.get("q_bcast", False), case.get("splits", 1)
+    dev = "cuda"
+    ldq, ldk, ldv = ops.pad8(H * dqk), ops.pad8(H * dqk), ops.pad8(H * dv)
+    Qb = 1 if q_bcast else B
+    Q = torch.zeros(Qb, Nq, ldq, dtype=torch.bfloat16, device=dev)
+    Q[:, :, :H * dqk] = (torch.randn(Qb, Nq, H * dqk, device=dev) * case.get("qscale", 1.0)).to(torch.bfloat16)
+    K = torch.zeros(B, Nk, ldk, dtype=torch.bfloat16, device=dev)
+    K[:, :, :H * dqk] = torch.randn(B, Nk, H * dqk, device=dev).to(torch.bfloat16)
+    if same_kv:
+        V = K
+    else:
+        V = torch.zeros(B, Nk, ldv, dtype=torch.bfloat16, device=dev)
+        V[:, :, :H * dv] = torch.randn(B, Nk, H * dv, device=dev).to(torch.bfloat16)
+    km = rk = None
+    if case.get("mask"):
+        km = (torch.rand(B, Nk, device=dev) > 0.3).to(torch.uint8)
+        km[0, Nk // 2:] = 0
+        rk = (torch.rand(B, Nq, device=dev) > 0.1).to(torch.uint8)
+    scale = dqk ** -0.5
+    qf = Q[:, :, :H * dqk].float().reshape(Qb, Nq, H, dqk).expand(B, Nq, H, dqk)
+    ref = _attn_ref(qf, K[:, :, :H * dqk].float().reshape(B, Nk, H, dqk),
+                    V[:, :, :H * dv].float().reshape(B, Nk, H, dv), scale, km, rk)
+    O = ops.attention_fwd(Q, K, V, B=B, H=H, Nq=Nq, Nk=Nk, dqk=dqk, dv=dv,
+                          strideQ=0 if q_bcast else Nq * ldq, strideK=Nk * ldk, strideV=Nk * ldv,
+                          ldq=ldq, ldk=ldk, ldv=ldv, scale=scale, key_mask=km, row_keep=rk, num_splits=splits)
+    torch.cuda.synchronize()
+    assert _rel(O[:, :, :H * dv].float(), ref) < 1.5e-2
+
+
+def test_lse_combine():
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(0)
+    parts, b, h, nq, dv = 3, 2, 4, 37, 40
+    Op = torch.randn(parts, b, h, nq, dv, device="cuda")
+    mp = torch.randn(parts, b, h, nq, device="cuda") * 3
+    lp = torch.rand(parts, b, h, nq, device="cuda") + 0.1
+    mp[1, 0] = float("-inf")
+    lp[1, 0] = 0
+    O = ops.attention_combine(Op, mp, lp)
+    M = mp.max(0).values
+    w = torch.exp(mp - M)
+    ref = ((Op * w[..., None]).sum(0) / (lp * w).sum(0)[..., None]).permute(0, 2, 1, 3).reshape(b, nq, h * dv)
+    assert _rel(O[:, :, :h * dv].float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 2, 322), (77, 5, 1026), (4097, 16, 64), (3, 1, 7)])
+def test_linear_f32(m, n, k):
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(0)
+    x, w, b = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda"), torch.randn(n, device="cuda")
+    y = ops.linear_f32(x, w, b)
+    ref = (x.double() @ w.double().t() + b.double()).float()
+    assert _rel(y, ref) < 1e-5   # fp32 accumulation order only
