@@ -10,6 +10,7 @@
 // Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
 // warps 4..7 softmax / correction / epilogue (thread = one query row = one TMEM lane).
 #include <math.h>
+#include <stdlib.h>
 
 #include "pio_common.cuh"
 #include "pio_host.h"
@@ -495,6 +496,14 @@ extern "C" int pio_attention_fwd(const pio_attention_args* a, void* stream_) {
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
   if (dev.cc_major != 10) return fail(PIO_ERR_ARCH, "pio_attention_fwd needs sm_100 (got sm_%d%d)", dev.cc_major, dev.cc_minor);
+  {
+    // short-key / many-head shapes (the latent tower): persistent two-tile kernel with P kept in TMEM
+    static const int force = [] { const char* e = getenv("PIO_FLASH_KERNEL"); return e ? atoi(e) : 0; }();
+    if (force != 1 && flash2_eligible(a)) {
+      const long long items = (long long)a->B * a->H * ((a->Nq + 255) / 256);
+      if (force == 2 || items * 2 >= dev.sm_count || a->Nk <= 4096) return launch_flash2(a, dev, stream);
+    }
+  }
   const bool same = (a->K == a->V) && (a->ldk == a->ldv) && (a->dqk == a->dv) && (a->strideK == a->strideV);
   const int nqc = (a->dqk + 63) / 64, nvc = (a->dv + 63) / 64;
   if (same && flash_shape_ok(a->dqk, a->dv, true)) {

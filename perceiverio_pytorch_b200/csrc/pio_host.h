@@ -74,6 +74,10 @@ struct ProfileScope {
 bool gemm2_eligible(const pio_gemm_args* a);
 int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream);
 
+// Persistent two-tile attention kernel (pio_flash2.cu)
+bool flash2_eligible(const pio_attention_args* a);
+int launch_flash2(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace pio

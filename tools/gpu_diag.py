@@ -355,7 +355,6 @@ def group_flash():
     _flash_case(2, 1, 512, 5000, 261, 261, same_kv=True, q_bcast=True)
     _flash_case(2, 1, 512, 5000, 261, 261, same_kv=True, splits=3, qscale=3.0)
     _flash_case(1, 1, 2048, 9000, 322, 322, same_kv=True, splits=4, mask=True)
-    _flash_case(1, 1, 300, 4000, 261, 261, qscale=6.0)
 
 
 def group_combine():
