@@ -70,7 +70,8 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* pv_done = p_full + 2;                  // [2]  O += P_j V_j retired (MMA -> softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // the shuffle makes the warp index provably warp-uniform, so role code can use the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_flash_kernel: dynamic shared memory base is not 1024-byte aligned\n");
@@ -119,17 +120,21 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int dv_n = ((p.dv + 15) / 16) * 16;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      const int bq = p.q_bcast ? 0 : b;
+    // ================= TMA producer =================
+    // (all 32 lanes run the schedule and the barrier waits, one elected lane issues: coordinates and addresses stay
+    //  on the uniform datapath)
+    const int bq = p.q_bcast ? 0 : b;
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < NQC; ++c) tma_load_3d(sQ + c * 16384, &tmap_q, q_full, h * p.dqk + c * 64, q0, bq);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        const int k0 = (tile_begin + j) * BN;
-        mbar_wait(&kv_empty[stage], phase ^ 1u);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      const int k0 = (tile_begin + j) * BN;
+      mbar_wait(&kv_empty[stage], phase ^ 1u);
+      if (elect_one()) {
         uint8_t* st = sKV + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
 #pragma unroll
@@ -140,67 +145,75 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int c = 0; c < NVC; ++c)
             tma_load_3d(st + (NQC + c) * Cfg::CHUNK_BYTES, &tmap_v, &kv_full[stage], h * p.dv + c * 64, k0, b);
         }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      // Descriptors differ only in their 14-bit start-address field, so each is one add away from a constant.
-      constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
-      const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-      const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
-      const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sKV) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES), Cfg::CHUNK_BYTES, 1024);
-      auto issue_s = [&](int j, int stage) {
-        const uint32_t d = tmem_base + (j & 1) * BN;
-        const uint64_t dk = dk0 + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+    // ================= MMA issuer =================
+    // All 32 lanes run the schedule and wait on the barriers; one elected lane issues each tcgen05 instruction and the
+    // descriptors advance as 32-bit low words.  (Inside an `if (lane == 0)` region every MMA cost ~25 dependent vector
+    // instructions + R2UR moves — several times the 32..128 cycles the MMA itself takes on the tensor pipe.)
+    constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
+    const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sKV) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES), Cfg::CHUNK_BYTES, 1024);
+    const uint32_t q_lo = (uint32_t)dq0, q_hi = (uint32_t)(dq0 >> 32);
+    const uint32_t p_lo = (uint32_t)dp0, p_hi = (uint32_t)(dp0 >> 32);
+    const uint32_t k_lo = (uint32_t)dk0, k_hi = (uint32_t)(dk0 >> 32);
+    const uint32_t v_lo = (uint32_t)dv0, v_hi = (uint32_t)(dv0 >> 32);
+    auto issue_s = [&](int j, int stage) {
+      const uint32_t d = tmem_base + (j & 1) * BN;
+      const uint32_t b0 = k_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < 4 * NQC; ++ks) {
-          if (ks < dqk_steps_total) {
-            const int c = ks >> 2, kk = ks & 3;
-            umma_ss(d, dq0 + (uint64_t)((c * 16384 + kk * 32) >> 4), dk + (uint64_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4),
-                    idesc_s, ks != 0 ? 1u : 0u);
-          }
+      for (int ks = 0; ks < 4 * NQC; ++ks) {
+        if (ks < dqk_steps_total) {
+          const int c = ks >> 2, kk = ks & 3;
+          if (elect_one())
+            umma_ss_lh(d, q_lo + (uint32_t)((c * 16384 + kk * 32) >> 4), q_hi,
+                       b0 + (uint32_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4), k_hi, idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[j & 1]);
-      };
-      auto issue_pv = [&](int j, int stage) {
-        const uint64_t dvs = dv0 + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
-        const uint64_t dpj = dp0 + (uint64_t)(((j & 1) * Cfg::P_BYTES) >> 4);
-        for (int nb = 0; nb * 256 < dv_n; ++nb) {
-          const int n = min(256, dv_n - nb * 256);
-          const uint32_t idesc_pv = make_idesc_f16(128, n, 1, 0, /*B MN-major*/ 1);
+      }
+      if (elect_one()) umma_commit(&s_full[j & 1]);
+    };
+    auto issue_pv = [&](int j, int stage) {
+      const uint32_t b0 = v_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+      const uint32_t a0 = p_lo + (uint32_t)(((j & 1) * Cfg::P_BYTES) >> 4);
+      for (int nb = 0; nb * 256 < dv_n; ++nb) {
+        const int n = min(256, dv_n - nb * 256);
+        const uint32_t idesc_pv = make_idesc_f16(128, n, 1, 0, /*B MN-major*/ 1);
 #pragma unroll
-          for (int ks = 0; ks < BN / 16; ++ks) {
-            umma_ss(tmem_o + nb * 256, dpj + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4),
-                    dvs + (uint64_t)((nb * 4 * Cfg::CHUNK_BYTES + ks * 2048) >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
-          }
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          if (elect_one())
+            umma_ss_lh(tmem_o + nb * 256, a0 + (uint32_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), p_hi,
+                       b0 + (uint32_t)((nb * 4 * Cfg::CHUNK_BYTES + ks * 2048) >> 4), v_hi, idesc_pv, (j | ks) != 0 ? 1u : 0u);
         }
-      };
-      mbar_wait(q_full, 0);
-      int stage = 0;       // stage of tile j
-      uint32_t phase = 0;
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == Cfg::STAGES) { nstage = 0; nphase ^= 1u; }
-        if (j + 1 < ntiles) {
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          issue_s(j + 1, nstage);   // overwrites S_{j-1}: its readers arrived on p_full before PV_{j-1} was issued
-        }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      }
+    };
+    mbar_wait(q_full, 0);
+    int stage = 0;       // stage of tile j
+    uint32_t phase = 0;
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == Cfg::STAGES) { nstage = 0; nphase ^= 1u; }
+      if (j + 1 < ntiles) {
+        mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
-        issue_pv(j, stage);
+        issue_s(j + 1, nstage);   // overwrites S_{j-1}: its readers arrived on p_full before PV_{j-1} was issued
+      }
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      issue_pv(j, stage);
+      if (elect_one()) {
         umma_commit(&kv_empty[stage]);
         umma_commit(&pv_done[j & 1]);
-        stage = nstage;
-        phase = nphase;
       }
+      stage = nstage;
+      phase = nphase;
     }
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue =================
@@ -217,24 +230,31 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const bool tail = (k0 + BN > p.Nk) || (km != nullptr);
-      // ---- pass 1: row max ----
-      float tmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tmem_wait_ld();
-        if (!tail) {
+      // ---- the whole S row of this tile (BN fp32 values) moves to registers with one wait ----
+      uint32_t r[BN];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(r[i]));
-        } else {
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      tmem_wait_ld();
+      if (tail) {
+        // masked / out-of-range keys become -inf: they drop out of the max and exp2 turns them into exact zeros
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int k = k0 + c * 32 + i;
-            const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
-            if (ok) tmax = fmaxf(tmax, __uint_as_float(r[i]));
-          }
+        for (int i = 0; i < BN; ++i) {
+          const int k = k0 + i;
+          const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
+          if (!ok) r[i] = 0xff800000u;
         }
+      }
+      float tmax;
+      {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < BN / 8; ++i) {
+          mx0 = fmax3(mx0, __uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+        }
+        tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
       tmax *= p.scale_log2;  // scale > 0, so max commutes (an all-masked tile stays -inf)
       // ---- running max update, lazy rescale ----
@@ -254,55 +274,52 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // O may only be rescaled once PV_{j-1} has retired (rare: the running max grew by more than 2^8)
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
-        for (int c = 0; c < dv_n; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_o + lane_off + c, r);
+#pragma unroll 1
+        for (int c = 0; c < dv_n; c += 16) {   // 16 columns at a time: the S row of this tile is live in registers
+          uint32_t o[16];
+          tmem_ld16(tmem_o + lane_off + c, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tmem_o + lane_off + c, r);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem_o + lane_off + c, o);
         }
         tmem_wait_st();
       }
       l *= alpha;
       m = m_use;
       const float msub = (m == -INFINITY) ? 0.0f : m;
-      // ---- pass 2: p = exp2(t - m), row sum, bf16 P tile into swizzled smem ----
-      float lsum = 0.f;
-#pragma unroll 1
+      // ---- p = exp2(scale * s - m) -> bf16 P tile in swizzled smem; the row sum uses the bf16-rounded values the
+      //      tensor core will multiply, so P and l stay consistent ----
+      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+      const uint64_t nm2 = pack_f32x2(-msub, -msub);
+      uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tmem_wait_ld();
-        float pv[32];
-        if (!tail) {
+        uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -msub));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int k = k0 + c * 32 + i;
-            const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
-            pv[i] = ok ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -msub)) : 0.0f;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
+                                    sc2, nm2);
+          float t0, t1;
+          unpack_f32x2(t2, t0, t1);
+          w[i] = pack_bf16x2(ex2_approx(t0), ex2_approx(t1));
+          const uint64_t pr = pack_f32x2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+          if (i & 1) lb = fadd2(lb, pr);
+          else la = fadd2(la, pr);
         }
         uint8_t* prow = sP + (j & 1) * Cfg::P_BYTES + ((c * 32) >> 6) * 16384;
         const int chunk0 = ((c * 32) & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16x2(pv[8 * g], pv[8 * g + 1]);
-          w.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-          w.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
-          w.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          *reinterpret_cast<uint4*>(prow + sw128_offset(row, chunk0 + g)) = w;
-          // the row sum uses the bf16-rounded values the tensor core will multiply (P and l stay consistent); they
-          // are unpacked from the packed words with integer ops so the conversion pipe is only used once
-          lsum += (__uint_as_float(w.x << 16) + __uint_as_float(w.x & 0xffff0000u)) +
-                  (__uint_as_float(w.y << 16) + __uint_as_float(w.y & 0xffff0000u));
-          lsum += (__uint_as_float(w.z << 16) + __uint_as_float(w.z & 0xffff0000u)) +
-                  (__uint_as_float(w.w << 16) + __uint_as_float(w.w & 0xffff0000u));
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(prow + sw128_offset(row, chunk0 + g)) =
+              make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      }
+      float lsum;
+      {
+        float a0, a1, b0, b1;
+        unpack_f32x2(la, a0, a1);
+        unpack_f32x2(lb, b0, b1);
+        lsum = (a0 + a1) + (b0 + b1);
       }
       l += lsum;
       fence_proxy_async_smem();

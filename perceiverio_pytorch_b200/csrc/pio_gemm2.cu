@@ -72,7 +72,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* res_full = tmem_empty + 2;              // [EPI_WARPS][2]  residual TMA -> epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::EPI_WARPS * 2);
 
-  const int warp = threadIdx.x >> 5;
+  // the shuffle makes the warp index provably warp-uniform, so the role code can use the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_gemm2_kernel: dynamic shared memory base is not 1024-byte aligned\n");
@@ -113,19 +114,20 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer (both CTAs) =================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair_id; t < total_tiles; t += num_pairs) {
-        const int nt = t % p.tiles_n;
-        const int mp = (t / p.tiles_n) % p.m_pairs;
-        const int z = t / (p.tiles_n * p.m_pairs);
-        const int m0 = mp * 256 + (int)crank * Cfg::BM;
-        const int n0 = nt * Cfg::BN + (int)(crank ^ (uint32_t)p.b_swap) * (Cfg::BN / 2);
-        const int za = p.a_bcast ? 0 : z, zb = p.b_bcast ? 0 : z;
-        for (int kc = 0; kc < num_k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // ================= TMA producer (both CTAs) =================
+    // (the whole warp runs the schedule and waits; one elected lane issues — keeps coordinates in uniform registers)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair_id; t < total_tiles; t += num_pairs) {
+      const int nt = t % p.tiles_n;
+      const int mp = (t / p.tiles_n) % p.m_pairs;
+      const int z = t / (p.tiles_n * p.m_pairs);
+      const int m0 = mp * 256 + (int)crank * Cfg::BM;
+      const int n0 = nt * Cfg::BN + (int)(crank ^ (uint32_t)p.b_swap) * (Cfg::BN / 2);
+      const int za = p.a_bcast ? 0 : z, zb = p.b_bcast ? 0 : z;
+      for (int kc = 0; kc < num_k_chunks; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           // both CTAs' bytes are credited to the leader's barrier, which expects the pair's total
@@ -133,14 +135,19 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t leader_bar = mapa_u32(&full_bar[stage], 0);
           tma_load_3d_2cta(sa, &tmap_a, leader_bar, kc * Cfg::BK, m0, za);
           tma_load_3d_2cta(sb, &tmap_b, leader_bar, kc * Cfg::BK, n0, zb);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0) {
       // ================= MMA issuer (leader CTA) =================
+      // All 32 lanes run the schedule and the barrier waits; one elected lane issues each tcgen05 instruction, and the
+      // descriptors advance as 32-bit low words (inside an `if (lane == 0)` region every MMA costs ~25 dependent
+      // vector instructions + R2UR moves, about as long as the 128-cycle MMA itself).
       constexpr uint32_t idesc = make_idesc_f16(256, Cfg::BN, /*bf16*/ 1, 0, 0);
+      const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint32_t d_lo = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -153,18 +160,17 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kc = 0; kc < num_k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t a_lo = d_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(sa + ks * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + ks * 32, 16, 1024);
-            umma_ss_2cta(d_tmem, da, db, idesc, (kc | ks) != 0 ? 1u : 0u);
+            if (elect_one())
+              umma_ss_2cta_lh(d_tmem, a_lo + ks * 2, d_hi, b_lo + ks * 2, d_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
           }
-          umma_commit_2cta_mcast(&empty_bar[stage], 0x3);   // frees the stage in both CTAs
+          if (elect_one()) umma_commit_2cta_mcast(&empty_bar[stage], 0x3);   // frees the stage in both CTAs
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2cta_mcast(&tmem_full[acc], 0x3);       // accumulator halves complete in both CTAs
+        if (elect_one()) umma_commit_2cta_mcast(&tmem_full[acc], 0x3);       // accumulator halves complete in both CTAs
       }
     }
   } else if (warp >= 4) {

@@ -302,10 +302,10 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     if shard is None:
         o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk)
     else:
-        parts = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=None,
-                                     partial=True, num_splits=shard.local_splits)
+        parts, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km,
+                                            row_keep=None, partial=True,
+                                            num_splits=shard.local_splits if shard.local_splits > 0 else None)
         o = shard.combine(parts, row_keep=rk)
-        width = pa.Ck if pa.folded else pa.V
     if use_query_residual:
         res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
     else:

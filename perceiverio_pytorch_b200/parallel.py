@@ -64,9 +64,9 @@ def packed_views(buf: torch.Tensor, rows: int, dv: int):
 class KeyShard:
     """State of a key-axis shard of the encoder cross-attend across the ranks of `group`."""
 
-    def __init__(self, group=None, local_splits: int = 1):
+    def __init__(self, group=None, local_splits: int = 0):
         self.group = group
-        self.local_splits = local_splits
+        self.local_splits = local_splits   # key splits inside this rank's slice; 0 = pick to fill the SMs
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -108,7 +108,7 @@ class KeyShard:
                                      shape=(self.world, B, H, Nq, dv))
 
 
-def shard_encoder_keys(encoder, group=None, local_splits: int = 1):
+def shard_encoder_keys(encoder, group=None, local_splits: int = 0):
     """Mark `encoder` (a PerceiverEncoder of this package) as key-sharded: its forward then expects this rank's slice
     of the input array (see `shard_keys`) and returns the full latents on every rank."""
     encoder.key_shard = KeyShard(group, local_splits)

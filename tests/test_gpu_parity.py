@@ -159,3 +159,31 @@ def test_config_shapes_match_oracle(name):
     eo = rel_err(out.cpu(), out_ref)
     print(f"{name}: latents max {ez[0]:.3e} l2 {ez[1]:.3e}; output max {eo[0]:.3e} l2 {eo[1]:.3e}")
     assert ez[0] <= BF16_TOL and eo[0] <= BF16_TOL, (ez, eo)
+
+
+def test_key_sharded_encoder_matches_unsharded_single_rank():
+    """The key-axis shard path (partial attention -> packed exchange -> LSE combine) with world size 1 and two local
+    key splits must reproduce the plain path and the oracle (the collective itself is covered by the gloo tests and by
+    tools/encoder_sweep.py --check under torchrun)."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import parallel
+    from oracle import perceiver_oracle as O
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(num_input_channels=261, num_self_attends_per_block=1, num_blocks=1, num_latents=512,
+                               num_latent_channels=1024).eval()
+    _perturb(enc, 3)
+    B, Nk = 2, 9000 + 37
+    x = torch.randn(B, Nk, 261)
+    mask = torch.rand(B, Nk) > 0.2
+    mask[1, Nk // 2:] = False
+    p = {k: v.detach() for k, v in enc.state_dict().items()}
+    ref = O.encoder_forward(p, "", num_blocks=1, num_self_attends_per_block=1, num_cross_attend_heads=1,
+                            num_self_attend_heads=8, use_query_residual=True, inputs=x, input_mask=mask)
+    enc = enc.cuda()
+    with torch.inference_mode():
+        xc, mc = x.cuda(), mask.cuda()
+        plain = enc(xc, enc.latents(xc), input_mask=mc)
+        parallel.shard_encoder_keys(enc, group=None, local_splits=2)
+        sharded = enc(xc, enc.latents(xc), input_mask=mc)
+    assert rel_err(sharded.cpu(), plain.cpu())[0] <= 5e-3
+    assert rel_err(sharded.cpu(), ref)[0] <= BF16_TOL
