@@ -83,9 +83,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples received while the timed region ran (wall interval [t0, t1]); the sampler itself is
+        started before the warm-up because nvidia-smi needs a few hundred ms to produce its first row."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +97,16 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.15]
+            if inside:
+                rows = inside
+            else:   # region shorter than the sampling period: take the samples closest to it
+                rows = [r for r in rows if t0 - 1.0 <= r[0] <= t1 + 1.0]
+                window = "within 1 s of the timed region (region shorter than the 100 ms sampling period)"
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -109,7 +120,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def peaks():
@@ -237,24 +249,25 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step(inputs)
     sync_all()
 
     # ---- timed region 1: device-resident inputs ----
-    sampler = ClockSampler(local)
-    sampler.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step(inputs)
     e1.record()
     sync_all()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches_eager_per_step = None
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -32,7 +32,10 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
                                                                 const float* __restrict__ beta, long long rows, int C,
                                                                 int normalize, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  // Rows are walked from the END of the array: x was just written front-to-back by the producing GEMM (or H2D copy),
+  // so its tail is what is still resident in the 126 MB L2; and the bf16 rows written last (the front) are the first
+  // ones the consuming GEMM's TMA loads ask for.
+  const long long row = (long long)(gridDim.x - 1 - blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   const int nvec = C >> 2;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ beta, long long rows, int C,
                                                             int normalize, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * ROWS;
+  const long long row0 = ((long long)(gridDim.x - 1 - blockIdx.x) * 4 + (threadIdx.x >> 5)) * ROWS;   // back to front, see above
   if (row0 >= rows) return;
   float v[ROWS][MAXV];
   float s[ROWS];
