@@ -2,13 +2,17 @@
 //
 // One CTA = one 128-query tile of one (batch, head) [and one key split].  K/V tiles stream through a TMA ring
 // (SWIZZLE_128B, 64-column chunks); S = Q.K^T is accumulated by tcgen05.mma into a double-buffered TMEM tile, the
-// softmax warps read it with tcgen05.ld, keep running max / sum in registers (fp32, log2 domain), write P as bf16 into
-// a swizzled smem tile, and O += P.V is accumulated in TMEM by a second tcgen05.mma whose B operand is the V tile read
-// MN-major — so when K and V are the same array (the folded single-head cross-attends) one TMA load
+// softmax warps read it with tcgen05.ld, keep running max / sum in registers (fp32, log2 domain), overwrite S in place
+// with bf16 P (tcgen05.st), and O += P.V is accumulated in TMEM by a second tcgen05.mma whose A operand is P in TMEM
+// and whose B operand is the V tile read MN-major — so when K and V are the same array (the folded single-head cross-attends) one TMA load
 // feeds both products.  O is rescaled lazily (only when the running max grows by more than 2^8).
 //
-// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
-// warps 4..7 softmax / correction / epilogue (thread = one query row = one TMEM lane).
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
+// warps 4..11 softmax / correction / epilogue: thread = one query row (TMEM lane) x one half of the tile's key columns.
+// The two warps that share a lane quarter exchange their partial row maxima through shared memory once per tile
+// (a 64-thread named barrier), keep separate partial row sums, and split the O columns for the rescale and the
+// epilogue.  With one warp per scheduler the softmax was latency-bound (ncu: the MMA issuer waiting on p_full); two
+// warps per scheduler halve the per-tile softmax time.
 #include <math.h>
 #include <stdlib.h>
 
@@ -31,36 +35,35 @@ struct FlashParams {
 template <int NQC, int NVC, bool SAME>
 struct FlashCfg {
   static constexpr int KV_CHUNKS = SAME ? NQC : (NQC + NVC);
-  static constexpr int SMEM_LIMIT = 232448 - 256;  // 227 KB minus the barrier block
-  // BN = 128 needs Q + two P buffers (2 x 32 KB) + two K/V stages in shared memory and 2 x 128 + dv columns of TMEM
-  static constexpr int SMEM128 = NQC * 16384 + 2 * 32768 + 2 * KV_CHUNKS * 16384;
+  static constexpr int BAR_BYTES = 256 + 2048;     // mbarriers + the row-max / row-sum exchange buffer
+  static constexpr int SMEM_LIMIT = 232448 - BAR_BYTES;  // 227 KB minus that block
+  // BN = 128 needs Q + three K/V stages in shared memory and 2 x 128 + dv columns of TMEM (P lives in TMEM)
+  static constexpr int SMEM128 = NQC * 16384 + 3 * KV_CHUNKS * 16384;
   static constexpr int TMEM128 = 2 * 128 + NVC * 64;
   static constexpr int BN = (SMEM128 <= SMEM_LIMIT && TMEM128 <= 512) ? 128 : 64;
   static constexpr int CHUNK_BYTES = BN * 128;            // one 64-column chunk of a K/V tile
   static constexpr int STAGE_BYTES = KV_CHUNKS * CHUNK_BYTES;
   static constexpr int Q_BYTES = NQC * 16384;
-  static constexpr int P_BYTES = (BN / 64) * 16384;       // one P buffer; there are two
-  static constexpr int AVAIL = SMEM_LIMIT - Q_BYTES - 2 * P_BYTES;
+  static constexpr int AVAIL = SMEM_LIMIT - Q_BYTES;
   static constexpr int STAGES_RAW = AVAIL / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
   static constexpr int TMEM_NEED = 2 * BN + NVC * 64;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
-  static constexpr int SMEM_USED = Q_BYTES + 2 * P_BYTES + STAGES * STAGE_BYTES + 256;
+  static constexpr int SMEM_USED = Q_BYTES + STAGES * STAGE_BYTES + BAR_BYTES;
   // request > half of the SM's shared memory so that exactly one CTA is resident per SM (TMEM is not oversubscribed)
   static constexpr int SMEM_BYTES = SMEM_USED < 120 * 1024 ? 120 * 1024 : SMEM_USED;
   static constexpr bool VALID = STAGES >= 2 && TMEM_NEED <= 512 && SMEM_USED <= 232448;
 };
 
 template <int NQC, int NVC, bool SAME>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
   using Cfg = FlashCfg<NQC, NVC, SAME>;
   constexpr int BN = Cfg::BN;
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory: the window starts 1024-aligned
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + Cfg::Q_BYTES;                 // two P buffers (tile j uses buffer j & 1)
-  uint8_t* sKV = sP + 2 * Cfg::P_BYTES;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* q_full = bars;                         // [1]
   uint64_t* kv_full = bars + 1;                    // [STAGES]
@@ -69,6 +72,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* p_full = s_full + 2;                   // [2]  P_j written          (softmax -> MMA, 128 arrivals)
   uint64_t* pv_done = p_full + 2;                  // [2]  O += P_j V_j retired (MMA -> softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 slots][2 halves][128 rows]
 
   // the shuffle makes the warp index provably warp-uniform, so role code can use the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -100,7 +104,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
@@ -155,11 +159,9 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // instructions + R2UR moves — several times the 32..128 cycles the MMA itself takes on the tensor pipe.)
     constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
     const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-    const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
     const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sKV) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES), Cfg::CHUNK_BYTES, 1024);
     const uint32_t q_lo = (uint32_t)dq0, q_hi = (uint32_t)(dq0 >> 32);
-    const uint32_t p_lo = (uint32_t)dp0, p_hi = (uint32_t)(dp0 >> 32);
     const uint32_t k_lo = (uint32_t)dk0, k_hi = (uint32_t)(dk0 >> 32);
     const uint32_t v_lo = (uint32_t)dv0, v_hi = (uint32_t)(dv0 >> 32);
     auto issue_s = [&](int j, int stage) {
@@ -178,15 +180,15 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     };
     auto issue_pv = [&](int j, int stage) {
       const uint32_t b0 = v_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
-      const uint32_t a0 = p_lo + (uint32_t)(((j & 1) * Cfg::P_BYTES) >> 4);
+      const uint32_t a0 = tmem_base + (j & 1) * BN;   // P_j overlays the first BN/2 columns of S_j (bf16 pairs)
       for (int nb = 0; nb * 256 < dv_n; ++nb) {
         const int n = min(256, dv_n - nb * 256);
-        const uint32_t idesc_pv = make_idesc_f16(128, n, 1, 0, /*B MN-major*/ 1);
+        const uint32_t idesc_pv = make_idesc_f16(128, n, 1, /*A (TMEM) K-major*/ 0, /*B MN-major*/ 1);
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks) {
           if (elect_one())
-            umma_ss_lh(tmem_o + nb * 256, a0 + (uint32_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), p_hi,
-                       b0 + (uint32_t)((nb * 4 * Cfg::CHUNK_BYTES + ks * 2048) >> 4), v_hi, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            umma_ts_lh(tmem_o + nb * 256, a0 + ks * 8, b0 + (uint32_t)((nb * 4 * Cfg::CHUNK_BYTES + ks * 2048) >> 4), v_hi,
+                       idesc_pv, (j | ks) != 0 ? 1u : 0u);
         }
       }
     };
@@ -203,7 +205,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (j + 1 < ntiles) {
         mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
-        issue_s(j + 1, nstage);   // overwrites S_{j-1}: its readers arrived on p_full before PV_{j-1} was issued
+        issue_s(j + 1, nstage);   // overwrites S_{j-1} / P_{j-1}: in order after PV_{j-1}, which consumed P_{j-1}
       }
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -217,28 +219,35 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue =================
+    constexpr int HC = BN / 2;            // key columns of a tile handled by this thread
     const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const int q = q0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint8_t* km = p.key_mask ? p.key_mask + (long long)b * p.stride_km : nullptr;
-    float m = -INFINITY;  // running max of scale_log2 * s
-    float l = 0.f;        // running sum of exp2(t - m)
+    // O columns owned by this half for the rescale and the epilogue (32-column chunks)
+    const int nchunks = (dv_n + 31) / 32;
+    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2 * 32;
+    const int c_end = half == 0 ? min(dv_n, (nchunks + 1) / 2 * 32) : dv_n;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
+    float m = -INFINITY;  // running max of scale_log2 * s (identical in both halves)
+    float l = 0.f;        // running sum of exp2(t - m) over this half's columns
     for (int j = 0; j < ntiles; ++j) {
-      const int k0 = (tile_begin + j) * BN;
-      const uint32_t t_s = tmem_base + (j & 1) * BN + lane_off;
+      const int k0 = (tile_begin + j) * BN + half * HC;
+      const uint32_t t_s = tmem_base + (j & 1) * BN + half * HC + lane_off;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const bool tail = (k0 + BN > p.Nk) || (km != nullptr);
-      // ---- the whole S row of this tile (BN fp32 values) moves to registers with one wait ----
-      uint32_t r[BN];
+      const bool tail = (k0 + HC > p.Nk) || (km != nullptr);
+      // ---- this half of the S row moves to registers with one wait ----
+      uint32_t r[HC];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      for (int c = 0; c < HC / 32; ++c) tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
       tmem_wait_ld();
       if (tail) {
         // masked / out-of-range keys become -inf: they drop out of the max and exp2 turns them into exact zeros
 #pragma unroll
-        for (int i = 0; i < BN; ++i) {
+        for (int i = 0; i < HC; ++i) {
           const int k = k0 + i;
           const bool ok = (k < p.Nk) && (km == nullptr || km[k] != 0);
           if (!ok) r[i] = 0xff800000u;
@@ -248,7 +257,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < BN / 8; ++i) {
+        for (int i = 0; i < HC / 8; ++i) {
           mx0 = fmax3(mx0, __uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
           mx1 = fmax3(mx1, __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
           mx2 = fmax3(mx2, __uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
@@ -256,8 +265,16 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
+      // ---- the row max over the whole tile: exchange with the partner warp (slots alternate with the tile parity, so
+      //      one barrier per tile is enough) ----
+      {
+        float* slot = xchg + (j & 1) * 256;
+        slot[half * 128 + row] = tmax;
+        pair_sync();
+        tmax = fmaxf(tmax, slot[(half ^ 1) * 128 + row]);
+      }
       tmax *= p.scale_log2;  // scale > 0, so max commutes (an all-masked tile stays -inf)
-      // ---- running max update, lazy rescale ----
+      // ---- running max update, lazy rescale (both halves take identical decisions) ----
       float m_use = m;
       const bool grow = tmax > m + 8.0f;  // also true for the first valid tile (m == -inf)
       float alpha = 1.0f;
@@ -266,16 +283,12 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         m_use = tmax;
       }
       const bool any_grow = __any_sync(0xffffffffu, grow && j > 0 && m != -INFINITY);
-      if (j >= 2) {
-        // P buffer j&1 was last read by PV_{j-2}
-        mbar_wait(&pv_done[j & 1], ((j >> 1) - 1) & 1);
-      }
       if (any_grow) {
         // O may only be rescaled once PV_{j-1} has retired (rare: the running max grew by more than 2^8)
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < dv_n; c += 16) {   // 16 columns at a time: the S row of this tile is live in registers
+        for (int c = c_begin; c < c_end; c += 16) {   // 16 columns at a time: the S row of this tile is live in registers
           uint32_t o[16];
           tmem_ld16(tmem_o + lane_off + c, o);
           tmem_wait_ld();
@@ -294,7 +307,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint64_t nm2 = pack_f32x2(-msub, -msub);
       uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < HC / 32; ++c) {
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -307,26 +320,27 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (i & 1) lb = fadd2(lb, pr);
           else la = fadd2(la, pr);
         }
-        uint8_t* prow = sP + (j & 1) * Cfg::P_BYTES + ((c * 32) >> 6) * 16384;
-        const int chunk0 = ((c * 32) & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(prow + sw128_offset(row, chunk0 + g)) =
-              make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+        // P overwrites S in place (two bf16 values per 32-bit column).  Both warps of the pair have their S values in
+        // registers (the pair barrier above), so no unread S column is clobbered.
+        tmem_st16(tmem_base + (j & 1) * BN + lane_off + (half * HC + c * 32) / 2, w);
       }
-      float lsum;
       {
         float a0, a1, b0, b1;
         unpack_f32x2(la, a0, a1);
         unpack_f32x2(lb, b0, b1);
-        lsum = (a0 + a1) + (b0 + b1);
+        l += (a0 + a1) + (b0 + b1);
       }
-      l += lsum;
-      fence_proxy_async_smem();
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[j & 1]);
     }
-    // ---- epilogue ----
+    // ---- epilogue: total row sum = both halves' partial sums ----
+    {
+      float* slot = xchg + (ntiles & 1) * 256;   // the slot the last tile did not use
+      slot[half * 128 + row] = l;
+      pair_sync();
+      l += slot[(half ^ 1) * 128 + row];
+    }
     mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     const bool keep = (q < p.Nq) && (p.row_keep == nullptr || p.row_keep[(long long)b * p.stride_rk + q] != 0);
@@ -334,7 +348,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (!emit_partial) {
       const float inv = (keep && l > 0.f) ? 1.0f / l : 0.0f;
       __nv_bfloat16* orow = p.O + (long long)b * p.strideO + (long long)q * p.ldo + (long long)h * p.dv;
-      for (int c = 0; c < dv_n; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_o + lane_off + c, r);
         tmem_wait_ld();
@@ -359,12 +373,12 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     } else {
       const long long prow = (((long long)split * p.B + b) * p.H + h) * p.Nq + q;
-      if (q < p.Nq) {
+      if (q < p.Nq && half == 0) {
         p.m_part[prow] = (m == -INFINITY) ? -INFINITY : m * 0.69314718055994531f;  // back to natural-log units
         p.l_part[prow] = l;
       }
       float* orow = p.O_part + prow * p.dv;
-      for (int c = 0; c < dv_n; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_o + lane_off + c, r);
         tmem_wait_ld();
@@ -447,7 +461,7 @@ static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cuda
   dim3 grid((a->Nq + 127) / 128, a->B * a->H, p.num_splits);
   {
     ProfileScope prof(KF_FLASH, 2.0 * a->B * a->H * (double)a->Nq * a->Nk * (a->dqk + a->dv), 0.0, stream);
-    pio_flash_kernel<NQC, NVC, SAME><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    pio_flash_kernel<NQC, NVC, SAME><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
