@@ -396,4 +396,9 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) {
   return r * 128u + ((chunk16 ^ (r & 7u)) << 4);
 }
 
+// Same for a [rows x 64 B] SWIZZLE_64B tile: chunk index (2 bits) XOR ((row / 2) % 4).
+__device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t chunk16) {
+  return r * 64u + ((chunk16 ^ ((r >> 1) & 3u)) << 4);
+}
+
 }  // namespace pio

@@ -461,7 +461,8 @@ static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cuda
   dim3 grid((a->Nq + 127) / 128, a->B * a->H, p.num_splits);
   {
     ProfileScope prof(KF_FLASH, 2.0 * a->B * a->H * (double)a->Nq * a->Nk * (a->dqk + a->dv), 0.0, stream);
-    pio_flash_kernel<NQC, NVC, SAME><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    PIO_CUDA_OK(launch_kernel(pio_flash_kernel<NQC, NVC, SAME>, grid, dim3(384, 1, 1), Cfg::SMEM_BYTES, stream, 1, tq, tk,
+                              tv, p));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

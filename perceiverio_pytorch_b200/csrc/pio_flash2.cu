@@ -464,7 +464,8 @@ static int launch_flash2_cfg(const pio_attention_args* a, const DeviceInfo& dev,
   const int grid = p.items < dev.sm_count ? p.items : dev.sm_count;
   {
     ProfileScope prof(KF_FLASH, 2.0 * a->B * a->H * (double)a->Nq * a->Nk * (a->dqk + a->dv), 0.0, stream);
-    pio_flash2_kernel<NQC, NVC, BN><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    PIO_CUDA_OK(launch_kernel(pio_flash2_kernel<NQC, NVC, BN>, dim3((unsigned)grid, 1, 1), dim3(384, 1, 1), Cfg::SMEM_BYTES,
+                              stream, 1, tq, tk, tv, p));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

@@ -407,19 +407,8 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   if (total < clusters) clusters = (int)total;
   {
     ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, 0.0, stream);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
-    cfg.blockDim = dim3(384, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PIO_CUDA_OK(cudaLaunchKernelEx(&cfg, pio_gemm_kernel<BN, B_MN, CL>, ta, tb, ep));
+    PIO_CUDA_OK(launch_kernel(pio_gemm_kernel<BN, B_MN, CL>, dim3((unsigned)(clusters * CL), 1, 1), dim3(384, 1, 1),
+                              Cfg::SMEM_BYTES, stream, CL, ta, tb, ep));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

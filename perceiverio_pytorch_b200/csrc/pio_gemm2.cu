@@ -43,11 +43,13 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (KIND == G2_BF16) ? 5 : 4;
+  static constexpr int STAGES = 5;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int SLOT_BYTES = 4096;              // 32 rows x 128 B
+  // staging slots: bf16 output 32 rows x 64 columns (128-byte rows, SWIZZLE_128B); fp32 32 rows x 16 columns (64-byte
+  // rows, SWIZZLE_64B) so that two residual + two output slots per warp leave room for the fifth operand stage
+  static constexpr int SLOT_BYTES = (KIND == G2_F32) ? 2048 : 4096;
   static constexpr int RES_SLOTS = (KIND == G2_F32) ? 2 : 0;
-  static constexpr int OUT_SLOTS = (KIND == G2_F32) ? 1 : 2;
+  static constexpr int OUT_SLOTS = 2;
   static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
   static constexpr int BAR_BYTES = 512;
@@ -182,7 +184,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_out = my + Cfg::RES_SLOTS * Cfg::SLOT_BYTES;
     uint64_t* my_res_full = res_full + ew * 2;
     const bool has_res = (KIND == G2_F32) && p.has_residual;
-    constexpr int CHUNK_COLS = (KIND == G2_F32) ? 32 : 64;
+    constexpr int CHUNK_COLS = (KIND == G2_F32) ? 16 : 64;
     constexpr int CHUNKS = 128 / CHUNK_COLS;           // chunks of this warp's column half per tile
     const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
@@ -225,20 +227,22 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = nt * Cfg::BN + half * 128 + c * CHUNK_COLS;
         float v[CHUNK_COLS];
-        {
-          uint32_t r[32];
+        if constexpr (CHUNK_COLS == 64) {
+          uint32_t r[32], r2[32];
           tmem_ld32(t_row + c * CHUNK_COLS, r);
-          if constexpr (CHUNK_COLS == 64) {
-            uint32_t r2[32];
-            tmem_ld32(t_row + c * CHUNK_COLS + 32, r2);
-            tmem_wait_ld();
+          tmem_ld32(t_row + c * CHUNK_COLS + 32, r2);
+          tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[32 + j] = fmaf(__uint_as_float(r2[j]), p.alpha, row_bias);
-          } else {
-            tmem_wait_ld();
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
+            v[32 + j] = fmaf(__uint_as_float(r2[j]), p.alpha, row_bias);
           }
+        } else {
+          uint32_t r[16];
+          tmem_ld16(t_row + c * CHUNK_COLS, r);
+          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
         }
         if (c == CHUNKS - 1) {
           // this warp has read its whole share of the accumulator: hand the TMEM buffer back to the MMA issuer
@@ -269,22 +273,22 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&my_res_full[slot], (use_idx >> 1) & 1u);
             const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 rq = *reinterpret_cast<const float4*>(rs + sw128_offset(lane, j));
+            for (int j = 0; j < 4; ++j) {
+              const float4 rq = *reinterpret_cast<const float4*>(rs + sw64_offset(lane, j));
               v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
             }
           }
-          // the staging slot is free once the previous chunk's TMA store has read it
-          if (lane == 0) bulk_wait_read<0>();
+          uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(my_out + sw128_offset(lane, j)) =
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(slot_out + sw64_offset(lane, j)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
           if (lane == 0) {
-            tma_store_3d(&tmap_out, my_out, col0, row0, z);
+            tma_store_3d(&tmap_out, slot_out, col0, row0, z);
             bulk_commit();
             if (has_res) issue_res();   // refills the residual slot that was just consumed
           }
@@ -350,15 +354,15 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   if (KIND == G2_F32) {
     const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
     const uint64_t strides[2] = {(uint64_t)a->ldo32 * 4, (uint64_t)(a->batch > 1 ? a->strideO32 : a->ldo32 * (int64_t)a->M) * 4};
-    const uint32_t box[3] = {32, 32, 1};
-    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box);
+    const uint32_t box[3] = {16, 32, 1};
+    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, 64);
     if (rc != PIO_OK) return rc;
     tr = to;
     if (a->residual) {
       const uint64_t rb = r_bcast ? 1 : a->batch;
       const uint64_t rdims[3] = {(uint64_t)a->N, (uint64_t)a->M, rb};
       const uint64_t rstrides[2] = {(uint64_t)a->ldr * 4, (uint64_t)(rb > 1 ? a->strideR : a->ldr * (int64_t)a->M) * 4};
-      rc = encode_tmap(&tr, a->residual, true, 3, rdims, rstrides, box);
+      rc = encode_tmap(&tr, a->residual, true, 3, rdims, rstrides, box, 64);
       if (rc != PIO_OK) return rc;
     }
   } else {
@@ -395,19 +399,8 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   {
     const double bytes = (KIND == G2_F32 ? 4.0 * (a->residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
     ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, bytes, stream);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(pairs * 2), 1, 1);
-    cfg.blockDim = dim3(384, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PIO_CUDA_OK(cudaLaunchKernelEx(&cfg, pio_gemm2_kernel<KIND>, ta, tb, to, tr, p));
+    PIO_CUDA_OK(launch_kernel(pio_gemm2_kernel<KIND>, dim3((unsigned)(pairs * 2), 1, 1), dim3(384, 1, 1), Cfg::SMEM_BYTES,
+                              stream, 2, ta, tb, to, tr, p));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

@@ -1,6 +1,7 @@
 // Host plumbing: last-error storage, device info cache, TMA tensor-map encoding, ABI bookkeeping.
 #include "pio_host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -75,11 +76,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
-  return encode_tmap(map, base, /*is_f32=*/false, rank, dims, strides_bytes, box);
+  return encode_tmap(map, base, /*is_f32=*/false, rank, dims, strides_bytes, box, 128);
 }
 
 int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(PIO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -94,7 +95,8 @@ int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const
   }
   CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(PIO_ERR_CUDA,

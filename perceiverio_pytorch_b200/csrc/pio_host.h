@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <utility>
 
 #include "../../include/pio_b200.h"
 
@@ -52,9 +53,9 @@ int get_device_info(DeviceInfo* out);
 // Encodes a bf16 tensor of rank `rank` (dims[0] innermost) with SWIZZLE_128B and zero OOB fill.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 entries, for dims[1..] */, const uint32_t* box);
-// Same for fp32 (is_f32) or bf16 elements; the box's inner extent must span exactly 128 bytes (SWIZZLE_128B).
+// Same for fp32 (is_f32) or bf16 elements; the box's inner extent must span exactly `swizzle_bytes` (128 or 64) bytes.
 int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box);
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 // Optional per-launch profiling: when enabled (pio_profile_enable), every entry point brackets its kernel launch
 // with CUDA events recorded on the launching stream *inside* the library, so the interval contains the kernel and
@@ -77,6 +78,31 @@ int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t str
 // Persistent two-tile attention kernel (pio_flash2.cu)
 bool flash2_eligible(const pio_attention_args* a);
 int launch_flash2(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream);
+
+// cudaLaunchKernelEx with an optional cluster width.  (Programmatic dependent launch was tried for these kernels and
+// measured slower — 33.1 vs 31.7 ms per bench step: every kernel fills all SMs with one large-smem CTA, so a dependent
+// grid can only overlap its prologue with the predecessor's last wave — and is not used.)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

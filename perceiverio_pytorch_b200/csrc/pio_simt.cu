@@ -337,8 +337,8 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
     const int need = (int)((a->ldy / 4 + 31) / 32);
 #define PIO_LNV_LAUNCH(NV)                                                                                        \
-  pio_layernorm_vec_kernel<NV><<<(unsigned)blocks, 128, 0, stream>>>(a->x, a->ldx, y, a->ldy, a->gamma, a->beta, \
-                                                                     a->rows, a->C, a->normalize, a->eps)
+  launch_kernel(pio_layernorm_vec_kernel<NV>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x, (long long)a->ldx, y, \
+                (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C, (int)a->normalize, a->eps)
     if (need <= 2) PIO_LNV_LAUNCH(2);
     else if (need <= 4) PIO_LNV_LAUNCH(4);
     else if (need <= 8) PIO_LNV_LAUNCH(8);
@@ -351,8 +351,9 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     const long long blocks = (a->rows + 4 * rows_per_warp - 1) / (4 * rows_per_warp);
     PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
 #define PIO_LN_LAUNCH(MAXV, ROWS)                                                                                      \
-  pio_layernorm_kernel<MAXV, ROWS><<<(unsigned)blocks, 128, 0, stream>>>(a->x, a->ldx, y, a->ldy, a->gamma, a->beta, \
-                                                                         a->rows, a->C, a->normalize, a->eps)
+  launch_kernel(pio_layernorm_kernel<MAXV, ROWS>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x,                 \
+                (long long)a->ldx, y, (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C,              \
+                (int)a->normalize, a->eps)
     if (need <= 4) PIO_LN_LAUNCH(4, 2);
     else if (need <= 12) PIO_LN_LAUNCH(12, 2);
     else if (need <= 24) PIO_LN_LAUNCH(24, 1);
