@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 2
+#define PIO_ABI_VERSION 3
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -60,6 +60,10 @@ typedef struct pio_layernorm_args {
   int32_t C;
   int32_t normalize;
   float eps;
+  int32_t split;    /* validation mode (bf16 x 2 split operands): y has ldy = 3 * pad8(C) columns laid out as
+                       [hi | lo | hi] (split = 1, the A side of a product) or [hi | hi | lo] (split = 2, the B side) with
+                       hi = bf16(v), lo = bf16(v - hi); one K = 3 * pad8(C) GEMM of an A-side by a B-side operand
+                       evaluates hi*hi + lo*hi + hi*lo in fp32 */
 } pio_layernorm_args;
 int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream);
 
@@ -111,6 +115,7 @@ typedef struct pio_softmax_args {
   const uint8_t* row_keep; int64_t stride_rk;     /* [batch, rows] 1 = keep, or NULL */
   int32_t batch, rows, cols;
   float scale;
+  int32_t split;    /* validation mode: P has ldp = 3 * pad8(cols) columns laid out as [hi | lo | hi] */
 } pio_softmax_args;
 int pio_softmax_bf16(const pio_softmax_args* a, void* stream);
 

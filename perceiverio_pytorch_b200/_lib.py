@@ -25,7 +25,7 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 class LayerNormArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
-                ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32)]
+                ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32), ("split", i32)]
 
 
 class GemmArgs(C.Structure):
@@ -48,7 +48,7 @@ class SoftmaxArgs(C.Structure):
                 ("key_mask", vp), ("stride_km", i64),
                 ("row_keep", vp), ("stride_rk", i64),
                 ("batch", i32), ("rows", i32), ("cols", i32),
-                ("scale", f32)]
+                ("scale", f32), ("split", i32)]
 
 
 class AttentionArgs(C.Structure):
@@ -114,7 +114,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 2:
+        if lib.pio_abi_version() != 3:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

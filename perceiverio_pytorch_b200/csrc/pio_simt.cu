@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
                                                                 __nv_bfloat16* __restrict__ y, long long ldy,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, long long rows, int C,
-                                                                int normalize, float eps) {
+                                                                int mode, float eps) {
+  const int normalize = mode & 1;
   const int lane = threadIdx.x & 31;
   // Rows are walked from the END of the array: x was just written front-to-back by the producing GEMM (or H2D copy),
   // so its tail is what is still resident in the 126 MB L2; and the bf16 rows written last (the front) are the first
@@ -61,7 +62,10 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
     rstd = rsqrtf(warp_sum(q) / (float)C + eps);
   }
   uint2* yr = reinterpret_cast<uint2*>(y + row * ldy);
-  const int nvec_out = (int)(ldy >> 2);
+  // validation mode: three segments of ldy / 3 columns, [hi | lo | hi] (A side, bit 1) or [hi | hi | lo] (B side, bit 2)
+  const bool split = (mode & 6) != 0;
+  const bool b_side = (mode & 4) != 0;
+  const int nvec_out = split ? (int)((ldy / 3) >> 2) : (int)(ldy >> 2);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
@@ -79,7 +83,14 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
           o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
         }
       }
-      yr[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      const uint2 hi = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      yr[c] = hi;
+      if (split) {
+        const uint2 lo = make_uint2(pack_bf16x2(o.x - __uint_as_float(hi.x << 16), o.y - __uint_as_float(hi.x & 0xffff0000u)),
+                                    pack_bf16x2(o.z - __uint_as_float(hi.y << 16), o.w - __uint_as_float(hi.y & 0xffff0000u)));
+        yr[nvec_out + c] = b_side ? hi : lo;
+        yr[2 * nvec_out + c] = b_side ? lo : hi;
+      }
     }
   }
 }
@@ -89,7 +100,12 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ y, long long ldy,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows, int C,
-                                                            int normalize, float eps) {
+                                                            int mode, float eps) {
+  const int normalize = mode & 1;
+  // validation mode: three segments of ldy / 3 columns, [hi | lo | hi] (A side, bit 1) or [hi | hi | lo] (B side, bit 2)
+  const bool split = (mode & 6) != 0;
+  const bool b_side = (mode & 4) != 0;
+  const int seg = split ? (int)(ldy / 3) : (int)ldy;
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)(gridDim.x - 1 - blockIdx.x) * 4 + (threadIdx.x >> 5)) * ROWS;   // back to front, see above
   if (row0 >= rows) return;
@@ -126,14 +142,20 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + 32 * i;
-      if (c < ldy) {
+      if (c < seg) {
         float o = 0.f;
         if (c < C) {
           o = (v[r][i] - mean) * rstd;
           if (gamma) o = o * __ldg(gamma + c);
           if (beta) o += __ldg(beta + c);
         }
-        yr[c] = __float2bfloat16_rn(o);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        yr[c] = hi;
+        if (split) {
+          const __nv_bfloat16 lo = __float2bfloat16_rn(o - __bfloat162float(hi));
+          yr[seg + c] = b_side ? hi : lo;
+          yr[2 * seg + c] = b_side ? lo : hi;
+        }
       }
     }
   }
@@ -154,6 +176,7 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   const uint8_t* km = a.key_mask ? a.key_mask + (long long)b * a.stride_km : nullptr;
   const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + r] != 0 : true;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = a.split ? (int)(a.ldp / 3) : (int)a.ldp;   // validation mode: [hi | lo | hi] segments
   if (!keep) {
     for (int c = tid; c < a.ldp; c += 256) p[c] = __float2bfloat16_rn(0.f);
     return;
@@ -189,10 +212,15 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   }
   __syncthreads();
   const float inv = bcast;
-  for (int c = tid; c < a.ldp; c += 256) {
+  for (int c = tid; c < seg; c += 256) {
     float o = 0.f;
     if (c < a.cols && (!km || km[c])) o = __expf(__ldg(s + c) * a.scale - m) * inv;
-    p[c] = __float2bfloat16_rn(o);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+    p[c] = hi;
+    if (a.split) {
+      p[seg + c] = __float2bfloat16_rn(o - __bfloat162float(hi));
+      p[2 * seg + c] = hi;
+    }
   }
 }
 
@@ -324,21 +352,27 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   PIO_REQUIRE(a && a->x && a->y, "pio_layernorm_bf16: null pointer");
   PIO_REQUIRE(a->rows > 0 && a->C > 0, "pio_layernorm_bf16: bad shape rows=%lld C=%d", (long long)a->rows, a->C);
   PIO_REQUIRE(a->ldy >= a->C && a->ldx >= 0, "pio_layernorm_bf16: bad leading dimension");
-  PIO_REQUIRE(a->ldy <= 2048, "pio_layernorm_bf16: C up to 2048 supported (got ldy=%lld)", (long long)a->ldy);
+  PIO_REQUIRE(a->split >= 0 && a->split <= 2, "pio_layernorm_bf16: split must be 0, 1 (A side) or 2 (B side)");
+  const int split = a->split;
+  const long long seg = split ? a->ldy / 3 : a->ldy;
+  PIO_REQUIRE(!split || (a->ldy % 24 == 0 && seg >= a->C), "pio_layernorm_bf16: split output needs ldy = 3 * pad8(C)");
+  PIO_REQUIRE(seg <= 2048, "pio_layernorm_bf16: C up to 2048 supported (got %lld columns)", (long long)seg);
+  const int mode = (a->normalize ? 1 : 0) | (split == 1 ? 2 : 0) | (split == 2 ? 4 : 0);
   DeviceInfo dev;
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a->y);
   ProfileScope prof(KF_LAYERNORM, 0.0, (double)a->rows * (4.0 * a->C + 2.0 * a->ldy), stream);
+  (void)seg;
   const bool vec = (a->C % 4 == 0) && (a->ldx % 4 == 0) && aligned16(a->x) && aligned16(a->y) &&
                    (!a->gamma || aligned16(a->gamma)) && (!a->beta || aligned16(a->beta));
   if (vec) {
     const long long blocks = (a->rows + 3) / 4;
     PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
-    const int need = (int)((a->ldy / 4 + 31) / 32);
+    const int need = (int)((seg / 4 + 31) / 32);
 #define PIO_LNV_LAUNCH(NV)                                                                                        \
   launch_kernel(pio_layernorm_vec_kernel<NV>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x, (long long)a->ldx, y, \
-                (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C, (int)a->normalize, a->eps)
+                (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C, mode, a->eps)
     if (need <= 2) PIO_LNV_LAUNCH(2);
     else if (need <= 4) PIO_LNV_LAUNCH(4);
     else if (need <= 8) PIO_LNV_LAUNCH(8);
@@ -346,14 +380,14 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     else PIO_LNV_LAUNCH(16);
 #undef PIO_LNV_LAUNCH
   } else {
-    const int need = (int)((a->ldy + 31) / 32);
+    const int need = (int)((seg + 31) / 32);
     const int rows_per_warp = need <= 12 ? 2 : 1;
     const long long blocks = (a->rows + 4 * rows_per_warp - 1) / (4 * rows_per_warp);
     PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
 #define PIO_LN_LAUNCH(MAXV, ROWS)                                                                                      \
   launch_kernel(pio_layernorm_kernel<MAXV, ROWS>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x,                 \
                 (long long)a->ldx, y, (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C,              \
-                (int)a->normalize, a->eps)
+                mode, a->eps)
     if (need <= 4) PIO_LN_LAUNCH(4, 2);
     else if (need <= 12) PIO_LN_LAUNCH(12, 2);
     else if (need <= 24) PIO_LN_LAUNCH(24, 1);
@@ -370,7 +404,8 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
   using namespace pio;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PIO_REQUIRE(a && a->S && a->P, "pio_softmax_bf16: null pointer");
-  PIO_REQUIRE(a->batch > 0 && a->rows > 0 && a->cols > 0 && a->ldp >= a->cols && a->lds >= a->cols,
+  PIO_REQUIRE(a->batch > 0 && a->rows > 0 && a->cols > 0 && a->lds >= a->cols &&
+                  (a->split ? (a->ldp % 3 == 0 && a->ldp / 3 >= a->cols) : a->ldp >= a->cols),
               "pio_softmax_bf16: bad shape");
   const long long blocks = (long long)a->batch * a->rows;
   PIO_REQUIRE(blocks < (1ll << 31), "pio_softmax_bf16: too many rows");

@@ -17,6 +17,18 @@ import torch
 from . import ops
 from .ops import BF16, pad8
 
+# Arithmetic mode: "bf16" (default: bf16 MMA operands, fp32 everything else) or "bf16x3" (validation precision: bf16 x 2
+# split operands, three MMAs per product — validate.py)
+PRECISION = "bf16"
+
+
+def set_precision(mode: str) -> None:
+    global PRECISION
+    if mode not in ("bf16", "bf16x3"):
+        raise ValueError(f"unknown precision {mode!r}: use 'bf16' or 'bf16x3'")
+    PRECISION = mode
+
+
 # Flags (module-level so tests / bench can flip them)
 ENABLE_FOLDING = True      # single-head cross-attention: K == V == LN(x)
 ENCODER_KEY_SPLITS = 0     # 0 = auto

@@ -37,19 +37,21 @@ def _need_cuda(*ts):
 
 
 def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
-                   normalize: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [rows, pad8(C)]."""
+                   normalize: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
+                   split: int = 0) -> torch.Tensor:
+    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [rows, pad8(C)].
+    split = 1 / 2 (validation precision): bf16 [rows, 3 * pad8(C)] laid out [hi | lo | hi] / [hi | hi | lo]."""
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.stride(-1) == 1
     c = x.shape[-1]
     x2 = x.reshape(-1, c) if x.dim() != 2 else x
     rows = x2.shape[0]
-    ldy = pad8(c)
+    ldy = pad8(c) * (3 if split else 1)
     if out is None:
         out = torch.empty((rows, ldy), dtype=BF16, device=x.device)
     assert out.dtype == BF16 and out.shape[-1] == ldy and out.is_contiguous()
     a = _lib.LayerNormArgs(_ptr(x2), x2.stride(0), _ptr(out), ldy, _ptr(gamma), _ptr(beta), rows, c,
-                           1 if normalize else 0, eps)
+                           1 if normalize else 0, eps, split)
     _lib.check(_lib.load().pio_layernorm_bf16(C.byref(a), _stream()), "pio_layernorm_bf16")
     return out
 
@@ -104,16 +106,16 @@ def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -
 
 
 def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[torch.Tensor] = None,
-                 row_keep: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)]."""
+                 row_keep: Optional[torch.Tensor] = None, split: bool = False) -> torch.Tensor:
+    """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)] (split: [B, rows, 3 * pad8(cols)] as [hi | lo | hi])."""
     _need_cuda(S, key_mask, row_keep)
     b, rows, lds = S.shape
-    ldp = pad8(cols)
+    ldp = pad8(cols) * (3 if split else 1)
     P = torch.empty((b, rows, ldp), dtype=BF16, device=S.device)
     a = _lib.SoftmaxArgs(_ptr(S), lds, S.stride(0), _ptr(P), ldp, P.stride(0),
                          _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
-                         b, rows, cols, scale)
+                         b, rows, cols, scale, 1 if split else 0)
     _lib.check(_lib.load().pio_softmax_bf16(C.byref(a), _stream()), "pio_softmax_bf16")
     return P
 

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine, ops, validate
 from .primitives import CrossAttention, SelfAttention, lecun_normal_, make_cross_attention_mask  # noqa: F401
 
 
@@ -126,6 +126,8 @@ class PerceiverDecoder(nn.Module):
             return y32
         B, Nq, C = y32.shape
         n_out = self._output_num_channels
+        if engine.PRECISION == "bf16x3":
+            return validate.final_layer(self.final_layer, y32)
         if n_out <= 16:
             # a handful of output channels (optical flow: 322 -> 2): fp32 on CUDA cores.  The head is 0.01 % of the
             # FLOPs but its bf16 rounding alone would cost 1.2e-2 of the 1e-2 error budget.

@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine, ops, validate
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -125,6 +125,8 @@ class Attention(nn.Module):
         pa = engine.prepared(self, "plain", lambda: engine.PreparedAttention(self, self_attention=False,
                                                                              allow_fold=False))
         row_keep, key_mask = _factor_mask(attention_mask)
+        if engine.PRECISION == "bf16x3":
+            return validate.attention_module(self, inputs_q, inputs_k, inputs_v, key_mask, row_keep)
         qn = ops.layernorm_bf16(inputs_q.contiguous().view(B * Nq, Cq), None, None, normalize=False)
         kn = ops.layernorm_bf16(inputs_k.contiguous().view(B * Nk, -1), None, None, normalize=False)
         _, q = ops.linear(qn, pa.Cq, pa.wq, pa.QK, pa.bq)
@@ -169,6 +171,9 @@ class MLP(nn.Module):
 
     def forward(self, x):
         _check_inference(self, self._dropout_prob)
+        if engine.PRECISION == "bf16x3":
+            ops._need_cuda(x)
+            return validate.mlp_module(self, x)
         pm = engine.prepared(self, "mlp", lambda: engine.PreparedMLP(self))
         shape = x.shape
         xb = ops.layernorm_bf16(x.contiguous().view(-1, shape[-1]), None, None, normalize=False)
@@ -200,6 +205,10 @@ class SelfAttention(nn.Module):
         if attention_bias is not None or return_matrix:
             raise NotImplementedError("attention_bias / return_matrix are not implemented by the sm_100a kernels")
         _check_inference(self, *self._dropout_probs)
+        if engine.PRECISION == "bf16x3":
+            ops._need_cuda(inputs)
+            row_keep, key_mask = _factor_mask(attention_mask)
+            return validate.self_attention_block(self, inputs.contiguous(), key_mask, row_keep)
         pa = engine.prepared(self.attention, "self", lambda: engine.PreparedAttention(self.attention,
                                                                                      self_attention=True,
                                                                                      allow_fold=False))
@@ -252,6 +261,11 @@ class CrossAttention(nn.Module):
     def _forward_factored(self, inputs_q, inputs_kv, *, key_mask=None, row_keep=None, want_bf16_out=False,
                           shard=None):
         _check_inference(self, *self._dropout_probs)
+        if engine.PRECISION == "bf16x3":
+            ops._need_cuda(inputs_q, inputs_kv)
+            if shard is not None:
+                raise RuntimeError("perceiverio_pytorch_b200: the validation precision runs unsharded")
+            return validate.cross_attention_block(self, inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep), None
         pa = engine.prepared(self.attention, "cross", lambda: engine.PreparedAttention(self.attention,
                                                                                       self_attention=False,
                                                                                       allow_fold=True))
