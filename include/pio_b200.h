@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 3
+#define PIO_ABI_VERSION 4
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -162,6 +162,12 @@ typedef struct pio_combine_args {
   const uint8_t* row_keep; int64_t stride_rk;
   void* O; int64_t ldo; int64_t strideO;                          /* bf16 [B, Nq, ldo] or NULL */
   float* O_out_part; float* m_out; float* l_out;                  /* fp32 [B, H, Nq, dv] / [B, H, Nq] or NULL */
+  /* Fused exchange over NVLink peer memory (the key-sharded encoder on one NVSwitch box): if part_ptrs != NULL it is a
+   * DEVICE array of `parts` base pointers, one per rank, each addressing that rank's packed partial
+   * [O (rows*dv) | m (rows) | l (rows)] in peer-mapped (symmetric) memory; the kernel then loads every rank's partial
+   * straight through NVLink instead of reading a gathered copy, and O_part / m_part / l_part / part_stride_* are
+   * ignored.  The caller orders the ranks' writes before this launch (a symmetric-memory barrier on the stream). */
+  const float* const* part_ptrs;
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
 

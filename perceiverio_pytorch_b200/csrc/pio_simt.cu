@@ -238,6 +238,86 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
   const long long so = a.part_stride_O ? a.part_stride_O : rows * a.dv;
   const long long sm = a.part_stride_ml ? a.part_stride_ml : rows;
   const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + q] != 0 : true;
+  // Part p: either a slice of one local buffer, or rank p's packed partial in peer-mapped memory (plain loads: peer
+  // lines are not cached in the local L2, and the L1 was invalidated when this kernel was launched).
+  constexpr int MAXP = 16;
+  const float* Op[MAXP];
+  const float* mp_[MAXP];
+  const float* lp_[MAXP];
+  const int parts = a.parts;
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p) {
+    if (p < parts) {
+      if (a.part_ptrs) {
+        const float* base = a.part_ptrs[p];
+        Op[p] = base + row * a.dv;
+        mp_[p] = base + rows * a.dv + row;
+        lp_[p] = base + rows * a.dv + rows + row;
+      } else {
+        Op[p] = a.O_part + p * so + row * a.dv;
+        mp_[p] = a.m_part + p * sm + row;
+        lp_[p] = a.l_part + p * sm + row;
+      }
+    }
+  }
+  float w[MAXP];
+  float M = -INFINITY;
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p)
+    if (p < parts) {
+      w[p] = *mp_[p];
+      M = fmaxf(M, w[p]);
+    }
+  float L = 0.f;
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p)
+    if (p < parts) {
+      w[p] = (M != -INFINITY && w[p] != -INFINITY) ? __expf(w[p] - M) : 0.f;
+      if (w[p] != 0.f) L += *lp_[p] * w[p];
+    }
+  if (a.O_out_part) {  // merged, still un-normalised partial (referenced to M)
+    if (lane == 0) {
+      a.m_out[row] = M;
+      a.l_out[row] = L;
+    }
+    for (int c = lane; c < a.dv; c += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int p = 0; p < MAXP; ++p)
+        if (p < parts && w[p] != 0.f) acc += Op[p][c] * w[p];
+      a.O_out_part[row * a.dv + c] = acc;
+    }
+  }
+  if (a.O) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.O) + (long long)b * a.strideO + (long long)q * a.ldo +
+                       (long long)h * a.dv;
+    if (!keep || M == -INFINITY || !(L > 0.f)) {
+      for (int c = lane; c < a.dv; c += 32) o[c] = __float2bfloat16_rn(0.f);
+      return;
+    }
+    const float inv = 1.0f / L;
+    for (int c = lane; c < a.dv; c += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int p = 0; p < MAXP; ++p)
+        if (p < parts && w[p] != 0.f) acc += Op[p][c] * w[p];
+      o[c] = __float2bfloat16_rn(acc * inv);
+    }
+  }
+}
+
+// More than 16 parts (deep local key splits): the general loop over one local buffer.
+__global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)a.B * a.H * a.Nq;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int q = (int)(row % a.Nq);
+  const int h = (int)((row / a.Nq) % a.H);
+  const int b = (int)(row / ((long long)a.Nq * a.H));
+  const long long so = a.part_stride_O ? a.part_stride_O : rows * a.dv;
+  const long long sm = a.part_stride_ml ? a.part_stride_ml : rows;
+  const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + q] != 0 : true;
   float M = -INFINITY;
   for (int p = 0; p < a.parts; ++p) M = fmaxf(M, __ldg(a.m_part + p * sm + row));
   float L = 0.f;
@@ -247,7 +327,7 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
       if (mp != -INFINITY) L += __ldg(a.l_part + p * sm + row) * __expf(mp - M);
     }
   }
-  if (a.O_out_part) {  // merged, still un-normalised partial (referenced to M)
+  if (a.O_out_part) {
     if (lane == 0) {
       a.m_out[row] = M;
       a.l_out[row] = L;
@@ -421,14 +501,16 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
 extern "C" int pio_attention_combine(const pio_combine_args* a, void* stream_) {
   using namespace pio;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PIO_REQUIRE(a && a->O_part && a->m_part && a->l_part, "pio_attention_combine: null pointer");
+  PIO_REQUIRE(a && (a->part_ptrs || (a->O_part && a->m_part && a->l_part)), "pio_attention_combine: null pointer");
+  PIO_REQUIRE(!a->part_ptrs || a->parts <= 16, "pio_attention_combine: at most 16 peer parts (got %d)", a->parts);
   PIO_REQUIRE(a->O || (a->O_out_part && a->m_out && a->l_out), "pio_attention_combine: no output");
   PIO_REQUIRE(a->parts > 0 && a->B > 0 && a->H > 0 && a->Nq > 0 && a->dv > 0, "pio_attention_combine: bad shape");
   const long long rows = (long long)a->B * a->H * a->Nq;
   const long long blocks = (rows + 7) / 8;
   {
     ProfileScope prof(KF_COMBINE, 0.0, (double)rows * a->parts * (a->dv + 2) * 4.0 + (double)rows * a->dv * 2.0, stream);
-    pio_combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    if (a->parts <= 16) pio_combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    else pio_combine_many_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

@@ -157,23 +157,25 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
     return O
 
 
-def attention_combine(Op: torch.Tensor, mp: torch.Tensor, lp: torch.Tensor, *,
+def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp: Optional[torch.Tensor], *,
                       row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                       part_stride_O: int = 0, part_stride_ml: int = 0, shape=None,
-                      merged_out=None, normalised: bool = True):
+                      merged_out=None, normalised: bool = True, part_ptrs_dev: int = 0, device=None):
     """Merge partials -> O bf16 [B, Nq, pad8(H*dv)] and/or a merged un-normalised partial.
 
     Op/mp/lp are [parts, B, H, Nq, dv] / [parts, B, H, Nq] tensors, or flat buffers with explicit part strides and
-    `shape=(parts, B, H, Nq, dv)`.  `merged_out=(O, m, l)` (fp32 [B,H,Nq,dv] / [B,H,Nq]) receives the merged partial."""
+    `shape=(parts, B, H, Nq, dv)`.  `merged_out=(O, m, l)` (fp32 [B,H,Nq,dv] / [B,H,Nq]) receives the merged partial.
+    `part_ptrs_dev` (an integer device address of an array of `parts` peer pointers, e.g. a symmetric-memory handle's
+    buffer_ptrs_dev) selects the fused NVLink exchange: every part is loaded from its rank's packed partial."""
     _need_cuda(Op, mp, lp, row_keep)
     parts, b, h, nq, dv = Op.shape if shape is None else shape
     ldo = pad8(h * dv)
     if out is None and normalised:
-        out = torch.empty((b, nq, ldo), dtype=BF16, device=Op.device)
+        out = torch.empty((b, nq, ldo), dtype=BF16, device=Op.device if Op is not None else device)
     mo = merged_out if merged_out is not None else (None, None, None)
     a = _lib.CombineArgs(_ptr(Op), _ptr(mp), _ptr(lp), part_stride_O, part_stride_ml, parts, b, h, nq, dv,
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
                          _ptr(out), ldo, out.stride(0) if out is not None else 0,
-                         _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]))
+                         _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]), C.c_void_p(part_ptrs_dev) if part_ptrs_dev else None)
     _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
     return out

@@ -6,9 +6,14 @@ SURVEY.md §8(e): the path shards naturally in three ways, and only one of them 
 * decoder cross-attend — query axis, no collective (`shard_queries`; an all_gather only if the caller wants the
   full output on every rank);
 * encoder cross-attend — key axis: every rank streams its slice of the input array through the attention kernel
-  and produces an un-normalised partial (O, m, l) per latent; the partials are exchanged with ONE all_gather of a
-  packed fp32 buffer of B*H*Nq*(dv+2) floats per rank (0.54 MB per sample for the ImageNet geometry — latency
-  bound on NVSwitch) and merged by the log-sum-exp combine kernel (`KeyShard`).
+  and produces an un-normalised partial (O, m, l) per latent, packed as one fp32 buffer of B*H*Nq*(dv+2) floats
+  (0.54 MB per sample for the ImageNet geometry — latency bound on NVSwitch).  The exchange step (`KeyShard`) is
+  either
+    - `exchange="peer"`: the packed partial lives in symmetric (peer-mapped) memory; after a symmetric-memory barrier
+      ONE combine kernel on every rank loads all ranks' partials straight through NVLink and merges them (log-sum-exp)
+      — the collective is fused into the consumer, nothing is gathered or copied; or
+    - `exchange="nccl"`: one all_gather of the packed buffers followed by the same combine kernel on the gathered
+      copy (the baseline, and what the gloo tests exercise on CPU).
 
 The collective plumbing is backend-agnostic (it is exercised with gloo on CPU tensors in tests/); the kernels that
 produce and merge the partials are the sm_100a ones.
@@ -64,11 +69,15 @@ def packed_views(buf: torch.Tensor, rows: int, dv: int):
 class KeyShard:
     """State of a key-axis shard of the encoder cross-attend across the ranks of `group`."""
 
-    def __init__(self, group=None, local_splits: int = 0):
+    def __init__(self, group=None, local_splits: int = 0, exchange: str = "nccl"):
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
         self.group = group
         self.local_splits = local_splits   # key splits inside this rank's slice; 0 = pick to fill the SMs
+        self.exchange = exchange
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._symm = {}                    # packed size -> [[(buffer, handle), (buffer, handle)], next index]
 
     # -- collectives ------------------------------------------------------------------------------------------
     def any_over_ranks(self, flag: torch.Tensor) -> torch.Tensor:
@@ -87,6 +96,24 @@ class KeyShard:
         dist.all_gather_into_tensor(out, packed.contiguous(), group=self.group)
         return out.view(self.world, packed.numel())
 
+    def _peer_buffer(self, n: int, device):
+        """This rank's packed-partial buffer in symmetric memory (+ its rendezvous handle).  Two buffers are used
+        alternately: a rank only overwrites a buffer two exchanges later, i.e. after a barrier that every peer can only
+        have reached once it finished reading — so ONE barrier per exchange is enough."""
+        import torch.distributed._symmetric_memory as symm_mem
+        entry = self._symm.get(n)
+        if entry is None:
+            group = self.group if self.group is not None else dist.group.WORLD
+            pairs = []
+            for _ in range(2):
+                t = symm_mem.empty(n, dtype=torch.float32, device=device)
+                pairs.append((t, symm_mem.rendezvous(t, group.group_name)))
+            entry = [pairs, 0]
+            self._symm[n] = entry
+        t, h = entry[0][entry[1]]
+        entry[1] ^= 1
+        return t, h
+
     # -- the exchange step ------------------------------------------------------------------------------------
     def combine(self, parts, row_keep=None):
         """parts = (O_part [S,B,H,Nq,dv], m [S,B,H,Nq], l [S,B,H,Nq]) from this rank's attention kernel.
@@ -96,6 +123,14 @@ class KeyShard:
         S, B, H, Nq, dv = Op.shape
         rows = B * H * Nq
         n = rows * (dv + 2)
+        if self.exchange == "peer" and self.world > 1:
+            buf, hdl = self._peer_buffer(n, Op.device)
+            o, m, l = packed_views(buf, rows, dv)
+            # this rank's (merged) partial goes straight into its symmetric buffer
+            ops.attention_combine(Op, mp, lp, normalised=False, merged_out=(o, m, l))
+            hdl.barrier(channel=0)   # every rank's partial is complete and visible
+            return ops.attention_combine(None, None, None, row_keep=row_keep, shape=(self.world, B, H, Nq, dv),
+                                         part_ptrs_dev=int(hdl.buffer_ptrs_dev), device=Op.device)
         if S == 1:
             packed = pack_partial(Op[0], mp[0], lp[0])
         else:
@@ -108,8 +143,8 @@ class KeyShard:
                                      shape=(self.world, B, H, Nq, dv))
 
 
-def shard_encoder_keys(encoder, group=None, local_splits: int = 0):
+def shard_encoder_keys(encoder, group=None, local_splits: int = 0, exchange: str = "nccl"):
     """Mark `encoder` (a PerceiverEncoder of this package) as key-sharded: its forward then expects this rank's slice
     of the input array (see `shard_keys`) and returns the full latents on every rank."""
-    encoder.key_shard = KeyShard(group, local_splits)
+    encoder.key_shard = KeyShard(group, local_splits, exchange)
     return encoder

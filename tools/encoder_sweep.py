@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--nk", type=int, nargs="*", default=[16384, 65536, 262144, 1048576])
     ap.add_argument("--batch", type=int, nargs="*", default=[1, 8])
     ap.add_argument("--channels", type=int, default=261)
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="nccl: all_gather + combine; peer: combine kernel loads the peers' partials over NVLink")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -65,7 +67,7 @@ def main():
             lat = enc.latents(x)
             full, _ = ca._forward_factored(lat, x, key_mask=mask, row_keep=None)
             xs, ms, (b0, e0) = parallel.shard_keys(x, rank, world, mask, multiple=64)
-            shard = parallel.KeyShard(local_splits=2)
+            shard = parallel.KeyShard(local_splits=2, exchange=args.exchange)
             got, _ = ca._forward_factored(lat, xs.contiguous(), key_mask=ms.contiguous(), row_keep=None, shard=shard)
         err = float((got - full).abs().max() / full.abs().max())
         from oracle import perceiver_oracle as O
@@ -77,7 +79,8 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(json.dumps({"check": "key-sharded encoder cross-attend", "world": world, "keys_rank0": [b0, e0],
+            print(json.dumps({"check": "key-sharded encoder cross-attend", "world": world, "exchange": args.exchange,
+                              "keys_rank0": [b0, e0],
                               "max_rel_err_vs_unsharded_cuda": float(t[0]), "max_rel_err_vs_fp32_oracle": float(t[1]),
                               "ok": bool(t[0] <= 5e-3 and t[1] <= 1e-2)}), flush=True)
 
@@ -90,7 +93,7 @@ def main():
             if e0 - b0 <= 0 or B * (e0 - b0) * C * 4 > 40e9:
                 continue
             xs = torch.randn(B, e0 - b0, C, device=dev)
-            shard = parallel.KeyShard() if world > 1 else None
+            shard = parallel.KeyShard(exchange=args.exchange) if world > 1 else None
             with torch.inference_mode():
                 lat = enc.latents(xs)
                 for _ in range(2):
@@ -111,7 +114,8 @@ def main():
             ms = float(t.item())
             if rank == 0:
                 fl = xattn_flops(B, 512, Nk, 1024, C, 1024)
-                print(json.dumps({"sweep": "encoder cross-attend, key axis sharded", "n_gpus": world, "Nk": Nk, "B": B,
+                print(json.dumps({"sweep": "encoder cross-attend, key axis sharded", "n_gpus": world,
+                                  "exchange": args.exchange if world > 1 else "none", "Nk": Nk, "B": B,
                                   "channels": C, "ms": round(ms, 4), "samples_per_s": round(B / (ms * 1e-3), 2),
                                   "tflops_reference_algorithm": round(fl / (ms * 1e-3) / 1e12, 1),
                                   "input_gbs": round(B * Nk * C * 4 / (ms * 1e-3) / 1e9, 1)}), flush=True)
