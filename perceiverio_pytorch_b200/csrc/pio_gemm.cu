@@ -439,18 +439,25 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   if (dev.cc_major != 10) return fail(PIO_ERR_ARCH, "pio_gemm_bf16 needs sm_100 (got sm_%d%d)", dev.cc_major, dev.cc_minor);
   PIO_REQUIRE(a->kernel >= 0 && a->kernel <= 2, "pio_gemm_bf16: kernel must be 0 (auto), 1 or 2 (got %d)", a->kernel);
   {
-    // CTA-pair kernel: when explicitly requested, or when there are enough 256 x 256 tiles to occupy the SM pairs
+    // CTA-pair kernel: when explicitly requested, or when there are enough 256 x 256 tiles to occupy a third of the SM
+    // pairs (per tile it is ~1.4x faster than the single-CTA kernel, so it wins well before the grid is full)
     const bool elig = gemm2_eligible(a) && (dev.sm_count % 2 == 0);
     if (a->kernel == 2 && !elig)
       return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the CTA-pair kernel needs K-major B, exactly one output and "
                                        "16-byte aligned output / residual rows");
     const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
     const bool want = a->kernel == 2 ||
-                      (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && pair_tiles * 10 >= 8ll * (dev.sm_count / 2));
+                      (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && pair_tiles * 3 >= (long long)(dev.sm_count / 2));
     if (elig && want) return launch_gemm2(a, dev, stream);
   }
   int bn = a->tile_n;
-  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  if (bn == 0) {
+    bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+    // small problems are bound by how many CTAs stream the weight matrix concurrently, not by tile efficiency: shrink
+    // the tile until at least half of the SMs have one (narrower tiles also get deeper operand rings)
+    const long long tiles_m = ((long long)a->M + 127) / 128 * a->batch;
+    while (bn > 64 && tiles_m * ((a->N + bn - 1) / bn) * 2 < dev.sm_count) bn >>= 1;
+  }
   // cluster width along M: multicast pays when there are at least two M tiles to pair up
   int cl = a->cluster_m;
   if (cl == 0) cl = (a->M > 128) ? 2 : 1;
