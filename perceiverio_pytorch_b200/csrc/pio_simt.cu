@@ -225,6 +225,65 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Row softmax for rows of up to 2048 columns (the decoders: 256 .. 2048 latents as keys): one warp per row, the row
+// lives in registers (lane l owns the float4 at columns 4 (l + 32 i)), S is read exactly once with 16-byte loads and P
+// is written with 8-byte stores.  HBM-bound: 4 cols bytes in + 2 ldp bytes out per row.
+// ------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) pio_softmax_warp_kernel(pio_softmax_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long row_id = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row_id >= (long long)a.batch * a.rows) return;
+  const int b = (int)(row_id / a.rows);
+  const int r = (int)(row_id % a.rows);
+  const float4* s4 = reinterpret_cast<const float4*>(a.S + (long long)b * a.strideS + (long long)r * a.lds);
+  uint2* p2 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.P) + (long long)b * a.strideP + (long long)r * a.ldp);
+  const uint8_t* km = a.key_mask ? a.key_mask + (long long)b * a.stride_km : nullptr;
+  const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + r] != 0 : true;
+  const int nvec = (a.cols + 3) >> 2;      // float4s that hold at least one valid column
+  const int nvec_out = (int)(a.ldp >> 2);
+  float4 v[NV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (keep && c4 < nvec) {
+      const float4 t = __ldg(s4 + c4);
+      const int c = 4 * c4;
+      const bool k0 = (c < a.cols) && (!km || km[c]), k1 = (c + 1 < a.cols) && (!km || km[c + 1]);
+      const bool k2 = (c + 2 < a.cols) && (!km || km[c + 2]), k3 = (c + 3 < a.cols) && (!km || km[c + 3]);
+      if (k0) v[i].x = t.x * a.scale;
+      if (k1) v[i].y = t.y * a.scale;
+      if (k2) v[i].z = t.z * a.scale;
+      if (k3) v[i].w = t.w * a.scale;
+      m = fmaxf(fmaxf(m, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+    }
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  if (m != -INFINITY) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m);
+      v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+      l += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  l = warp_sum(l);
+  const float inv = (m != -INFINITY && l > 0.f) ? 1.0f / l : 0.0f;   // wiped / fully masked rows are written as zeros
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < nvec_out) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inv != 0.f && c4 < nvec) o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      p2[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Merge partial attention results: one warp per (b, h, query row).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
@@ -491,7 +550,18 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
   PIO_REQUIRE(blocks < (1ll << 31), "pio_softmax_bf16: too many rows");
   {
     ProfileScope prof(KF_SOFTMAX, 0.0, (double)blocks * (4.0 * a->cols + 2.0 * a->ldp), stream);
-    pio_softmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    const bool warp_rows = !a->split && a->ldp <= 2048 && a->lds % 4 == 0 && a->strideS % 4 == 0 && a->ldp % 4 == 0 &&
+                           a->strideP % 4 == 0 && aligned16(a->S) && (reinterpret_cast<uintptr_t>(a->P) & 7u) == 0;
+    if (warp_rows) {
+      const unsigned wblocks = (unsigned)((blocks + 7) / 8);
+      const int need = (int)((a->ldp / 4 + 31) / 32);
+      if (need <= 2) pio_softmax_warp_kernel<2><<<wblocks, 256, 0, stream>>>(*a);
+      else if (need <= 4) pio_softmax_warp_kernel<4><<<wblocks, 256, 0, stream>>>(*a);
+      else if (need <= 8) pio_softmax_warp_kernel<8><<<wblocks, 256, 0, stream>>>(*a);
+      else pio_softmax_warp_kernel<16><<<wblocks, 256, 0, stream>>>(*a);
+    } else {
+      pio_softmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
+    }
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

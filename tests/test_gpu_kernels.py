@@ -106,7 +106,7 @@ def test_gemm_pair_kernel_rejects_unaligned_output():
         ops.gemm(A, W, M=256, N=261, K=64, out_f32=o, ldo32=261, kernel=2)
 
 
-@pytest.mark.parametrize("b,r,c", [(2, 40, 512), (1, 7, 52097), (3, 130, 785)])
+@pytest.mark.parametrize("b,r,c", [(2, 40, 512), (1, 7, 52097), (3, 130, 785), (2, 300, 2048), (1, 33, 256)])
 def test_softmax(b, r, c):
     from perceiverio_pytorch_b200 import ops
     torch.manual_seed(0)
@@ -117,6 +117,18 @@ def test_softmax(b, r, c):
     ref = torch.softmax(torch.where(km[:, None, :].bool(), S * 0.37, torch.tensor(float("-inf"), device="cuda")), -1)
     ref = ref * rk[:, :, None]
     assert _rel(P[:, :, :c].float(), ref) < 1e-2
+    # row pitch padded to a multiple of 4 floats (what the engine allocates): rows <= 2048 columns take the
+    # warp-per-row register kernel; pad columns of P must come out as zeros
+    lds = (c + 3) // 4 * 4
+    Sp = torch.full((b, r, lds), 1e30, device="cuda")     # garbage in the pad must never be used
+    Sp[:, :, :c] = S
+    P2 = ops.softmax_bf16(Sp, c, 0.37, km, rk)
+    assert _rel(P2[:, :, :c].float(), ref) < 1e-2
+    assert float(P2[:, :, c:].float().abs().max()) == 0.0 if P2.shape[2] > c else True
+    km0 = km.clone()
+    km0[0] = 0                                            # a sample with no valid key at all: zero rows
+    P3 = ops.softmax_bf16(Sp, c, 0.37, km0, None)
+    assert float(P3[0].float().abs().max()) == 0.0
 
 
 def _attn_ref(q, k, v, scale, km=None, rk=None):
