@@ -152,6 +152,32 @@ def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, N
     return O
 
 
+def _streaming_ok(H, dqk, dv, same_kv=False) -> bool:
+    """Whether the streaming kernels cover these head sizes (otherwise attention goes through explicit S / P)."""
+    if not ops.attention_supported(dqk, dv) or not (H == 1 or dqk % 16 == 0):
+        return False
+    return same_kv or ((dqk + 63) // 64 <= 2 and (dv + 63) // 64 <= 3)
+
+
+def _materialised_attention_h1(q, k, vT, *, B, Nq, Nk, dqk, dv, scale, key_mask, row_keep, q_bcast):
+    """Single-head attention through explicit S and P with every product on the CTA-pair GEMM kernel:
+    q bf16 [(1|B)*Nq, pad8(dqk)], k bf16 [B*Nk, pad8(dqk)], vT bf16 [B, dv, pad8(Nk)] (V already transposed by
+    swapping the operands of its projection, so P.V has a K-major B operand too).  Returns O bf16 [B, Nq, pad8(dv)]."""
+    dev = q.device
+    ldq, ldk, nkp = q.shape[-1], k.shape[-1], vT.shape[-1]
+    lds = (Nk + 3) // 4 * 4
+    S = torch.empty((B, Nq, lds), dtype=torch.float32, device=dev)
+    ops.gemm(q, k, M=Nq, N=Nk, K=dqk, batch=B, strideA=0 if q_bcast else Nq * ldq, strideB=Nk * ldk, lda=ldq, ldb=ldk,
+             out_f32=S, ldo32=lds, strideO32=Nq * lds)
+    P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)          # [B, Nq, pad8(Nk)]
+    del S
+    ldo = pad8(dv)
+    O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+    ops.gemm(P, vT, M=Nq, N=dv, K=Nk, batch=B, strideA=Nq * P.shape[-1], strideB=dv * nkp, lda=P.shape[-1], ldb=nkp,
+             out_bf16=O, ldo16=ldo, strideO16=Nq * ldo)
+    return O
+
+
 def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv, sm_count: int = 148) -> int:
     """Key-axis splits inside one GPU: fill the SMs when (batch x heads x query tiles) is small, and trim the
     partial last wave otherwise (256 CTAs on 148 SMs waste 14 % of the machine; 4 x 256 waste 1 %)."""
@@ -252,6 +278,25 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
                       num_splits=num_splits)
         return o, pa.Ck
     _, q = ops.linear(qn, pa.Cq, pa.wq, pa.QK, pa.bq)
+    if pa.H == 1 and not partial and not _streaming_ok(1, pa.dqk, pa.dv):
+        # wide single head (the decoders: d = 512 / 1024; the multimodal encoder: 704): explicit S / P, all three
+        # products K-major.  V^T [B, V, Nk] comes straight out of its projection with the operands swapped
+        # (W_v as the A operand, the LayerNorm'd key/value array as B, bias per output row).
+        if pa.kv_fused:
+            wk, bk, wv, bv = pa.wkv[:pa.QK], pa.bkv[:pa.QK], pa.wkv[pa.QK:], pa.bkv[pa.QK:]
+        else:
+            wk, bk, wv, bv = pa.wk, pa.bk, pa.wv, pa.bv
+        _, k = ops.linear(kvn, pa.Ck, wk, pa.QK, bk)
+        nkp = pad8(Nk)
+        ldkv = kvn.shape[-1]
+        vT = torch.empty((B, pa.V, nkp), dtype=BF16, device=kvn.device)
+        if nkp != Nk:
+            vT[:, :, Nk:].zero_()       # P's pad columns are zero as well; keep the products finite
+        ops.gemm(wv, kvn, M=pa.V, N=Nk, K=pa.Ck, batch=B, strideA=0, strideB=Nk * ldkv, lda=wv.stride(0), ldb=ldkv,
+                 bias=bv, bias_mode=2, out_bf16=vT, ldo16=nkp, strideO16=pa.V * nkp)
+        o = _materialised_attention_h1(q, k, vT, B=B, Nq=Nq, Nk=Nk, dqk=pa.dqk, dv=pa.dv, scale=pa.scale,
+                                       key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast)
+        return o, pa.V
     if pa.kv_fused:
         n = pa.QK + pa.V
         _, kv = ops.linear(kvn, pa.Ck, pa.wkv, n, pa.bkv)
@@ -274,15 +319,16 @@ def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B
     else:
         w, b = pa.wf, pa.bf
     o2 = o.view(B * Nq, -1)
-    y = torch.empty((B * Nq, pa.O), dtype=torch.float32, device=o.device)
+    y = ops.empty_f32_rows(B * Nq, pa.O, o.device)
+    ldy = y.stride(0)
     if residual is None:
-        ops.gemm(o2, w, M=B * Nq, N=pa.O, K=width, bias=b, out_f32=y, ldo32=pa.O)
+        ops.gemm(o2, w, M=B * Nq, N=pa.O, K=width, bias=b, out_f32=y, ldo32=ldy)
     else:
         # residual is the un-normalised query [B, Nq, Cq], possibly a stride-0 batch broadcast
         assert residual.stride(2) == 1
         ops.gemm(o2, w, M=Nq, N=pa.O, K=width, batch=B, strideA=Nq * o2.shape[1], strideB=0, bias=b,
                  residual=residual, ldr=residual.stride(1), strideR=residual.stride(0) if B > 1 else 0,
-                 out_f32=y, ldo32=pa.O, strideO32=Nq * pa.O)
+                 out_f32=y, ldo32=ldy, strideO32=Nq * ldy)
     return y
 
 

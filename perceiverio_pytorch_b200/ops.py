@@ -21,6 +21,15 @@ def pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def empty_f32_rows(m: int, n: int, device) -> torch.Tensor:
+    """fp32 [m, n] whose row pitch is a multiple of 4 floats (16 bytes): rows of 261 / 322 / 1026 channels then satisfy
+    the TMA stride rule, so GEMMs writing / reading them as output or residual can use the CTA-pair kernel's TMA
+    epilogue.  Returns a (possibly non-contiguous) [m, n] view; the pad columns are never read."""
+    n4 = (n + 3) // 4 * 4
+    t = torch.empty((m, n4), dtype=torch.float32, device=device)
+    return t if n4 == n else t[:, :n]
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -83,13 +92,13 @@ def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torc
     """y = act(alpha * x @ w^T + bias) (+ residual).  x bf16 [M, ldx], w bf16 [N, ldw] (nn.Linear layout).
     Returns (y_f32 [M, N] or None, y_bf16 [M, pad8(N)] or None)."""
     m = x.shape[0]
-    y32 = torch.empty((m, N), dtype=torch.float32, device=x.device) if want_f32 else None
+    y32 = empty_f32_rows(m, N, x.device) if want_f32 else None
     y16 = torch.empty((m, pad8(N)), dtype=BF16, device=x.device) if want_bf16 else None
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.stride(-1) == 1
     gemm(x, w, M=m, N=N, K=K, bias=bias, bias_mode=bias_mode, act=act, alpha=alpha,
          residual=residual, ldr=residual.stride(0) if residual is not None else 0,
-         out_f32=y32, ldo32=N, out_bf16=y16, ldo16=pad8(N))
+         out_f32=y32, ldo32=y32.stride(0) if y32 is not None else 0, out_bf16=y16, ldo16=pad8(N))
     return y32, y16
 
 

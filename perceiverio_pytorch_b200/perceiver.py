@@ -123,7 +123,7 @@ class PerceiverDecoder(nn.Module):
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
         y32, _ = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep)
         if not self._final_project:
-            return y32
+            return y32 if y32.is_contiguous() else y32.contiguous()   # odd widths carry a 16-byte row pitch inside
         B, Nq, C = y32.shape
         n_out = self._output_num_channels
         if engine.PRECISION == "bf16x3":
@@ -138,4 +138,4 @@ class PerceiverDecoder(nn.Module):
                                                            self.final_layer.bias.detach().float().contiguous()))
         y16 = ops.layernorm_bf16(y32.view(B * Nq, C), None, None, normalize=False)
         out, _ = ops.linear(y16, C, w[0], n_out, w[1], want_f32=True, want_bf16=False)
-        return out.view(B, Nq, -1)
+        return out.contiguous().view(B, Nq, -1)

@@ -150,7 +150,7 @@ class Attention(nn.Module):
                              dqk=pa.dqk, dv=pa.dv, scale=pa.scale, key_mask=engine._as_u8(key_mask),
                              row_keep=engine._as_u8(row_keep))
         y, _ = ops.linear(o.view(B * Nq, -1), pa.V, pa.wf, pa.O, pa.bf, want_f32=True, want_bf16=False)
-        return y.view(B, Nq, -1)
+        return y.contiguous().view(B, Nq, -1)
 
 
 class MLP(nn.Module):
@@ -177,7 +177,7 @@ class MLP(nn.Module):
         pm = engine.prepared(self, "mlp", lambda: engine.PreparedMLP(self))
         shape = x.shape
         xb = ops.layernorm_bf16(x.contiguous().view(-1, shape[-1]), None, None, normalize=False)
-        return engine.mlp_only(pm, xb).view(*shape[:-1], -1)
+        return engine.mlp_only(pm, xb).contiguous().view(*shape[:-1], -1)
 
 
 class SelfAttention(nn.Module):
@@ -215,8 +215,9 @@ class SelfAttention(nn.Module):
         pm = engine.prepared(self.mlp, "mlp", lambda: engine.PreparedMLP(self.mlp))
         row_keep, key_mask = _factor_mask(attention_mask)
         x = inputs if inputs.is_contiguous() else inputs.contiguous()
-        return engine.self_attention_block(pa, pm, x, self.layer_norm1, self.layer_norm2,
-                                           key_mask=engine._as_u8(key_mask), row_keep=engine._as_u8(row_keep))
+        y = engine.self_attention_block(pa, pm, x, self.layer_norm1, self.layer_norm2,
+                                        key_mask=engine._as_u8(key_mask), row_keep=engine._as_u8(row_keep))
+        return y if y.is_contiguous() else y.contiguous()
 
 
 class CrossAttention(nn.Module):
@@ -256,7 +257,7 @@ class CrossAttention(nn.Module):
             raise NotImplementedError("attention_bias / return_matrix are not implemented by the sm_100a kernels")
         row_keep, key_mask = _factor_mask(attention_mask)
         y, _ = self._forward_factored(inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep)
-        return y
+        return y if y.is_contiguous() else y.contiguous()   # odd widths are carried with a 16-byte row pitch inside
 
     def _forward_factored(self, inputs_q, inputs_kv, *, key_mask=None, row_keep=None, want_bf16_out=False,
                           shard=None):
