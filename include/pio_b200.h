@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 4
+#define PIO_ABI_VERSION 5
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -100,6 +100,20 @@ typedef struct pio_gemm_args {
   int32_t kernel;       /* 0 = auto, 1 = single-CTA kernel (128 x tile_n tiles), 2 = CTA-pair kernel (cta_group::2,
                            256 x 256 tiles, TMA epilogue; needs K-major B, exactly one output and 16-byte aligned
                            output / residual rows) */
+  /* LayerNorm fused into the projections around it (CTA-pair kernel, batch == 1; SelfAttention :281 / :292):
+   *  - producer side (the GEMM that writes the fp32 residual stream x): additionally writes out_bf16 = bf16(x), the
+   *    UN-normalised rows, and accumulates row_stats_out[m] += (sum_n x[m,n], sum_n x[m,n]^2) with atomics (the caller
+   *    zeroes the buffer; every N tile of a row contributes);
+   *  - consumer side (the GEMM that multiplies LN(x) by W): A is that bf16(x), B is W' = W * diag(gamma), and the
+   *    epilogue applies the normalisation per output row:
+   *        v = rstd_m * (alpha * acc - mean_m * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k],
+   *        mean_m = sum / ln_channels, rstd_m = rsqrt(sumsq / ln_channels - mean_m^2 + ln_eps)
+   *    (bias must already contain W * beta). */
+  float* row_stats_out;       /* [M][2] or NULL */
+  const float* row_stats_in;  /* [M][2] or NULL */
+  const float* ln_colsum;     /* [N], required with row_stats_in */
+  int32_t ln_channels;
+  float ln_eps;
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 

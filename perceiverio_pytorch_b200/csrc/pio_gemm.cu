@@ -446,9 +446,12 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
       return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the CTA-pair kernel needs K-major B, exactly one output and "
                                        "16-byte aligned output / residual rows");
     const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
-    const bool want = a->kernel == 2 ||
+    const bool want = a->kernel == 2 || a->row_stats_out || a->row_stats_in ||
                       (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && pair_tiles * 3 >= (long long)(dev.sm_count / 2));
     if (elig && want) return launch_gemm2(a, dev, stream);
+    if (a->row_stats_out || a->row_stats_in)
+      return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the fused-LayerNorm epilogues exist in the CTA-pair kernel only "
+                                       "(batch 1, aligned outputs, enough 256 x 256 tiles)");
   }
   int bn = a->tile_n;
   if (bn == 0) {

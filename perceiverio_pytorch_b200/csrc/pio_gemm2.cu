@@ -31,6 +31,14 @@ struct Gemm2Params {
   float alpha;
   int has_residual;
   int b_swap;                    // debug: which CTA of the pair stages which half of the B tile
+  // LayerNorm fusion (pio_gemm_args): producer side ...
+  float* row_stats_out;          // [M][2] += (sum, sum of squares) of the final fp32 rows
+  __nv_bfloat16* raw_bf16;       // bf16 copy of the fp32 output (un-normalised rows), row pitch ld_raw
+  long long ld_raw;
+  // ... consumer side
+  const float* row_stats_in;     // [M][2] of the A operand's rows
+  const float* ln_colsum;        // [N]
+  float ln_inv_c, ln_eps;
 };
 
 enum { G2_BF16 = 0, G2_F32 = 1 };
@@ -43,14 +51,17 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = (KIND == G2_F32) ? 4 : 5;
   static constexpr int EPI_WARPS = 8;
   // staging slots: bf16 output 32 rows x 64 columns (128-byte rows, SWIZZLE_128B); fp32 32 rows x 16 columns (64-byte
   // rows, SWIZZLE_64B) so that two residual + two output slots per warp leave room for the fifth operand stage
   static constexpr int SLOT_BYTES = (KIND == G2_F32) ? 2048 : 4096;
   static constexpr int RES_SLOTS = (KIND == G2_F32) ? 2 : 0;
   static constexpr int OUT_SLOTS = 2;
-  static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES;
+  // fused-LayerNorm producer: raw bf16 copy of the fp32 output, 32 rows x 16 columns (32-byte rows, no swizzle)
+  static constexpr int RAW_SLOT_BYTES = 1024;
+  static constexpr int RAW_SLOTS = (KIND == G2_F32) ? 2 : 0;
+  static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES + RAW_SLOTS * RAW_SLOT_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -62,7 +73,7 @@ template <int KIND>
 __global__ void __launch_bounds__(384, 1)
 pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                 const Gemm2Params p) {
+                 const __grid_constant__ CUtensorMap tmap_raw, const Gemm2Params p) {
   using Cfg = Gemm2Cfg<KIND>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* epi_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -182,6 +193,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = ew >> 2;
     uint8_t* my = epi_base + ew * Cfg::WARP_EPI_BYTES;
     uint8_t* my_out = my + Cfg::RES_SLOTS * Cfg::SLOT_BYTES;
+    uint8_t* my_raw = my_out + Cfg::OUT_SLOTS * Cfg::SLOT_BYTES;
     uint64_t* my_res_full = res_full + ew * 2;
     const bool has_res = (KIND == G2_F32) && p.has_residual;
     constexpr int CHUNK_COLS = (KIND == G2_F32) ? 16 : 64;
@@ -220,6 +232,14 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = mp * 256 + (int)crank * Cfg::BM + quarter * 32;   // first row of this warp's block
       const int row = row0 + lane;
       const float row_bias = (p.bias_mode == 2 && row < p.M) ? __ldg(p.bias + row) : 0.0f;
+      // fused LayerNorm, consumer side: this row's mean / rstd from the statistics its producer accumulated
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (KIND == G2_BF16 && p.row_stats_in != nullptr && row < p.M) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.row_stats_in) + row);
+        ln_mean = st.x * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(st.y * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;   // producer side: this row's partial statistics over the tile
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -250,6 +270,28 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
         }
+        if constexpr (KIND == G2_BF16) {
+          if (p.row_stats_in != nullptr) {
+            // v = rstd * (acc - mean * colsum[n])   (bias, which already holds W.beta, is added below)
+            const float nm = -ln_mean;
+            if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
+                v[4 * j] = ln_rstd * fmaf(nm, cs.x, v[4 * j]);
+                v[4 * j + 1] = ln_rstd * fmaf(nm, cs.y, v[4 * j + 1]);
+                v[4 * j + 2] = ln_rstd * fmaf(nm, cs.z, v[4 * j + 2]);
+                v[4 * j + 3] = ln_rstd * fmaf(nm, cs.w, v[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CHUNK_COLS; ++j) {
+                const float cs = (col0 + j < p.N) ? __ldg(p.ln_colsum + col0 + j) : 0.f;
+                v[j] = ln_rstd * fmaf(nm, cs, v[j]);
+              }
+            }
+          }
+        }
         if (p.bias_mode == 1) {
           if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15u) == 0)) {
 #pragma unroll
@@ -278,9 +320,27 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
             }
           }
+          if (p.row_stats_out != nullptr) {
+            // fused LayerNorm, producer side: statistics of the final row values (columns past N are zero-weighted)
+#pragma unroll
+            for (int j = 0; j < CHUNK_COLS; ++j)
+              if (col0 + j < p.N) {
+                st_sum += v[j];
+                st_sq = fmaf(v[j], v[j], st_sq);
+              }
+          }
           uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
-          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
+          uint8_t* slot_raw = my_raw + (use_idx & 1u) * Cfg::RAW_SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<1>();   // the stores issued two chunks ago used these slots
           __syncwarp();
+          if (p.raw_bf16 != nullptr) {
+            // bf16 copy of the un-normalised row segment (32 bytes per row) for the fused LayerNorm of the consumer
+            uint4* rp = reinterpret_cast<uint4*>(slot_raw + lane * 32);
+            rp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                               pack_bf16x2(v[6], v[7]));
+            rp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                               pack_bf16x2(v[14], v[15]));
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<float4*>(slot_out + sw64_offset(lane, j)) =
@@ -289,6 +349,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
           if (lane == 0) {
             tma_store_3d(&tmap_out, slot_out, col0, row0, z);
+            if (p.raw_bf16 != nullptr) tma_store_3d(&tmap_raw, slot_raw, col0, row0, z);
             bulk_commit();
             if (has_res) issue_res();   // refills the residual slot that was just consumed
           }
@@ -315,6 +376,10 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ++use_idx;
         }
       }
+      if (KIND == G2_F32 && p.row_stats_out != nullptr && row < p.M) {
+        atomicAdd(p.row_stats_out + 2 * (long long)row, st_sum);
+        atomicAdd(p.row_stats_out + 2 * (long long)row + 1, st_sq);
+      }
     }
     if (lane == 0) bulk_wait_read<0>();   // staging slots must outlive the stores that read them
   }
@@ -332,7 +397,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int KIND>
 static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<KIND>;
-  CUtensorMap ta, tb, to, tr;
+  CUtensorMap ta, tb, to, tr, traw;
   const bool a_bcast = a->batch > 1 && a->strideA == 0;
   const bool b_bcast = a->batch > 1 && a->strideB == 0;
   const bool r_bcast = a->batch > 1 && a->strideR == 0;
@@ -358,6 +423,14 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
     int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, 64);
     if (rc != PIO_OK) return rc;
     tr = to;
+    traw = to;
+    if (a->out_bf16) {
+      const uint64_t wdims[3] = {(uint64_t)a->N, (uint64_t)a->M, 1};
+      const uint64_t wstrides[2] = {(uint64_t)a->ldo16 * 2, (uint64_t)a->ldo16 * (uint64_t)a->M * 2};
+      const uint32_t wbox[3] = {16, 32, 1};
+      rc = encode_tmap(&traw, a->out_bf16, false, 3, wdims, wstrides, wbox, 0);
+      if (rc != PIO_OK) return rc;
+    }
     if (a->residual) {
       const uint64_t rb = r_bcast ? 1 : a->batch;
       const uint64_t rdims[3] = {(uint64_t)a->N, (uint64_t)a->M, rb};
@@ -372,6 +445,7 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
     int rc = encode_tmap(&to, a->out_bf16, false, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
     tr = to;
+    traw = to;
   }
   Gemm2Params p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
@@ -381,6 +455,13 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.bias = a->bias; p.bias_mode = a->bias ? a->bias_mode : 0;
   p.act = a->act; p.alpha = a->alpha;
   p.has_residual = a->residual != nullptr;
+  p.row_stats_out = (KIND == G2_F32) ? a->row_stats_out : nullptr;
+  p.raw_bf16 = (KIND == G2_F32) ? reinterpret_cast<__nv_bfloat16*>(a->out_bf16) : nullptr;
+  p.ld_raw = a->ldo16;
+  p.row_stats_in = (KIND == G2_BF16) ? a->row_stats_in : nullptr;
+  p.ln_colsum = a->ln_colsum;
+  p.ln_inv_c = a->ln_channels > 0 ? 1.0f / (float)a->ln_channels : 0.f;
+  p.ln_eps = a->ln_eps;
   static const int b_swap = [] { const char* e = getenv("PIO_GEMM2_BSWAP"); return (e && e[0] == '1') ? 1 : 0; }();
   p.b_swap = b_swap;
 
@@ -400,7 +481,7 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
     const double bytes = (KIND == G2_F32 ? 4.0 * (a->residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
     ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, bytes, stream);
     PIO_CUDA_OK(launch_kernel(pio_gemm2_kernel<KIND>, dim3((unsigned)(pairs * 2), 1, 1), dim3(384, 1, 1), Cfg::SMEM_BYTES,
-                              stream, 2, ta, tb, to, tr, p));
+                              stream, 2, ta, tb, to, tr, traw, p));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
@@ -411,8 +492,15 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
 bool gemm2_eligible(const pio_gemm_args* a) {
   if (a->b_mn_major) return false;
   const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
-  if (f32 == b16) return false;                       // exactly one output
-  if (b16 && a->residual) return false;
+  if (!f32 && !b16) return false;
+  if (f32 && b16) {
+    // fp32 output plus its raw bf16 copy (fused-LayerNorm producer): staged per 16-column chunk, TMA-stored
+    if (a->batch != 1 || a->ldo16 % 8 != 0 || a->ldo16 < a->N || !aligned16(a->out_bf16)) return false;
+  }
+  if (!f32 && a->residual) return false;
+  if ((a->row_stats_out || a->row_stats_in) && a->batch != 1) return false;
+  if (a->row_stats_out && !f32) return false;
+  if (a->row_stats_in && (f32 || !a->ln_colsum || a->ln_channels <= 0)) return false;
   if (f32) {
     if (!aligned16(a->out_f32) || a->ldo32 % 4 != 0 || a->ldo32 < a->N) return false;
     if (a->batch > 1 && (a->strideO32 % 4 != 0 || a->strideO32 <= 0)) return false;
@@ -420,7 +508,8 @@ bool gemm2_eligible(const pio_gemm_args* a) {
       if (!aligned16(a->residual) || a->ldr % 4 != 0 || a->ldr < a->N) return false;
       if (a->batch > 1 && a->strideR % 4 != 0) return false;
     }
-  } else {
+  }
+  if (!f32) {
     if (!aligned16(a->out_bf16) || a->ldo16 % 8 != 0 || a->ldo16 < a->N) return false;
     if (a->batch > 1 && (a->strideO16 % 8 != 0 || a->strideO16 <= 0)) return false;
   }

@@ -53,7 +53,8 @@ int get_device_info(DeviceInfo* out);
 // Encodes a bf16 tensor of rank `rank` (dims[0] innermost) with SWIZZLE_128B and zero OOB fill.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 entries, for dims[1..] */, const uint32_t* box);
-// Same for fp32 (is_f32) or bf16 elements; the box's inner extent must span exactly `swizzle_bytes` (128 or 64) bytes.
+// Same for fp32 (is_f32) or bf16 elements; the box's inner extent must span exactly `swizzle_bytes` (128 or 64) bytes,
+// or any multiple of 16 bytes with swizzle_bytes = 0 (no swizzle).
 int encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 

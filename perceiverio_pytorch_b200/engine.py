@@ -10,6 +10,7 @@ happens once per module and is cached as non-persistent derived state keyed on t
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -28,6 +29,11 @@ def set_precision(mode: str) -> None:
         raise ValueError(f"unknown precision {mode!r}: use 'bf16' or 'bf16x3'")
     PRECISION = mode
 
+
+# Tower LayerNorms folded into the projections around them when the latent array has at least
+# this many rows (the fused epilogues live in the CTA-pair GEMM kernel)
+FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
+FUSE_LN_MIN_ROWS = 2048
 
 # Flags (module-level so tests / bench can flip them)
 ENABLE_FOLDING = True      # single-head cross-attention: K == V == LN(x)
@@ -93,6 +99,76 @@ class PreparedMLP:
         self.w2, self.b2 = _bf16_weight(mlp.fc2.weight.detach()), mlp.fc2.bias.detach().float().contiguous()
         self.hidden, self.cin = mlp.fc1.weight.shape
         self.cout = mlp.fc2.weight.shape[0]
+
+
+class PreparedFusedLayer:
+    """One SelfAttention block with both LayerNorms folded into the projections that consume them:
+    LN(x) W^T = rstd (x (W diag(gamma))^T - mean colsum) + (W beta + b); the GEMM takes the raw bf16 rows and applies
+    the per-row normalisation in its epilogue (pio_gemm_args.row_stats_in)."""
+
+    def __init__(self, sa):
+        att, mlp = sa.attention, sa.mlp
+        d = torch.float64
+        g1, b1 = sa.layer_norm1.weight.detach().to(d), sa.layer_norm1.bias.detach().to(d)
+        g2, b2 = sa.layer_norm2.weight.detach().to(d), sa.layer_norm2.bias.detach().to(d)
+        wqkv = torch.cat([att.proj_q.weight, att.proj_k.weight, att.proj_v.weight], 0).detach().to(d)
+        bqkv = torch.cat([att.proj_q.bias, att.proj_k.bias, att.proj_v.bias], 0).detach().to(d)
+        self.H = att._num_heads
+        self.QK, self.C = att.proj_q.weight.shape
+        self.V = att.proj_v.weight.shape[0]
+        self.O = att.final.weight.shape[0]
+        self.dqk, self.dv = self.QK // self.H, self.V // self.H
+        self.scale = 1.0 / math.sqrt(self.dqk)
+        self.eps1, self.eps2 = float(sa.layer_norm1.eps), float(sa.layer_norm2.eps)
+        self.wqkv = _bf16_weight((wqkv * g1[None, :]).float())
+        self.bqkv = (bqkv + wqkv @ b1).float().contiguous()
+        # column sums of exactly the bf16 values the tensor core multiplies (so mean * colsum cancels consistently)
+        self.cs_qkv = self.wqkv[:, :self.C].double().sum(1).float().contiguous()
+        self.wf = _bf16_weight(att.final.weight.detach())
+        self.bf = att.final.bias.detach().float().contiguous()
+        w1, bb1 = mlp.fc1.weight.detach().to(d), mlp.fc1.bias.detach().to(d)
+        self.hidden, self.cin = mlp.fc1.weight.shape
+        self.cout = mlp.fc2.weight.shape[0]
+        self.w1 = _bf16_weight((w1 * g2[None, :]).float())
+        self.b1 = (bb1 + w1 @ b2).float().contiguous()
+        self.cs_1 = self.w1[:, :self.cin].double().sum(1).float().contiguous()
+        self.w2 = _bf16_weight(mlp.fc2.weight.detach())
+        self.b2 = mlp.fc2.bias.detach().float().contiguous()
+
+    def usable(self) -> bool:
+        # the producer GEMMs write a raw bf16 copy in 16-column chunks; the tower keeps its width
+        return (self.C % 16 == 0 and self.O == self.C and self.cin == self.C and self.cout == self.C
+                and _streaming_ok(self.H, self.dqk, self.dv))
+
+
+def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torch.Tensor, st: torch.Tensor, *,
+                               B: int, N: int, st_mid: torch.Tensor, st_out: Optional[torch.Tensor]):
+    """SelfAttention.forward with fused LayerNorms.  x fp32 [M, C] (the residual stream), xb = bf16(x) [M, C],
+    st = per-row (sum, sum of squares) of x; st_mid / st_out are zeroed [M, 2] buffers for the two residual-stream
+    states this block produces (st_out None: the block's output feeds no further fused LayerNorm).
+    Returns (y fp32 [M, C], bf16(y) or None)."""
+    M, C = x.shape
+    dev = x.device
+    nqkv = 2 * pf.QK + pf.V
+    ld = pad8(nqkv)
+    qkv = torch.empty((M, ld), dtype=BF16, device=dev)
+    ops.gemm(xb, pf.wqkv, M=M, N=nqkv, K=C, lda=xb.stride(0), bias=pf.bqkv, out_bf16=qkv, ldo16=ld,
+             row_stats_in=st, ln_colsum=pf.cs_qkv, ln_channels=C, ln_eps=pf.eps1)
+    o = attention(qkv, ld, 0, qkv, ld, pf.QK, qkv, ld, 2 * pf.QK, B=B, H=pf.H, Nq=N, Nk=N, dqk=pf.dqk, dv=pf.dv,
+                  scale=pf.scale)
+    o2 = o.view(M, -1)
+    x1 = torch.empty((M, C), dtype=torch.float32, device=dev)
+    x1b = torch.empty((M, C), dtype=BF16, device=dev)
+    ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, residual=x, ldr=x.stride(0), out_f32=x1, ldo32=C,
+             out_bf16=x1b, ldo16=C, row_stats_out=st_mid)
+    h = torch.empty((M, pad8(pf.hidden)), dtype=BF16, device=dev)
+    ops.gemm(x1b, pf.w1, M=M, N=pf.hidden, K=C, bias=pf.b1, act=1, out_bf16=h, ldo16=h.stride(0),
+             row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2)
+    y = torch.empty((M, C), dtype=torch.float32, device=dev)
+    yb = torch.empty((M, C), dtype=BF16, device=dev) if st_out is not None else None
+    ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, residual=x1, ldr=C, out_f32=y, ldo32=C,
+             out_bf16=yb, ldo16=C if yb is not None else 0, row_stats_out=st_out)
+    return y, yb
 
 
 def _versions(module):
@@ -233,12 +309,19 @@ def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv
 # blocks
 # ---------------------------------------------------------------------------------------------------------------
 
-def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False):
-    """x + fc2(gelu(fc1(LN(x)))) on a flat fp32 [M, C] matrix.  Returns (fp32 [M, cout], bf16 copy or None)."""
+def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False, stats_out=None):
+    """x + fc2(gelu(fc1(LN(x)))) on a flat fp32 [M, C] matrix.  Returns (fp32 [M, cout], bf16 copy or None).
+    `stats_out` (zeroed fp32 [M, 2]) additionally receives the per-row (sum, sum of squares) of the result — the
+    producer side of the fused LayerNorm of the next block."""
     xn = ops.layernorm_bf16(x_f32, ln_w, ln_b)
     _, h = ops.linear(xn, pm.cin, pm.w1, pm.hidden, pm.b1, act=1)
-    y32, y16 = ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, residual=x_f32, want_f32=True,
-                          want_bf16=want_bf16_out)
+    if stats_out is None:
+        return ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, residual=x_f32, want_f32=True, want_bf16=want_bf16_out)
+    m = h.shape[0]
+    y32 = ops.empty_f32_rows(m, pm.cout, h.device)
+    y16 = torch.empty((m, pad8(pm.cout)), dtype=BF16, device=h.device)
+    ops.gemm(h, pm.w2, M=m, N=pm.cout, K=pm.hidden, bias=pm.b2, residual=x_f32, ldr=x_f32.stride(0),
+             out_f32=y32, ldo32=y32.stride(0), out_bf16=y16, ldo16=y16.stride(0), row_stats_out=stats_out)
     return y32, y16
 
 
@@ -340,7 +423,7 @@ def _as_u8(mask: Optional[torch.Tensor]):
 
 def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torch.Tensor, inputs_kv: torch.Tensor,
                           ln_q, ln_kv, ln2, *, use_query_residual: bool, key_mask=None, row_keep=None,
-                          want_bf16_out=False, shard=None):
+                          want_bf16_out=False, shard=None, stats_out=None):
     """CrossAttention.forward (transformer_primitives.py:371-406).
 
     inputs_q fp32 [B, Nq, Cq] (batch stride may be 0), inputs_kv fp32 [B, Nk, Ck].  `shard`, if given, is a
@@ -369,5 +452,5 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     else:
         res = None
     x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res)
-    y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out)
+    y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
     return y32.view(B, Nq, -1), y16

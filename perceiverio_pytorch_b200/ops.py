@@ -71,7 +71,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          residual: Optional[torch.Tensor] = None, ldr: int = 0, strideR: int = 0,
          out_f32: Optional[torch.Tensor] = None, ldo32: int = 0, strideO32: int = 0,
          out_bf16: Optional[torch.Tensor] = None, ldo16: int = 0, strideO16: int = 0,
-         tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None) -> None:
+         tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None,
+         row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None,
+         ln_colsum: Optional[torch.Tensor] = None, ln_channels: int = 0, ln_eps: float = 1e-5) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
     assert A.dtype == BF16 and B.dtype == BF16
@@ -82,7 +84,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       _ptr(residual), ldr, strideR, _ptr(out_f32), ldo32, strideO32,
                       _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas,
                       GEMM_CLUSTER_M if cluster_m is None else cluster_m,
-                      GEMM_KERNEL if kernel is None else kernel)
+                      GEMM_KERNEL if kernel is None else kernel,
+                      _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 

@@ -81,12 +81,33 @@ class PerceiverEncoder(nn.Module):
             if self.key_shard is not None:
                 any_key = self.key_shard.any_over_ranks(any_key)
             row_keep = any_key.expand(latents.shape[0], latents.shape[1])
-        z, _ = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
-                                                   shard=self.key_shard)
-        for _ in range(self._num_blocks):
-            for self_attend in self.self_attends:
+        B, N, C = latents.shape
+        layers = [sa for _ in range(self._num_blocks) for sa in self.self_attends]
+        fused = None
+        if (engine.FUSE_LN and engine.PRECISION == "bf16" and layers and B * N >= engine.FUSE_LN_MIN_ROWS
+                and latents.is_cuda and not any(sa.training and any(p > 0 for p in sa._dropout_probs) for sa in layers)):
+            fused = [engine.prepared(sa, "fused", lambda sa=sa: engine.PreparedFusedLayer(sa)) for sa in self.self_attends]
+            if not all(pf.usable() for pf in fused):
+                fused = None
+        if fused is None:
+            z, _ = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
+                                                       shard=self.key_shard)
+            for self_attend in layers:
                 z = self_attend(z)
-        return z
+            return z
+        # Latent tower with the LayerNorms folded into the projections: every residual-stream
+        # state travels as (fp32 rows, their raw bf16 copy, per-row sum / sum of squares); no LayerNorm kernel runs.
+        M = B * N
+        stats = torch.zeros((2 * len(layers) + 1, M, 2), dtype=torch.float32, device=latents.device)
+        z, zb = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
+                                                    shard=self.key_shard, want_bf16_out=True, stats_out=stats[0])
+        x = z.view(M, C)
+        for i in range(len(layers)):
+            pf = fused[i % len(self.self_attends)]
+            last = i == len(layers) - 1
+            x, zb = engine.self_attention_block_fused(pf, x, zb, stats[2 * i], B=B, N=N, st_mid=stats[2 * i + 1],
+                                                      st_out=None if last else stats[2 * i + 2])
+        return x.view(B, N, C)
 
 
 class PerceiverDecoder(nn.Module):

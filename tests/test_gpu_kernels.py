@@ -208,3 +208,42 @@ def test_linear_f32(m, n, k):
     y = ops.linear_f32(x, w, b)
     ref = (x.double() @ w.double().t() + b.double()).float()
     assert _rel(y, ref) < 1e-5   # fp32 accumulation order only
+
+
+def test_gemm_fused_layernorm_epilogues():
+    """Producer side: fp32 output + raw bf16 copy + per-row (sum, sum of squares).  Consumer side: raw bf16 rows times
+    W diag(gamma) with the normalisation applied per output row in the epilogue == LayerNorm(x) @ W^T + b."""
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(3)
+    M, C, N = 2048, 1024, 768
+    dev = "cuda"
+    # ---- producer: x = h @ W2^T + b + residual
+    h = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    w2 = (torch.randn(C, C, device=dev) / 32).to(torch.bfloat16)
+    b2 = torch.randn(C, device=dev)
+    res = torch.randn(M, C, device=dev) * 2 + 0.3
+    x = torch.empty(M, C, device=dev)
+    xb = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+    st = torch.zeros(M, 2, device=dev)
+    ops.gemm(h, w2, M=M, N=C, K=C, bias=b2, residual=res, ldr=C, out_f32=x, ldo32=C, out_bf16=xb, ldo16=C,
+             row_stats_out=st)
+    x_ref = h.float() @ w2.float().t() + b2 + res
+    assert _rel(x, x_ref) < 2e-3
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert _rel(st[:, 0], x.sum(1)) < 1e-4 and _rel(st[:, 1], (x * x).sum(1)) < 1e-4
+    # ---- consumer: LN(x) @ W^T + b through the raw bf16 rows
+    gamma, beta = 1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)
+    w = torch.randn(N, C, device=dev) / 32
+    b = torch.randn(N, device=dev)
+    wp = (w * gamma[None, :]).to(torch.bfloat16)
+    bias = b + w @ beta
+    colsum = wp.double().sum(1).float()
+    y = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ops.gemm(xb, wp, M=M, N=N, K=C, bias=bias, out_bf16=y, ldo16=N, row_stats_in=st, ln_colsum=colsum, ln_channels=C,
+             ln_eps=1e-5)
+    ref = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
+    assert _rel(y.float(), ref) < 1e-2
+    # the epilogues exist in the CTA-pair kernel only: a problem it cannot take is rejected, not silently unfused
+    with pytest.raises(RuntimeError, match="fused-LayerNorm"):
+        ops.gemm(xb, wp, M=M // 2, N=N, K=C, batch=2, strideA=(M // 2) * C, strideB=0, bias=bias, out_bf16=y, ldo16=N,
+                 strideO16=(M // 2) * N, row_stats_in=st, ln_colsum=colsum, ln_channels=C)

@@ -272,3 +272,37 @@ def test_full_depth_language_config_matches_oracle():
     ez, eo = rel_err(z.cpu(), z_ref), rel_err(out.cpu(), out_ref)
     print(f"language full depth: latents max {ez[0]:.3e} l2 {ez[1]:.3e}; output max {eo[0]:.3e} l2 {eo[1]:.3e}")
     assert ez[0] <= BF16_TOL and eo[0] <= BF16_TOL, (ez, eo)
+
+
+def test_fused_layernorm_tower_matches_oracle_and_unfused_path():
+    """Latent arrays of >= 2048 rows take the tower with the LayerNorms folded into the projections (no LayerNorm
+    kernel, statistics accumulated by the producing GEMMs): same 1e-2 bound against the oracle, and close to the
+    unfused CUDA path."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import engine
+    cfg = CONFIGS["classification"]
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(**dict(cfg["enc"], num_self_attends_per_block=3, num_blocks=2)).eval()
+    _perturb(enc, 7)
+    B, Nk = 4, 3000
+    inputs = torch.randn(B, Nk, 261)
+    pe = {k: v.detach() for k, v in enc.state_dict().items()}
+    from oracle import perceiver_oracle as O
+    z_ref = O.encoder_forward(pe, "", num_blocks=2, num_self_attends_per_block=3, num_cross_attend_heads=1,
+                              num_self_attend_heads=8, use_query_residual=True, inputs=inputs)
+    enc = enc.cuda()
+    x = inputs.cuda()
+    assert B * 512 >= engine.FUSE_LN_MIN_ROWS
+    with torch.inference_mode():
+        n0 = pio._lib.launch_count() if hasattr(pio, "_lib") else None
+        z_fused = enc(x, enc.latents(x))
+        engine.FUSE_LN = False
+        try:
+            z_plain = enc(x, enc.latents(x))
+        finally:
+            engine.FUSE_LN = True
+    ef, ep = rel_err(z_fused.cpu(), z_ref), rel_err(z_plain.cpu(), z_ref)
+    print(f"fused tower: max {ef[0]:.3e} l2 {ef[1]:.3e}; unfused: max {ep[0]:.3e} l2 {ep[1]:.3e}; "
+          f"fused vs unfused {rel_err(z_fused, z_plain)[0]:.3e}")
+    assert ef[0] <= BF16_TOL, ef
+    assert rel_err(z_fused, z_plain)[0] <= 5e-3

@@ -241,6 +241,27 @@ def group_perf():
             t = _time(lambda: ops.gemm(A, W, M=M, N=N, K=1024, bias=bias, act=1, out_bf16=o16, ldo16=N, kernel=2))
             line += f"; gelu bf16-out {2 * M * N * 1024 / t / 1e9:.0f} TF/s"
         print(line, flush=True)
+    # fused-LayerNorm epilogues
+    W1 = torch.randn(1024, 1024, device=dev).to(torch.bfloat16)
+    o16 = torch.empty(M, 1024, dtype=torch.bfloat16, device=dev)
+    o32 = torch.empty(M, 1024, device=dev)
+    st = torch.zeros(M, 2, device=dev)
+    cs = torch.randn(1024, device=dev)
+    fl = 2 * M * 1024 * 1024
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, residual=res, ldr=1024, out_f32=o32, ldo32=1024, kernel=2))
+    line = f"producer 32768x1024x1024: plain {fl / t / 1e9:.0f}"
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, residual=res, ldr=1024, out_f32=o32, ldo32=1024, out_bf16=o16, ldo16=1024, kernel=2))
+    line += f"; +raw bf16 {fl / t / 1e9:.0f}"
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, residual=res, ldr=1024, out_f32=o32, ldo32=1024, row_stats_out=st, kernel=2))
+    line += f"; +stats {fl / t / 1e9:.0f}"
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, residual=res, ldr=1024, out_f32=o32, ldo32=1024, out_bf16=o16, ldo16=1024, row_stats_out=st, kernel=2))
+    line += f"; +both {fl / t / 1e9:.0f} TF/s"
+    print(line, flush=True)
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, act=1, out_bf16=o16, ldo16=1024, kernel=2))
+    line = f"consumer 32768x1024x1024 gelu: plain {fl / t / 1e9:.0f}"
+    t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, act=1, out_bf16=o16, ldo16=1024, kernel=2, row_stats_in=st, ln_colsum=cs, ln_channels=1024))
+    line += f"; +row affine {fl / t / 1e9:.0f} TF/s"
+    print(line, flush=True)
     Ab = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
     Wb = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
     ob = torch.empty(8192, 8192, dtype=torch.bfloat16, device=dev)
