@@ -67,6 +67,13 @@ class PerceiverEncoder(nn.Module):
                                                    v_channels=v_channels,
                                                    widening_factor=self_attend_widening_factor))
         self.key_shard = None  # set by parallel.shard_encoder_keys(): inputs hold this rank's slice of the key axis
+        # Encode-once: the reference's chunked decoders call the whole PerceiverIO — encoder
+        # included — once per output chunk on the SAME inputs (multimodal_perceiver.py:146-161: 128 calls).  With
+        # cache_latents = True the encoder returns the latents of the previous call when it is handed inputs / latents /
+        # mask that are exactly equal to the previous call's and its parameters are unchanged (opt-in: it keeps the
+        # previous input array alive and spends one comparison pass + host sync per call).
+        self.cache_latents = False
+        self._latent_cache = None
 
     def latents(self, inputs):
         return self.latent_pos_enc(batch_size=inputs.shape[0])
@@ -81,6 +88,34 @@ class PerceiverEncoder(nn.Module):
             if self.key_shard is not None:
                 any_key = self.key_shard.any_over_ranks(any_key)
             row_keep = any_key.expand(latents.shape[0], latents.shape[1])
+        use_cache = (self.cache_latents and self.key_shard is None and inputs.is_cuda
+                     and not torch.cuda.is_current_stream_capturing())
+        if use_cache:
+            params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            c = self._latent_cache
+            if (c is not None and c["params"] == params and c["precision"] == engine.PRECISION
+                    and self._equal(inputs, c["inputs"]) and self._equal(latents, c["latents"])
+                    and (input_mask is None) == (c["mask"] is None)
+                    and (input_mask is None or self._equal(input_mask, c["mask"]))):
+                return c["z"]
+        z = self._encode(inputs, latents, key_mask, row_keep)
+        if use_cache:
+            # private copies: the caller may overwrite its tensors in place afterwards
+            self._latent_cache = dict(params=params, precision=engine.PRECISION, z=z, inputs=inputs.clone(),
+                                      latents=latents.clone(),
+                                      mask=None if input_mask is None else input_mask.clone())
+        return z
+
+    @staticmethod
+    def _equal(t, cached) -> bool:
+        """Exact content equality with the private copy kept from the previous call (one device-side comparison and a
+        host sync; the reference's wrappers rebuild the preprocessed input array for every chunk, so identity of the
+        tensor object cannot be used)."""
+        if t.shape != cached.shape or t.dtype != cached.dtype or t.device != cached.device:
+            return False
+        return bool(torch.equal(t, cached))
+
+    def _encode(self, inputs, latents, key_mask, row_keep):
         B, N, C = latents.shape
         layers = [sa for _ in range(self._num_blocks) for sa in self.self_attends]
         fused = None

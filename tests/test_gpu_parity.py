@@ -306,3 +306,26 @@ def test_fused_layernorm_tower_matches_oracle_and_unfused_path():
           f"fused vs unfused {rel_err(z_fused, z_plain)[0]:.3e}")
     assert ef[0] <= BF16_TOL, ef
     assert rel_err(z_fused, z_plain)[0] <= 5e-3
+
+
+def test_encode_once_latent_cache():
+    """cache_latents: a second call with equal (but re-built) inputs returns the cached latents without launching the
+    encoder; different inputs, an in-place change or a parameter update invalidate it."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import _lib
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(num_input_channels=64, num_self_attends_per_block=1, num_blocks=1, num_latents=128,
+                               num_latent_channels=256).eval().cuda()
+    enc.cache_latents = True
+    x = torch.randn(2, 500, 64, device="cuda")
+    with torch.inference_mode():
+        z0 = enc(x, enc.latents(x))
+        n0 = _lib.launch_count()
+        z1 = enc(x.clone(), enc.latents(x))              # same content, new tensor
+        assert _lib.launch_count() == n0 and z1 is z0
+        z2 = enc(x + 1.0, enc.latents(x))                 # different content
+        assert _lib.launch_count() > n0 and not torch.equal(z2, z0)
+        n1 = _lib.launch_count()
+        enc.cross_attend.attention.proj_q.bias.add_(0.5)  # parameter update
+        enc(x + 1.0, enc.latents(x))
+        assert _lib.launch_count() > n1
