@@ -177,11 +177,15 @@ class PerceiverDecoder(nn.Module):
 
     def forward(self, query, latents, *, query_mask=None):
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
-        y32, _ = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep)
+        n_out = self._output_num_channels
+        # the wide final projection consumes bf16 rows: let the MLP's last GEMM write them next to the fp32 result
+        want16 = (self._final_project and n_out > 16 and engine.PRECISION == "bf16"
+                  and self.query_channels % 16 == 0)
+        y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
+                                                              want_bf16_out=want16)
         if not self._final_project:
             return y32 if y32.is_contiguous() else y32.contiguous()   # odd widths carry a 16-byte row pitch inside
         B, Nq, C = y32.shape
-        n_out = self._output_num_channels
         if engine.PRECISION == "bf16x3":
             return validate.final_layer(self.final_layer, y32)
         if n_out <= 16:
@@ -192,6 +196,7 @@ class PerceiverDecoder(nn.Module):
             return out.view(B, Nq, -1)
         w = engine.prepared(self.final_layer, "w", lambda: (engine._bf16_weight(self.final_layer.weight.detach()),
                                                            self.final_layer.bias.detach().float().contiguous()))
-        y16 = ops.layernorm_bf16(y32.view(B * Nq, C), None, None, normalize=False)
+        if y16 is None:
+            y16 = ops.layernorm_bf16(y32.view(B * Nq, C), None, None, normalize=False)
         out, _ = ops.linear(y16, C, w[0], n_out, w[1], want_f32=True, want_bf16=False)
         return out.contiguous().view(B, Nq, -1)
