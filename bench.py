@@ -367,7 +367,11 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
         "roofline": {"bound": "tensor", "kernel": "pio_gemm2_kernel / pio_gemm_kernel (tcgen05 GEMMs with fused epilogue), all GEMM launches of the step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"], "traffic": None,
+                     "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"],
+                     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), averaged over the four GEMM
+                     # shapes of a tower layer, from the committed `ncu --set full` capture; their algorithmic bytes
+                     # (operands + fp32 residual in/out + raw bf16 rows) average 305 MB per launch
+                     "traffic": 2.60e8, "traffic_source": "profiles/r01h_ncu_full_encoder_and_tower_summary.csv",
                      "share_of_step": shares.get("gemm")},
         "model": {"flops_per_sample_reference_algorithm": mf,
                   "tflops_reference_algorithm": mf * value / 1e12,
