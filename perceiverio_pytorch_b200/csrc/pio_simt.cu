@@ -95,70 +95,229 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
   }
 }
 
-template <int MAXV, int ROWS>
+template <int MAXV, int ROWS, bool SPLIT>
 __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restrict__ x, long long ldx,
                                                             __nv_bfloat16* __restrict__ y, long long ldy,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows, int C,
                                                             int mode, float eps) {
+  // This path is instruction-issue bound (ncu: 72 % issue-active at 365 instructions per row in its first form), so
+  // each warp walks many row groups with the affine parameters held in registers and as little per-element control
+  // flow as possible.
   const int normalize = mode & 1;
   // validation mode: three segments of ldy / 3 columns, [hi | lo | hi] (A side, bit 1) or [hi | hi | lo] (B side, bit 2)
-  const bool split = (mode & 6) != 0;
   const bool b_side = (mode & 4) != 0;
-  const int seg = split ? (int)(ldy / 3) : (int)ldy;
+  const int seg = SPLIT ? (int)(ldy / 3) : (int)ldy;
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)(gridDim.x - 1 - blockIdx.x) * 4 + (threadIdx.x >> 5)) * ROWS;   // back to front, see above
-  if (row0 >= rows) return;
-  float v[ROWS][MAXV];
-  float s[ROWS];
+  const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 4;
+  const long long ngroups = (rows + ROWS - 1) / ROWS;
+  const float inv_c = 1.0f / (float)C;
+  float g[MAXV], bt[MAXV];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const bool rok = row0 + r < rows;
-    const float* xr = x + (row0 + r) * ldx;
-    s[r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + 32 * i;
-      v[r][i] = (rok && c < C) ? __ldg(xr + c) : 0.f;
-      s[r] += v[r][i];
-    }
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = (gamma && c < C) ? __ldg(gamma + c) : 1.f;
+    bt[i] = (beta && c < C) ? __ldg(beta + c) : 0.f;
   }
+  // back to front: the tail of x is what is still resident in L2, and the front of y is what the consumer asks for first
+  for (long long grp = ngroups - 1 - wid; grp >= 0; grp -= nwarps) {
+    const long long row0 = grp * ROWS;
+    float v[ROWS][MAXV];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    if (row0 + r >= rows) break;  // warp-uniform
-    float mean = 0.f, rstd = 1.f;
-    if (normalize) {
-      mean = warp_sum(s[r]) / (float)C;
-      float q = 0.f;
+    for (int r = 0; r < ROWS; ++r) {
+      const bool rok = row0 + r < rows;
+      const float* xr = x + (row0 + r) * ldx;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = lane + 32 * i;
-        const float d = (c < C) ? v[r][i] - mean : 0.f;
-        q += d * d;
+        v[r][i] = (rok && c < C) ? __ldg(xr + c) : 0.f;
       }
-      rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     }
-    __nv_bfloat16* yr = y + (row0 + r) * ldy;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < seg) {
-        float o = 0.f;
-        if (c < C) {
-          o = (v[r][i] - mean) * rstd;
-          if (gamma) o = o * __ldg(gamma + c);
-          if (beta) o += __ldg(beta + c);
+    for (int r = 0; r < ROWS; ++r) {
+      if (row0 + r >= rows) break;  // warp-uniform
+      float mean = 0.f, rstd = 1.f;
+      if (normalize) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s += v[r][i];
+        mean = warp_sum(s) * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const float d = (lane + 32 * i < C) ? v[r][i] - mean : 0.f;
+          q = fmaf(d, d, q);
         }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-        yr[c] = hi;
-        if (split) {
-          const __nv_bfloat16 lo = __float2bfloat16_rn(o - __bfloat162float(hi));
-          yr[seg + c] = b_side ? hi : lo;
-          yr[2 * seg + c] = b_side ? lo : hi;
+        rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+      }
+      __nv_bfloat16* yr = y + (row0 + r) * ldy;
+      const float nmr = -mean * rstd;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < seg) {
+          // (v - mean) * rstd * gamma + beta; pad columns (C <= c < seg) have v = 0, gamma = 1, beta = 0 -> forced to 0
+          float o = fmaf(fmaf(v[r][i], rstd, nmr), g[i], bt[i]);
+          if (c >= C) o = 0.f;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+          yr[c] = hi;
+          if (SPLIT) {
+            const __nv_bfloat16 lo = __float2bfloat16_rn(o - __bfloat162float(hi));
+            yr[seg + c] = b_side ? hi : lo;
+            yr[2 * seg + c] = b_side ? lo : hi;
+          }
         }
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm + cast for CONTIGUOUS arrays of odd-width rows (the 261 / 322 / 1026-channel input and query arrays:
+// rows are 1044 / 1288 / 4104 bytes, so neither vector loads nor a tiled tensor map can address them).  The array is
+// treated as a flat byte stream: a group of R rows (R % 4 == 0 -> 16-byte aligned start and size) arrives in shared
+// memory with ONE bulk copy (cp.async.bulk, mbarrier complete_tx), warps normalise rows shared -> registers -> shared,
+// and the padded bf16 rows (pitch ldy, contiguous in global memory) leave with ONE bulk store.  No per-thread global
+// access, NS input stages in flight per CTA, several CTAs per SM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LNB_THREADS = 128;
+constexpr int LNB_STAGES = 3;
+
+// NFULL = C / 32 column slots of a lane are always inside the row (no predicate); one more slot covers the row's tail
+// and the zero pad up to ldy (< 32 * (NFULL + 1)).  The row loop is instruction-issue bound, so this matters: the
+// generic form spent more instructions on column predicates than on arithmetic.
+template <int NFULL>
+__global__ void __launch_bounds__(LNB_THREADS) pio_layernorm_bulk_kernel(const float* __restrict__ x,
+                                                                         __nv_bfloat16* __restrict__ y, int ldy,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta,
+                                                                         long long ngroups, int R, int C, int normalize,
+                                                                         float eps) {
+  extern __shared__ __align__(128) uint8_t lnb_smem[];
+  const uint32_t in_bytes = (uint32_t)R * (uint32_t)C * 4u;          // multiple of 16 (R % 4 == 0)
+  const uint32_t in_pitch = (in_bytes + 127u) & ~127u;
+  const uint32_t out_bytes = (uint32_t)R * (uint32_t)ldy * 2u;       // multiple of 16 (ldy % 8 == 0)
+  const uint32_t out_pitch = (out_bytes + 127u) & ~127u;
+  uint8_t* in_buf = lnb_smem;
+  uint8_t* out_buf = lnb_smem + LNB_STAGES * in_pitch;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_buf + 2 * out_pitch);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long my_groups = (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x;   // groups blockIdx.x + i * gridDim.x
+
+  auto issue_load = [&](long long i) {
+    const long long g = blockIdx.x + i * gridDim.x;
+    const int s = (int)(i % LNB_STAGES);
+    mbar_arrive_expect_tx(&full[s], in_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(in_buf + s * in_pitch)), "l"(reinterpret_cast<uint64_t>(x) + (uint64_t)g * in_bytes),
+                 "r"(in_bytes), "r"(smem_u32(&full[s]))
+                 : "memory");
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    for (long long i = 0; i < LNB_STAGES - 1 && i < my_groups; ++i) issue_load(i);
+  }
+  const int ct = 32 * NFULL + lane;        // this lane's tail column
+  const bool t_in = ct < C, t_out = ct < ldy;
+  float g[NFULL + 1], bt[NFULL + 1];
+#pragma unroll
+  for (int i = 0; i < NFULL; ++i) {
+    g[i] = gamma ? __ldg(gamma + lane + 32 * i) : 1.f;
+    bt[i] = beta ? __ldg(beta + lane + 32 * i) : 0.f;
+  }
+  g[NFULL] = (gamma && t_in) ? __ldg(gamma + ct) : (t_in ? 1.f : 0.f);   // pad columns: 0 * x + 0
+  bt[NFULL] = (beta && t_in) ? __ldg(beta + ct) : 0.f;
+  const float inv_c = 1.0f / (float)C;
+  for (long long it = 0; it < my_groups; ++it) {
+    const int s = (int)(it % LNB_STAGES);
+    if (tid == 0) bulk_wait_read<1>();   // the store that read out_buf[it & 1] two iterations ago has drained
+    __syncthreads();                     // ... and every warp is done with the input stage of iteration it - 1
+    if (tid == 0 && it + LNB_STAGES - 1 < my_groups) issue_load(it + LNB_STAGES - 1);
+    mbar_wait(&full[s], (uint32_t)((it / LNB_STAGES) & 1));
+    const float* in = reinterpret_cast<const float*>(in_buf + s * in_pitch);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_buf + (it & 1) * out_pitch);
+    // two rows per warp at a time (R % 4 == 0 and 4 warps: rows warp*2 + {0,1} + 8 k)
+    for (int r = warp * 2; r < R; r += 2 * (LNB_THREADS / 32)) {
+      const float* x0 = in + r * C + lane;
+      const float* x1 = x0 + C;
+      float v0[NFULL + 1], v1[NFULL + 1];
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NFULL; ++i) {
+        v0[i] = x0[32 * i];
+        v1[i] = x1[32 * i];
+        s0 += v0[i];
+        s1 += v1[i];
+      }
+      v0[NFULL] = t_in ? x0[32 * NFULL] : 0.f;
+      v1[NFULL] = t_in ? x1[32 * NFULL] : 0.f;
+      s0 += v0[NFULL];
+      s1 += v1[NFULL];
+      float mean0 = 0.f, rstd0 = 1.f, mean1 = 0.f, rstd1 = 1.f;
+      if (normalize) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        mean0 = s0 * inv_c;
+        mean1 = s1 * inv_c;
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NFULL; ++i) {
+          const float d0 = v0[i] - mean0, d1 = v1[i] - mean1;
+          q0 = fmaf(d0, d0, q0);
+          q1 = fmaf(d1, d1, q1);
+        }
+        {
+          const float d0 = t_in ? v0[NFULL] - mean0 : 0.f, d1 = t_in ? v1[NFULL] - mean1 : 0.f;
+          q0 = fmaf(d0, d0, q0);
+          q1 = fmaf(d1, d1, q1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        rstd0 = rsqrtf(q0 * inv_c + eps);
+        rstd1 = rsqrtf(q1 * inv_c + eps);
+      }
+      const float n0 = -mean0 * rstd0, n1 = -mean1 * rstd1;
+      __nv_bfloat16* y0 = out + r * ldy + lane;
+      __nv_bfloat16* y1 = y0 + ldy;
+#pragma unroll
+      for (int i = 0; i < NFULL; ++i) {
+        y0[32 * i] = __float2bfloat16_rn(fmaf(fmaf(v0[i], rstd0, n0), g[i], bt[i]));
+        y1[32 * i] = __float2bfloat16_rn(fmaf(fmaf(v1[i], rstd1, n1), g[i], bt[i]));
+      }
+      if (t_out) {   // tail of the row and the zero pad (g = bt = 0 there)
+        y0[32 * NFULL] = __float2bfloat16_rn(fmaf(fmaf(v0[NFULL], rstd0, n0), g[NFULL], bt[NFULL]));
+        y1[32 * NFULL] = __float2bfloat16_rn(fmaf(fmaf(v1[NFULL], rstd1, n1), g[NFULL], bt[NFULL]));
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const long long gidx = blockIdx.x + it * gridDim.x;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(reinterpret_cast<uint64_t>(y) + (uint64_t)gidx * out_bytes),
+                   "r"(smem_u32(out_buf + (it & 1) * out_pitch)), "r"(out_bytes)
+                   : "memory");
+      bulk_commit();
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+using lnb_kernel_t = void (*)(const float*, __nv_bfloat16*, int, const float*, const float*, long long, int, int, int, float);
+constexpr int LNB_MAX_NFULL = 36;
+template <int... I>
+static const lnb_kernel_t* lnb_kernel_table(std::integer_sequence<int, I...>) {
+  static const lnb_kernel_t table[] = {pio_layernorm_bulk_kernel<I>...};
+  return table;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -485,6 +644,19 @@ extern "C" int pio_linear_f32(const pio_linear_f32_args* a, void* stream_) {
   return PIO_OK;
 }
 
+// rows per bulk group: a multiple of 4 (16-byte granularity of the flat copy) with <= ~17 KB of fp32 per stage
+static inline int lnb_rows_per_group(int C, int ldy) {
+  (void)ldy;
+  int R = (17 * 1024 / (4 * C)) & ~3;
+  if (R > 32) R = 32;
+  return R;   // 0 when a row is wider than 4 KB + ...: the caller falls back to the scalar kernel
+}
+static inline size_t lnb_smem_bytes(int R, int C, int ldy) {
+  const size_t in_pitch = ((size_t)R * C * 4 + 127) & ~(size_t)127;
+  const size_t out_pitch = ((size_t)R * ldy * 2 + 127) & ~(size_t)127;
+  return pio::LNB_STAGES * in_pitch + 2 * out_pitch + 64;
+}
+
 extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   using namespace pio;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -501,6 +673,21 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a->y);
+  const bool bulk = !split && (a->C % 4 != 0) && a->ldx == a->C && a->ldy % 8 == 0 && a->C / 32 <= LNB_MAX_NFULL && a->ldy < 32 * (a->C / 32 + 1) + 1 && aligned16(a->x) &&
+                    aligned16(a->y) && lnb_rows_per_group(a->C, (int)a->ldy) > 0 &&
+                    a->rows >= lnb_rows_per_group(a->C, (int)a->ldy);
+  if (bulk && a->rows % lnb_rows_per_group(a->C, (int)a->ldy) != 0) {
+    // whole groups of R rows go to the bulk-DMA kernel, the (< R rows) tail to the scalar kernel
+    const long long done = a->rows / lnb_rows_per_group(a->C, (int)a->ldy) * lnb_rows_per_group(a->C, (int)a->ldy);
+    pio_layernorm_args part = *a;
+    part.rows = done;
+    rc = pio_layernorm_bf16(&part, stream_);
+    if (rc != PIO_OK) return rc;
+    part.x = a->x + done * a->ldx;
+    part.y = y + done * a->ldy;
+    part.rows = a->rows - done;
+    return pio_layernorm_bf16(&part, stream_);
+  }
   ProfileScope prof(KF_LAYERNORM, 0.0, (double)a->rows * (4.0 * a->C + 2.0 * a->ldy), stream);
   (void)seg;
   const bool vec = (a->C % 4 == 0) && (a->ldx % 4 == 0) && aligned16(a->x) && aligned16(a->y) &&
@@ -518,15 +705,45 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     else if (need <= 12) PIO_LNV_LAUNCH(12);
     else PIO_LNV_LAUNCH(16);
 #undef PIO_LNV_LAUNCH
+  } else if (bulk) {
+    // contiguous odd-width rows: bulk-DMA kernel over whole groups of R rows
+    const int R = lnb_rows_per_group(a->C, (int)a->ldy);
+    const long long ngroups = a->rows / R;
+    const size_t smem = lnb_smem_bytes(R, a->C, (int)a->ldy);
+    const int nfull = a->C / 32;
+    const lnb_kernel_t kern = lnb_kernel_table(std::make_integer_sequence<int, LNB_MAX_NFULL + 1>{})[nfull];
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+      const lnb_kernel_t* table = lnb_kernel_table(std::make_integer_sequence<int, LNB_MAX_NFULL + 1>{});
+      for (int i = 0; i <= LNB_MAX_NFULL && attr_err == cudaSuccess; ++i)
+        attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+      return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(layernorm_bulk) failed: %s", cudaGetErrorString(attr_err));
+    const int ctas_per_sm = (int)(200 * 1024 / (smem + 1024)) < 8 ? (int)(200 * 1024 / (smem + 1024)) : 8;
+    long long blocks = (long long)dev.sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+    if (blocks > ngroups) blocks = ngroups;
+    PIO_CUDA_OK(launch_kernel(kern, dim3((unsigned)blocks), dim3(LNB_THREADS), smem, stream, 1, a->x, y, (int)a->ldy,
+                              a->gamma, a->beta, ngroups, R, (int)a->C, (int)(a->normalize ? 1 : 0), a->eps));
   } else {
     const int need = (int)((seg + 31) / 32);
     const int rows_per_warp = need <= 12 ? 2 : 1;
-    const long long blocks = (a->rows + 4 * rows_per_warp - 1) / (4 * rows_per_warp);
-    PIO_REQUIRE(blocks < (1ll << 31), "pio_layernorm_bf16: too many rows");
+    const long long groups = (a->rows + rows_per_warp - 1) / rows_per_warp;
+    long long blocks = (groups + 3) / 4;
+    const long long max_blocks = (long long)dev.sm_count * 16;   // persistent-style: each warp walks many row groups
+    if (blocks > max_blocks) blocks = max_blocks;
 #define PIO_LN_LAUNCH(MAXV, ROWS)                                                                                      \
-  launch_kernel(pio_layernorm_kernel<MAXV, ROWS>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x,                 \
-                (long long)a->ldx, y, (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C,              \
-                mode, a->eps)
+  do {                                                                                                                 \
+    if (split)                                                                                                         \
+      launch_kernel(pio_layernorm_kernel<MAXV, ROWS, true>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x,      \
+                    (long long)a->ldx, y, (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C, mode,   \
+                    a->eps);                                                                                           \
+    else                                                                                                               \
+      launch_kernel(pio_layernorm_kernel<MAXV, ROWS, false>, dim3((unsigned)blocks), dim3(128), 0, stream, 1, a->x,     \
+                    (long long)a->ldx, y, (long long)a->ldy, a->gamma, a->beta, (long long)a->rows, (int)a->C, mode,   \
+                    a->eps);                                                                                           \
+  } while (0)
     if (need <= 4) PIO_LN_LAUNCH(4, 2);
     else if (need <= 12) PIO_LN_LAUNCH(12, 2);
     else if (need <= 24) PIO_LN_LAUNCH(24, 1);

@@ -14,7 +14,8 @@ def _rel(got, ref):
     return float(d / ref.double().abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("rows,c", [(1000, 261), (513, 1024), (77, 322), (300, 1280), (64, 32), (50, 1026)])
+@pytest.mark.parametrize("rows,c", [(1000, 261), (513, 1024), (77, 322), (300, 1280), (64, 32), (50, 1026), (40003, 261),
+                                    (30001, 322), (9001, 1026), (3, 261)])
 def test_layernorm_cast(rows, c):
     from perceiverio_pytorch_b200 import ops
     torch.manual_seed(0)
