@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 5
+#define PIO_ABI_VERSION 6
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -130,6 +130,15 @@ typedef struct pio_softmax_args {
   int32_t batch, rows, cols;
   float scale;
   int32_t split;    /* validation mode: P has ldp = 3 * pad8(cols) columns laid out as [hi | lo | hi] */
+  /* General attention arguments of Attention.attend (all optional, NULL = absent); no recipe of the reference passes
+   * them, they complete the operator interface:
+   *   logits = (S + bias) * scale                    (transformer_primitives.py:143-147: the bias is added BEFORE the scale)
+   *   logits[dense_mask == 0] = -1e30                (:149-156; a row with no valid entry becomes uniform)
+   *   P_f32 = softmax(logits)                        (:158, what return_matrix hands back at :177-178)
+   *   P (bf16, the operand of P.V) = P_f32, but rows with no valid entry (or row_keep == 0) are zeros (:168-175) */
+  const uint8_t* dense_mask; int64_t dm_stride_b; int64_t dm_stride_r;                  /* [batch, rows, cols] */
+  const float* bias; int64_t bias_stride_b; int64_t bias_stride_r; int64_t bias_stride_c; /* broadcast strides (elements) */
+  float* P_f32; int64_t ldpf; int64_t stridePf;                                          /* [batch, rows, cols] */
 } pio_softmax_args;
 int pio_softmax_bf16(const pio_softmax_args* a, void* stream);
 

@@ -30,12 +30,18 @@ def _build(cls, **kwargs):
     return m
 
 
-def _save(name, module, meta, inputs, output):
+ONLY = set(sys.argv[1:])   # optional: regenerate just the named fixtures
+
+
+def _save(name, module, meta, inputs, output, **extra_outputs):
+    if ONLY and name not in ONLY:
+        return
     meta = dict(meta, ctor=json.dumps(module._ctor))
     arrays = {f"param::{k}": v.detach().numpy() for k, v in module.state_dict().items()}
     arrays.update({f"input::{k}": (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
                    for k, v in inputs.items()})
     arrays["output"] = output.detach().numpy()
+    arrays.update({f"output::{k}": v.detach().numpy() for k, v in extra_outputs.items()})
     arrays.update({f"meta::{k}": np.asarray(v) for k, v in meta.items()})
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **arrays)
@@ -121,6 +127,53 @@ def main():
         qmask[0, 20:] = False
         _save("decoder_querymask", dec, dict(kind="decoder", num_heads=4, use_query_residual=0, final_project=0),
               dict(query=query, latents=lat, query_mask=qmask), dec(query, lat, query_mask=qmask))
+
+        # ---- general attention arguments (transformer_primitives.py:90, :143-144, :149-156, :177-178).  No recipe of
+        # the reference passes them, but they are part of the operator interface.  Own seeds: adding cases never
+        # changes the fixtures above.
+        # 9. bare Attention: additive bias [B,H,Nq,Nk], dense (non-outer-product) mask with a fully masked row,
+        #    return_matrix
+        torch.manual_seed(109)
+        m = ref_shim.perturb_parameters(_build(P.Attention, q_in_channels=32, k_in_channels=24, v_in_channels=24,
+                                                num_heads=4, qk_out_channels=32, v_out_channels=48,
+                                                output_channels=40), 9)
+        q, kv = torch.randn(2, 20, 32), torch.randn(2, 50, 24)
+        bias = torch.randn(2, 4, 20, 50)
+        dmask = torch.rand(2, 20, 50) > 0.3
+        dmask[0, 3, :] = False
+        dmask[1, :, 45:] = False
+        mat, out = m(q, kv, kv, attention_mask=dmask, attention_bias=bias, return_matrix=True)
+        _save("attn_bias_densemask_matrix", m, dict(kind="attention", num_heads=4, return_matrix=1),
+              dict(q=q, kv=kv, bias=bias, dense_mask=dmask), out, matrix=mat)
+
+        # 10. SelfAttention: broadcast bias [1,1,N,N] (a relative-position table), causal mask, return_matrix
+        torch.manual_seed(110)
+        m = ref_shim.perturb_parameters(_build(P.SelfAttention, in_channels=64, widening_factor=1, num_heads=4), 10)
+        x = torch.randn(2, 40, 64)
+        bias = torch.randn(1, 1, 40, 40)
+        causal = torch.tril(torch.ones(40, 40, dtype=torch.bool))[None].expand(2, 40, 40).contiguous()
+        mat, out = m(x, attention_mask=causal, attention_bias=bias, return_matrix=True)
+        _save("selfattn_bias_causal_matrix", m, dict(kind="self", num_heads=4, return_matrix=1),
+              dict(x=x, bias=bias, dense_mask=causal), out, matrix=mat)
+
+        # 11. CrossAttention: dense random mask only (single head, odd channel count), no matrix
+        torch.manual_seed(111)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=64, kv_in_channels=37, num_heads=1), 11)
+        q, kv = torch.randn(2, 24, 64), torch.randn(2, 150, 37)
+        dmask = torch.rand(2, 24, 150) > 0.5
+        dmask[1, 7, :] = False
+        _save("xattn_densemask", m, dict(kind="cross", num_heads=1, use_query_residual=1),
+              dict(q=q, kv=kv, dense_mask=dmask), m(q, kv, attention_mask=dmask))
+
+        # 12. CrossAttention: per-head bias broadcast over the batch [1,H,Nq,Nk], return_matrix, no mask
+        torch.manual_seed(112)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=48, kv_in_channels=64, num_heads=4,
+                                                qk_channels=32, v_channels=48, use_query_residual=False), 12)
+        q, kv = torch.randn(2, 30, 48), torch.randn(2, 70, 64)
+        bias = 2.0 * torch.randn(1, 4, 30, 70)
+        mat, out = m(q, kv, attention_bias=bias, return_matrix=True)
+        _save("xattn_bias_matrix", m, dict(kind="cross", num_heads=4, use_query_residual=0, return_matrix=1),
+              dict(q=q, kv=kv, bias=bias), out, matrix=mat)
 
 
 if __name__ == "__main__":

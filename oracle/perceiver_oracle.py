@@ -56,13 +56,16 @@ def gelu_erf(x: Tensor) -> Tensor:
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
-def attend(q: Tensor, k: Tensor, v: Tensor, attention_mask: Optional[Tensor] = None) -> Tensor:
+def attend(q: Tensor, k: Tensor, v: Tensor, attention_mask: Optional[Tensor] = None,
+           attention_bias: Optional[Tensor] = None, return_matrix: bool = False):
     """Multi-head attention core (transformer_primitives.py:117-180).
 
-    q [B,Nq,H,Dqk], k [B,Nk,H,Dqk], v [B,Nk,H,Dv]; mask [B,Nq,Nk] (True = attend).
-    Order of operations follows the reference: logits, then 1/sqrt(Dqk) scale (:146-147), masked
-    positions replaced by -1e30 (:149-156), softmax (:158), P@V (:163), head-major merge (:164-166)
-    and finally rows whose mask row is entirely False are forced to zero (:168-175).
+    q [B,Nq,H,Dqk], k [B,Nk,H,Dqk], v [B,Nk,H,Dv]; mask [B,Nq,Nk] (True = attend); bias broadcastable to
+    [B,H,Nq,Nk].  Order of operations follows the reference: logits, additive bias BEFORE the scale (:143-144), the
+    1/sqrt(Dqk) scale (:146-147), masked positions replaced by -1e30 (:149-156), softmax (:158), P@V (:163),
+    head-major merge (:164-166) and finally rows whose mask row is entirely False are forced to zero (:168-175).
+    With return_matrix the un-wiped probabilities [B,H,Nq,Nk] are returned first (:177-178): a fully masked row is
+    uniform there.
     """
     b, nq, h, dqk = q.shape
     dv = v.shape[-1]
@@ -70,6 +73,8 @@ def attend(q: Tensor, k: Tensor, v: Tensor, attention_mask: Optional[Tensor] = N
     kh = k.permute(0, 2, 1, 3)
     vh = v.permute(0, 2, 1, 3)
     logits = qh @ kh.transpose(-2, -1)
+    if attention_bias is not None:
+        logits = logits + attention_bias
     logits = logits * (1.0 / math.sqrt(dqk))
     if attention_mask is not None:
         m = attention_mask.to(torch.bool)[:, None, :, :]
@@ -79,11 +84,14 @@ def attend(q: Tensor, k: Tensor, v: Tensor, attention_mask: Optional[Tensor] = N
     if attention_mask is not None:
         wipe = ~(attention_mask.to(torch.bool).any(dim=2, keepdim=True))
         out = torch.where(wipe, torch.zeros((), dtype=out.dtype), out)
+    if return_matrix:
+        return probs, out
     return out
 
 
 def attention(p: Mapping[str, Tensor], prefix: str, num_heads: int, xq: Tensor, xk: Tensor, xv: Tensor,
-              attention_mask: Optional[Tensor] = None) -> Tensor:
+              attention_mask: Optional[Tensor] = None, attention_bias: Optional[Tensor] = None,
+              return_matrix: bool = False):
     """`Attention.forward` (transformer_primitives.py:90-115): q/k/v Linear, attend, final Linear."""
     q = linear(xq, p[prefix + "proj_q.weight"], p[prefix + "proj_q.bias"])
     k = linear(xk, p[prefix + "proj_k.weight"], p[prefix + "proj_k.bias"])
@@ -94,8 +102,12 @@ def attention(p: Mapping[str, Tensor], prefix: str, num_heads: int, xq: Tensor, 
     q = q.reshape(b, nq, num_heads, qk // num_heads)
     k = k.reshape(b, nk, num_heads, qk // num_heads)
     v = v.reshape(b, nk, num_heads, vc // num_heads)
-    o = attend(q, k, v, attention_mask)
-    return linear(o, p[prefix + "final.weight"], p.get(prefix + "final.bias"))
+    o = attend(q, k, v, attention_mask, attention_bias, return_matrix)
+    matrix = None
+    if return_matrix:
+        matrix, o = o
+    y = linear(o, p[prefix + "final.weight"], p.get(prefix + "final.bias"))
+    return (matrix, y) if return_matrix else y
 
 
 def mlp(p: Mapping[str, Tensor], prefix: str, x: Tensor) -> Tensor:
@@ -105,25 +117,36 @@ def mlp(p: Mapping[str, Tensor], prefix: str, x: Tensor) -> Tensor:
 
 
 def self_attention(p: Mapping[str, Tensor], prefix: str, num_heads: int, x: Tensor,
-                   attention_mask: Optional[Tensor] = None) -> Tensor:
+                   attention_mask: Optional[Tensor] = None, attention_bias: Optional[Tensor] = None,
+                   return_matrix: bool = False):
     """`SelfAttention.forward` (transformer_primitives.py:275-297)."""
     xn = layer_norm(x, p[prefix + "layer_norm1.weight"], p[prefix + "layer_norm1.bias"])
-    x = x + attention(p, prefix + "attention.", num_heads, xn, xn, xn, attention_mask)
+    a = attention(p, prefix + "attention.", num_heads, xn, xn, xn, attention_mask, attention_bias, return_matrix)
+    matrix = None
+    if return_matrix:
+        matrix, a = a
+    x = x + a
     xn2 = layer_norm(x, p[prefix + "layer_norm2.weight"], p[prefix + "layer_norm2.bias"])
-    return x + mlp(p, prefix + "mlp.", xn2)
+    y = x + mlp(p, prefix + "mlp.", xn2)
+    return (matrix, y) if return_matrix else y
 
 
 def cross_attention(p: Mapping[str, Tensor], prefix: str, num_heads: int, use_query_residual: bool,
-                    inputs_q: Tensor, inputs_kv: Tensor, attention_mask: Optional[Tensor] = None) -> Tensor:
+                    inputs_q: Tensor, inputs_kv: Tensor, attention_mask: Optional[Tensor] = None,
+                    attention_bias: Optional[Tensor] = None, return_matrix: bool = False):
     """`CrossAttention.forward` (transformer_primitives.py:371-406).
 
     The query residual uses the un-normalised queries (:396-399)."""
     kvn = layer_norm(inputs_kv, p[prefix + "layer_norm_kv.weight"], p[prefix + "layer_norm_kv.bias"])
     qn = layer_norm(inputs_q, p[prefix + "layer_norm_q.weight"], p[prefix + "layer_norm_q.bias"])
-    a = attention(p, prefix + "attention.", num_heads, qn, kvn, kvn, attention_mask)
+    a = attention(p, prefix + "attention.", num_heads, qn, kvn, kvn, attention_mask, attention_bias, return_matrix)
+    matrix = None
+    if return_matrix:
+        matrix, a = a
     x = inputs_q + a if use_query_residual else a
     xn2 = layer_norm(x, p[prefix + "layer_norm2.weight"], p[prefix + "layer_norm2.bias"])
-    return x + mlp(p, prefix + "mlp.", xn2)
+    y = x + mlp(p, prefix + "mlp.", xn2)
+    return (matrix, y) if return_matrix else y
 
 
 def encoder_latents(p: Mapping[str, Tensor], prefix: str, batch: int) -> Tensor:

@@ -49,7 +49,10 @@ class SoftmaxArgs(C.Structure):
                 ("key_mask", vp), ("stride_km", i64),
                 ("row_keep", vp), ("stride_rk", i64),
                 ("batch", i32), ("rows", i32), ("cols", i32),
-                ("scale", f32), ("split", i32)]
+                ("scale", f32), ("split", i32),
+                ("dense_mask", vp), ("dm_stride_b", i64), ("dm_stride_r", i64),
+                ("bias", vp), ("bias_stride_b", i64), ("bias_stride_r", i64), ("bias_stride_c", i64),
+                ("P_f32", vp), ("ldpf", i64), ("stridePf", i64)]
 
 
 class AttentionArgs(C.Structure):
@@ -115,7 +118,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 5:
+        if lib.pio_abi_version() != 6:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -333,16 +333,22 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   const float* s = a.S + (long long)b * a.strideS + (long long)r * a.lds;
   __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(a.P) + (long long)b * a.strideP + (long long)r * a.ldp;
   const uint8_t* km = a.key_mask ? a.key_mask + (long long)b * a.stride_km : nullptr;
+  const uint8_t* dm = a.dense_mask ? a.dense_mask + (long long)b * a.dm_stride_b + (long long)r * a.dm_stride_r : nullptr;
+  const float* bias = a.bias ? a.bias + (long long)b * a.bias_stride_b + (long long)r * a.bias_stride_r : nullptr;
+  float* pf = a.P_f32 ? a.P_f32 + (long long)b * a.stridePf + (long long)r * a.ldpf : nullptr;
   const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + r] != 0 : true;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seg = a.split ? (int)(a.ldp / 3) : (int)a.ldp;   // validation mode: [hi | lo | hi] segments
-  if (!keep) {
-    for (int c = tid; c < a.ldp; c += 256) p[c] = __float2bfloat16_rn(0.f);
-    return;
-  }
+  auto valid = [&](int c) { return (!km || km[c]) && (!dm || dm[c]); };
+  auto logit = [&](int c) {
+    float v = __ldg(s + c);
+    if (bias) v += __ldg(bias + (long long)c * a.bias_stride_c);
+    return v * a.scale;
+  };
   float m = -INFINITY;
-  for (int c = tid; c < a.cols; c += 256)
-    if (!km || km[c]) m = fmaxf(m, __ldg(s + c) * a.scale);
+  if (keep)
+    for (int c = tid; c < a.cols; c += 256)
+      if (valid(c)) m = fmaxf(m, logit(c));
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -354,13 +360,18 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   __syncthreads();
   m = bcast;
   __syncthreads();
-  if (m == -INFINITY) {  // every key masked
+  if (m == -INFINITY) {  // wiped row or every key masked: zeros for P.V (:168-175); the returned matrix is uniform,
+                         // which is what softmax makes of a row of -1e30 in the reference
     for (int c = tid; c < a.ldp; c += 256) p[c] = __float2bfloat16_rn(0.f);
+    if (pf) {
+      const float u = 1.0f / (float)a.cols;
+      for (int c = tid; c < a.cols; c += 256) pf[c] = u;
+    }
     return;
   }
   float l = 0.f;
   for (int c = tid; c < a.cols; c += 256)
-    if (!km || km[c]) l += __expf(__ldg(s + c) * a.scale - m);
+    if (valid(c)) l += __expf(logit(c) - m);
   l = warp_sum(l);
   if (lane == 0) red[warp] = l;
   __syncthreads();
@@ -373,13 +384,14 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   const float inv = bcast;
   for (int c = tid; c < seg; c += 256) {
     float o = 0.f;
-    if (c < a.cols && (!km || km[c])) o = __expf(__ldg(s + c) * a.scale - m) * inv;
+    if (c < a.cols && valid(c)) o = __expf(logit(c) - m) * inv;
     const __nv_bfloat16 hi = __float2bfloat16_rn(o);
     p[c] = hi;
     if (a.split) {
       p[seg + c] = __float2bfloat16_rn(o - __bfloat162float(hi));
       p[2 * seg + c] = hi;
     }
+    if (pf && c < a.cols) pf[c] = o;
   }
 }
 
@@ -767,7 +779,7 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
   PIO_REQUIRE(blocks < (1ll << 31), "pio_softmax_bf16: too many rows");
   {
     ProfileScope prof(KF_SOFTMAX, 0.0, (double)blocks * (4.0 * a->cols + 2.0 * a->ldp), stream);
-    const bool warp_rows = !a->split && a->ldp <= 2048 && a->lds % 4 == 0 && a->strideS % 4 == 0 && a->ldp % 4 == 0 &&
+    const bool warp_rows = !a->split && !a->dense_mask && !a->bias && !a->P_f32 && a->ldp <= 2048 && a->lds % 4 == 0 && a->strideS % 4 == 0 && a->ldp % 4 == 0 &&
                            a->strideP % 4 == 0 && aligned16(a->S) && (reinterpret_cast<uintptr_t>(a->P) & 7u) == 0;
     if (warp_rows) {
       const unsigned wblocks = (unsigned)((blocks + 7) / 8);

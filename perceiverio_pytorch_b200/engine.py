@@ -202,10 +202,29 @@ def _head_slice(t: torch.Tensor, B: int, N: int, ld: int, col0: int, d: int):
     return out, pad8(d), 0
 
 
+class GeneralAttentionArgs:
+    """The arguments of `Attention.attend` no recipe of the reference uses (transformer_primitives.py:90): a dense
+    [B, Nq, Nk] mask that is not an outer product, an additive logit bias broadcastable to [B, H, Nq, Nk], and
+    return_matrix.  They are honoured on the explicit S / P path (the softmax kernel applies them)."""
+
+    def __init__(self, *, B, H, Nq, Nk, device, attention_mask=None, attention_bias=None, return_matrix=False):
+        self.dense_mask = None
+        if attention_mask is not None:
+            if tuple(attention_mask.shape) != (B, Nq, Nk):
+                raise ValueError(f"attention_mask must be [batch, q_indices, kv_indices] = {(B, Nq, Nk)}, "
+                                 f"got {tuple(attention_mask.shape)}")
+            self.dense_mask = (attention_mask != 0).to(torch.uint8).contiguous()
+        self.bias = None
+        if attention_bias is not None:
+            self.bias = torch.broadcast_to(attention_bias.to(torch.float32), (B, H, Nq, Nk))   # stride-0 view
+        self.matrix = torch.empty((B, H, Nq, Nk), dtype=torch.float32, device=device) if return_matrix else None
+
+
 def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv, scale,
-                            key_mask, row_keep, q_bcast):
+                            key_mask, row_keep, q_bcast, general: Optional[GeneralAttentionArgs] = None):
     """Attention through explicit S and P matrices (GEMM -> softmax -> GEMM), one head at a time.  Used when the
-    streaming kernel does not cover the head sizes (d > 384: the decoders, the multimodal encoder)."""
+    streaming kernel does not cover the head sizes (d > 384: the decoders, the multimodal encoder) and for the
+    general attention arguments (dense mask / bias / return_matrix)."""
     dev = q.device
     ldo = pad8(H * dv)
     O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
@@ -218,7 +237,12 @@ def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, N
         ops.gemm(qh.view(-1)[qo:], kh.view(-1)[ko:], M=Nq, N=Nk, K=dqk, batch=B,
                  strideA=0 if q_bcast else Nq * ldqh, strideB=Nk * ldkh, lda=ldqh, ldb=ldkh,
                  out_f32=S, ldo32=lds, strideO32=Nq * lds)
-        P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)
+        if general is None:
+            P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)
+        else:
+            P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep, dense_mask=general.dense_mask,
+                                 bias=general.bias[:, h] if general.bias is not None else None,
+                                 probs_out=general.matrix[:, h] if general.matrix is not None else None)
         del S
         ldp = P.shape[-1]
         oh = O.view(-1)[h * dv:]
@@ -280,7 +304,8 @@ def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv, sm_count: int = 148) -> int:
 
 
 def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv, scale, key_mask=None,
-              row_keep=None, q_bcast=False, partial=False, num_splits=None):
+              row_keep=None, q_bcast=False, partial=False, num_splits=None,
+              general: Optional[GeneralAttentionArgs] = None):
     """Dispatch between the streaming kernel and the materialised path.  q/k/v are flat bf16 [rows, ld] matrices;
     *col give the first column of head 0.  Returns O bf16 [B, Nq, pad8(H*dv)] (or partials)."""
     same_kv = (k.data_ptr() == v.data_ptr()) and kcol == vcol and ldk == ldv and dqk == dv
@@ -288,12 +313,15 @@ def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv
                 and all((c * 2) % 16 == 0 for c in (qcol, kcol, vcol)))
     if flash_ok and not same_kv and not ((dqk + 63) // 64 <= 2 and (dv + 63) // 64 <= 3):
         flash_ok = False
+    if general is not None:
+        flash_ok = False
     if not flash_ok:
         if partial:
             raise RuntimeError("perceiverio_pytorch_b200: key-sharded attention needs head sizes covered by the "
                                f"streaming kernel (got dqk={dqk}, dv={dv})")
         return _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, B=B, H=H, Nq=Nq, Nk=Nk, dqk=dqk,
-                                       dv=dv, scale=scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast)
+                                       dv=dv, scale=scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast,
+                                       general=general)
     if num_splits is None:
         num_splits = _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv)
     qv, kv_, vv = q.view(-1)[qcol:], k.view(-1)[kcol:], v.view(-1)[vcol:]
@@ -333,7 +361,7 @@ def mlp_only(pm: PreparedMLP, x_bf16: torch.Tensor):
 
 
 def self_attention_block(pa: PreparedAttention, pm: PreparedMLP, x: torch.Tensor, ln1, ln2,
-                         key_mask=None, row_keep=None) -> torch.Tensor:
+                         key_mask=None, row_keep=None, general: Optional[GeneralAttentionArgs] = None) -> torch.Tensor:
     """SelfAttention.forward (transformer_primitives.py:275-297) on x fp32 [B, N, C] (contiguous)."""
     B, N, C = x.shape
     x2 = x.reshape(B * N, C)
@@ -342,14 +370,14 @@ def self_attention_block(pa: PreparedAttention, pm: PreparedMLP, x: torch.Tensor
     _, qkv = ops.linear(xn, C, pa.wqkv, nqkv, pa.bqkv)
     ld = pad8(nqkv)
     o = attention(qkv, ld, 0, qkv, ld, pa.QK, qkv, ld, 2 * pa.QK, B=B, H=pa.H, Nq=N, Nk=N, dqk=pa.dqk, dv=pa.dv,
-                  scale=pa.scale, key_mask=key_mask, row_keep=row_keep)
+                  scale=pa.scale, key_mask=key_mask, row_keep=row_keep, general=general)
     x1, _ = ops.linear(o.view(B * N, -1), pa.V, pa.wf, pa.O, pa.bf, residual=x2, want_f32=True, want_bf16=False)
     y, _ = mlp_block(pm, x1, ln2.weight, ln2.bias)
     return y.view(B, N, -1)
 
 
 def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep,
-                         partial=False, num_splits=None):
+                         partial=False, num_splits=None, general: Optional[GeneralAttentionArgs] = None):
     """Projection(s) + attention for a cross-attend.  qn: bf16 [(1|B)*Nq, pad8(Cq)], kvn: bf16 [B*Nk, pad8(Ck)].
     Returns the attention output O bf16 [B, Nq, ld] *before* the output projection, and its logical width."""
     if pa.folded:
@@ -361,7 +389,7 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
                       num_splits=num_splits)
         return o, pa.Ck
     _, q = ops.linear(qn, pa.Cq, pa.wq, pa.QK, pa.bq)
-    if pa.H == 1 and not partial and not _streaming_ok(1, pa.dqk, pa.dv):
+    if pa.H == 1 and not partial and general is None and not _streaming_ok(1, pa.dqk, pa.dv):
         # wide single head (the decoders: d = 512 / 1024; the multimodal encoder: 704): explicit S / P, all three
         # products K-major.  V^T [B, V, Nk] comes straight out of its projection with the operands swapped
         # (W_v as the A operand, the LayerNorm'd key/value array as B, bias per output row).
@@ -391,7 +419,7 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
         ldk, kcol, ldv, vcol = pad8(pa.QK), 0, pad8(pa.V), 0
     o = attention(q, pad8(pa.QK), 0, k, ldk, kcol, v, ldv, vcol, B=B, H=pa.H, Nq=Nq, Nk=Nk, dqk=pa.dqk, dv=pa.dv,
                   scale=pa.scale, key_mask=key_mask, row_keep=row_keep, q_bcast=q_bcast, partial=partial,
-                  num_splits=num_splits)
+                  num_splits=num_splits, general=general)
     return o, pa.V
 
 
@@ -423,7 +451,8 @@ def _as_u8(mask: Optional[torch.Tensor]):
 
 def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torch.Tensor, inputs_kv: torch.Tensor,
                           ln_q, ln_kv, ln2, *, use_query_residual: bool, key_mask=None, row_keep=None,
-                          want_bf16_out=False, shard=None, stats_out=None):
+                          want_bf16_out=False, shard=None, stats_out=None,
+                          general: Optional[GeneralAttentionArgs] = None):
     """CrossAttention.forward (transformer_primitives.py:371-406).
 
     inputs_q fp32 [B, Nq, Cq] (batch stride may be 0), inputs_kv fp32 [B, Nk, Ck].  `shard`, if given, is a
@@ -440,7 +469,11 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
         q_src = q_src.contiguous()
     qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias)
     km, rk = _as_u8(key_mask), _as_u8(row_keep)
-    if shard is None:
+    if general is not None:
+        assert shard is None and not pa.folded
+        o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
+                                        general=general)
+    elif shard is None:
         o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk)
     else:
         parts, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km,

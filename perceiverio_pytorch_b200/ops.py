@@ -118,16 +118,32 @@ def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -
 
 
 def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[torch.Tensor] = None,
-                 row_keep: Optional[torch.Tensor] = None, split: bool = False) -> torch.Tensor:
-    """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)] (split: [B, rows, 3 * pad8(cols)] as [hi | lo | hi])."""
-    _need_cuda(S, key_mask, row_keep)
+                 row_keep: Optional[torch.Tensor] = None, split: bool = False, *,
+                 dense_mask: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                 probs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """S fp32 [B, rows, lds] -> P bf16 [B, rows, pad8(cols)] (split: [B, rows, 3 * pad8(cols)] as [hi | lo | hi]).
+
+    General attention arguments: dense_mask u8 [B, rows, cols]; bias fp32 [B, rows, cols] view (any strides, 0 =
+    broadcast), added to S before the scale; probs_out fp32 [B, rows, cols] view receiving the probabilities."""
+    _need_cuda(S, key_mask, row_keep, dense_mask, bias, probs_out)
     b, rows, lds = S.shape
     ldp = pad8(cols) * (3 if split else 1)
     P = torch.empty((b, rows, ldp), dtype=BF16, device=S.device)
+    if dense_mask is not None:
+        assert dense_mask.dtype == torch.uint8 and dense_mask.shape == (b, rows, cols) and dense_mask.stride(2) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.shape == (b, rows, cols)
+    if probs_out is not None:
+        assert probs_out.dtype == torch.float32 and probs_out.shape == (b, rows, cols) and probs_out.stride(2) == 1
     a = _lib.SoftmaxArgs(_ptr(S), lds, S.stride(0), _ptr(P), ldp, P.stride(0),
                          _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
-                         b, rows, cols, scale, 1 if split else 0)
+                         b, rows, cols, scale, 1 if split else 0,
+                         _ptr(dense_mask), dense_mask.stride(0) if dense_mask is not None else 0,
+                         dense_mask.stride(1) if dense_mask is not None else 0,
+                         _ptr(bias), *(bias.stride() if bias is not None else (0, 0, 0)),
+                         _ptr(probs_out), probs_out.stride(1) if probs_out is not None else 0,
+                         probs_out.stride(0) if probs_out is not None else 0)
     _lib.check(_lib.load().pio_softmax_bf16(C.byref(a), _stream()), "pio_softmax_bf16")
     return P
 

@@ -58,20 +58,34 @@ def _factor_mask(attention_mask: Optional[torch.Tensor]):
 
     The reference wipes a row when its whole mask row is False (:168-175); for an outer-product mask that is
     `query_mask[i] == 0 or no key valid`.  Masks that are not an outer product are not produced by any caller in
-    the reference (perceiver.py:99-102, :171-175) and are rejected loudly."""
+    the reference (perceiver.py:99-102, :171-175); they return None (the caller then takes the general path)."""
     if attention_mask is None:
         return None, None
     fac = getattr(attention_mask, "_pio_factors", None)
     if fac is None:
-        m = attention_mask.to(torch.bool)
+        m = attention_mask != 0
         qm, km = m.any(dim=2), m.any(dim=1)
         if not torch.equal(qm[:, :, None] & km[:, None, :], m):
-            raise NotImplementedError("perceiverio_pytorch_b200: only outer-product attention masks "
-                                      "(make_cross_attention_mask) are supported by the sm_100a kernels")
+            return None
     else:
         qm, km = fac[0].to(torch.bool), fac[1].to(torch.bool)
     row_keep = qm & km.any(dim=1, keepdim=True)
     return row_keep, km
+
+
+def _route_mask(attention_mask, attention_bias, return_matrix, *, B, H, Nq, Nk, device):
+    """Decide between the factored fast path and the general path of `Attention.attend`.
+
+    Returns (row_keep, key_mask, general): general is None on the fast path (no bias, no return_matrix, and the mask
+    — if any — is an outer product), otherwise an engine.GeneralAttentionArgs carrying the dense mask / bias /
+    matrix buffer (and row_keep / key_mask are None: the dense mask subsumes them)."""
+    if attention_bias is None and not return_matrix:
+        fac = _factor_mask(attention_mask)
+        if fac is not None:
+            return fac[0], fac[1], None
+    return None, None, engine.GeneralAttentionArgs(B=B, H=H, Nq=Nq, Nk=Nk, device=device,
+                                                   attention_mask=attention_mask, attention_bias=attention_bias,
+                                                   return_matrix=return_matrix)
 
 
 def _check_inference(module: nn.Module, *probs):
@@ -116,17 +130,17 @@ class Attention(nn.Module):
         nn.init.constant_(self.final.bias, 0)
 
     def forward(self, inputs_q, inputs_k, inputs_v, attention_mask=None, attention_bias=None, return_matrix=False):
-        if attention_bias is not None or return_matrix:
-            raise NotImplementedError("attention_bias / return_matrix are not used by any reference recipe and are "
-                                      "not implemented by the sm_100a kernels")
         _check_inference(self, self._dropout_prob)
+        ops._need_cuda(inputs_q, inputs_k, inputs_v)
         B, Nq, Cq = inputs_q.shape
         Nk = inputs_k.shape[1]
         pa = engine.prepared(self, "plain", lambda: engine.PreparedAttention(self, self_attention=False,
                                                                              allow_fold=False))
-        row_keep, key_mask = _factor_mask(attention_mask)
+        row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix, B=B, H=pa.H, Nq=Nq,
+                                                  Nk=Nk, device=inputs_q.device)
         if engine.PRECISION == "bf16x3":
-            return validate.attention_module(self, inputs_q, inputs_k, inputs_v, key_mask, row_keep)
+            y = validate.attention_module(self, inputs_q, inputs_k, inputs_v, key_mask, row_keep, general)
+            return (general.matrix, y) if return_matrix else y
         qn = ops.layernorm_bf16(inputs_q.contiguous().view(B * Nq, Cq), None, None, normalize=False)
         kn = ops.layernorm_bf16(inputs_k.contiguous().view(B * Nk, -1), None, None, normalize=False)
         _, q = ops.linear(qn, pa.Cq, pa.wq, pa.QK, pa.bq)
@@ -148,9 +162,10 @@ class Attention(nn.Module):
             ldk, kcol, ldv, vcol = ops.pad8(pa.QK), 0, ops.pad8(pa.V), 0
         o = engine.attention(q, ops.pad8(pa.QK), 0, k, ldk, kcol, v, ldv, vcol, B=B, H=pa.H, Nq=Nq, Nk=Nk,
                              dqk=pa.dqk, dv=pa.dv, scale=pa.scale, key_mask=engine._as_u8(key_mask),
-                             row_keep=engine._as_u8(row_keep))
+                             row_keep=engine._as_u8(row_keep), general=general)
         y, _ = ops.linear(o.view(B * Nq, -1), pa.V, pa.wf, pa.O, pa.bf, want_f32=True, want_bf16=False)
-        return y.contiguous().view(B, Nq, -1)
+        y = y.contiguous().view(B, Nq, -1)
+        return (general.matrix, y) if return_matrix else y
 
 
 class MLP(nn.Module):
@@ -202,22 +217,24 @@ class SelfAttention(nn.Module):
         self.dropout = nn.Dropout(dropout_prob)
 
     def forward(self, inputs, *, attention_mask=None, attention_bias=None, return_matrix: bool = False):
-        if attention_bias is not None or return_matrix:
-            raise NotImplementedError("attention_bias / return_matrix are not implemented by the sm_100a kernels")
         _check_inference(self, *self._dropout_probs)
+        ops._need_cuda(inputs)
+        B, N, _ = inputs.shape
+        row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix, B=B,
+                                                  H=self.attention._num_heads, Nq=N, Nk=N, device=inputs.device)
         if engine.PRECISION == "bf16x3":
-            ops._need_cuda(inputs)
-            row_keep, key_mask = _factor_mask(attention_mask)
-            return validate.self_attention_block(self, inputs.contiguous(), key_mask, row_keep)
+            y = validate.self_attention_block(self, inputs.contiguous(), key_mask, row_keep, general)
+            return (general.matrix, y) if return_matrix else y
         pa = engine.prepared(self.attention, "self", lambda: engine.PreparedAttention(self.attention,
                                                                                      self_attention=True,
                                                                                      allow_fold=False))
         pm = engine.prepared(self.mlp, "mlp", lambda: engine.PreparedMLP(self.mlp))
-        row_keep, key_mask = _factor_mask(attention_mask)
         x = inputs if inputs.is_contiguous() else inputs.contiguous()
         y = engine.self_attention_block(pa, pm, x, self.layer_norm1, self.layer_norm2,
-                                        key_mask=engine._as_u8(key_mask), row_keep=engine._as_u8(row_keep))
-        return y if y.is_contiguous() else y.contiguous()
+                                        key_mask=engine._as_u8(key_mask), row_keep=engine._as_u8(row_keep),
+                                        general=general)
+        y = y if y.is_contiguous() else y.contiguous()
+        return (general.matrix, y) if return_matrix else y
 
 
 class CrossAttention(nn.Module):
@@ -253,25 +270,33 @@ class CrossAttention(nn.Module):
         self.dropout = nn.Dropout(dropout_prob)
 
     def forward(self, inputs_q, inputs_kv, *, attention_mask=None, attention_bias=None, return_matrix: bool = False):
-        if attention_bias is not None or return_matrix:
-            raise NotImplementedError("attention_bias / return_matrix are not implemented by the sm_100a kernels")
-        row_keep, key_mask = _factor_mask(attention_mask)
-        y, _ = self._forward_factored(inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep)
-        return y if y.is_contiguous() else y.contiguous()   # odd widths are carried with a 16-byte row pitch inside
+        ops._need_cuda(inputs_q, inputs_kv)
+        row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix,
+                                                  B=inputs_q.shape[0], H=self.attention._num_heads,
+                                                  Nq=inputs_q.shape[1], Nk=inputs_kv.shape[1], device=inputs_q.device)
+        y, _ = self._forward_factored(inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep, general=general)
+        y = y if y.is_contiguous() else y.contiguous()   # odd widths are carried with a 16-byte row pitch inside
+        return (general.matrix, y) if return_matrix else y
 
     def _forward_factored(self, inputs_q, inputs_kv, *, key_mask=None, row_keep=None, want_bf16_out=False,
-                          shard=None, stats_out=None):
+                          shard=None, stats_out=None, general=None):
         _check_inference(self, *self._dropout_probs)
         if engine.PRECISION == "bf16x3":
             ops._need_cuda(inputs_q, inputs_kv)
             if shard is not None:
                 raise RuntimeError("perceiverio_pytorch_b200: the validation precision runs unsharded")
-            return validate.cross_attention_block(self, inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep), None
-        pa = engine.prepared(self.attention, "cross", lambda: engine.PreparedAttention(self.attention,
-                                                                                      self_attention=False,
-                                                                                      allow_fold=True))
+            return validate.cross_attention_block(self, inputs_q, inputs_kv, key_mask=key_mask, row_keep=row_keep,
+                                                  general=general), None
+        if general is not None:   # explicit S / P path: no K/V folding
+            pa = engine.prepared(self.attention, "plain", lambda: engine.PreparedAttention(self.attention,
+                                                                                          self_attention=False,
+                                                                                          allow_fold=False))
+        else:
+            pa = engine.prepared(self.attention, "cross", lambda: engine.PreparedAttention(self.attention,
+                                                                                          self_attention=False,
+                                                                                          allow_fold=True))
         pm = engine.prepared(self.mlp, "mlp", lambda: engine.PreparedMLP(self.mlp))
         return engine.cross_attention_block(pa, pm, inputs_q, inputs_kv, self.layer_norm_q, self.layer_norm_kv,
                                             self.layer_norm2, use_query_residual=self._use_query_residual,
                                             key_mask=key_mask, row_keep=row_keep, want_bf16_out=want_bf16_out,
-                                            shard=shard, stats_out=stats_out)
+                                            shard=shard, stats_out=stats_out, general=general)

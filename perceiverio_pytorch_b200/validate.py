@@ -58,8 +58,9 @@ def linear(x: torch.Tensor, wt: Weights, *, ln=None, act: int = 0, residual: Opt
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B, H, Nq, Nk, dqk, dv, scale,
-              key_mask=None, row_keep=None, q_bcast=False) -> torch.Tensor:
-    """q fp32 [(1|B)*Nq, H*dqk], k [B*Nk, H*dqk], v [B*Nk, H*dv] -> fp32 [B*Nq, H*dv] (heads merged head-major)."""
+              key_mask=None, row_keep=None, q_bcast=False, general=None) -> torch.Tensor:
+    """q fp32 [(1|B)*Nq, H*dqk], k [B*Nk, H*dqk], v [B*Nk, H*dv] -> fp32 [B*Nq, H*dv] (heads merged head-major).
+    `general`: engine.GeneralAttentionArgs (dense mask / additive bias / probabilities out), applied by the softmax."""
     dev = q.device
     o = torch.empty((B * Nq, H * dv), dtype=torch.float32, device=dev)
     dqp, dvp, nkp = pad8(dqk), pad8(dv), pad8(Nk)
@@ -71,7 +72,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B, H, Nq, Nk
         S = torch.empty((B, Nq, lds), dtype=torch.float32, device=dev)
         ops.gemm(qa, kb, M=Nq, N=Nk, K=3 * dqp, batch=B, strideA=0 if q_bcast else Nq * 3 * dqp, strideB=Nk * 3 * dqp,
                  lda=3 * dqp, ldb=3 * dqp, out_f32=S, ldo32=lds, strideO32=Nq * lds)
-        P3 = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep, split=True)                            # [hi | lo | hi]
+        if general is None:
+            P3 = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep, split=True)                        # [hi | lo | hi]
+        else:
+            P3 = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep, split=True, dense_mask=general.dense_mask,
+                                  bias=general.bias[:, h] if general.bias is not None else None,
+                                  probs_out=general.matrix[:, h] if general.matrix is not None else None)
         del S
         oh = o.view(-1)[h * dv:]
         ldo = H * dv
@@ -108,7 +114,7 @@ def _u8(mask):
     return None if mask is None else mask.to(torch.uint8).contiguous()
 
 
-def self_attention_block(mod, x: torch.Tensor, key_mask=None, row_keep=None) -> torch.Tensor:
+def self_attention_block(mod, x: torch.Tensor, key_mask=None, row_keep=None, general=None) -> torch.Tensor:
     """SelfAttention.forward (transformer_primitives.py:275-297) on x fp32 [B, N, C]."""
     pa = _prepared(mod.attention, "v_att", lambda: _Att(mod.attention))
     pm = _prepared(mod.mlp, "v_mlp", lambda: _Mlp(mod.mlp))
@@ -118,14 +124,15 @@ def self_attention_block(mod, x: torch.Tensor, key_mask=None, row_keep=None) -> 
     k = linear(x2, pa.k, ln=mod.layer_norm1)
     v = linear(x2, pa.v, ln=mod.layer_norm1)
     o = attention(q, k, v, B=B, H=pa.H, Nq=N, Nk=N, dqk=pa.dqk, dv=pa.dv, scale=pa.scale,
-                  key_mask=_u8(key_mask), row_keep=_u8(row_keep))
+                  key_mask=_u8(key_mask), row_keep=_u8(row_keep), general=general)
     x1 = linear(o, pa.f, residual=x2)
     h = linear(x1, pm.fc1, ln=mod.layer_norm2, act=1)
     y = linear(h, pm.fc2, residual=x1)
     return y.view(B, N, -1)
 
 
-def cross_attention_block(mod, inputs_q: torch.Tensor, inputs_kv: torch.Tensor, *, key_mask=None, row_keep=None):
+def cross_attention_block(mod, inputs_q: torch.Tensor, inputs_kv: torch.Tensor, *, key_mask=None, row_keep=None,
+                          general=None):
     """CrossAttention.forward (transformer_primitives.py:371-406): fp32 [B, Nq, Cq] x [B, Nk, Ck] -> fp32 [B, Nq, Cq]."""
     pa = _prepared(mod.attention, "v_att", lambda: _Att(mod.attention))
     pm = _prepared(mod.mlp, "v_mlp", lambda: _Mlp(mod.mlp))
@@ -140,7 +147,7 @@ def cross_attention_block(mod, inputs_q: torch.Tensor, inputs_kv: torch.Tensor, 
     k = linear(kv2, pa.k, ln=mod.layer_norm_kv)
     v = linear(kv2, pa.v, ln=mod.layer_norm_kv)
     o = attention(q, k, v, B=B, H=pa.H, Nq=Nq, Nk=Nk, dqk=pa.dqk, dv=pa.dv, scale=pa.scale,
-                  key_mask=_u8(key_mask), row_keep=_u8(row_keep), q_bcast=q_bcast)
+                  key_mask=_u8(key_mask), row_keep=_u8(row_keep), q_bcast=q_bcast, general=general)
     res = None
     if mod._use_query_residual:
         res = inputs_q.expand(B, Nq, Cq).contiguous().view(B * Nq, Cq)
@@ -150,7 +157,7 @@ def cross_attention_block(mod, inputs_q: torch.Tensor, inputs_kv: torch.Tensor, 
     return y.view(B, Nq, -1)
 
 
-def attention_module(mod, inputs_q, inputs_k, inputs_v, key_mask=None, row_keep=None):
+def attention_module(mod, inputs_q, inputs_k, inputs_v, key_mask=None, row_keep=None, general=None):
     """Bare Attention.forward (transformer_primitives.py:90-115)."""
     pa = _prepared(mod, "v_att", lambda: _Att(mod))
     B, Nq, _ = inputs_q.shape
@@ -159,7 +166,7 @@ def attention_module(mod, inputs_q, inputs_k, inputs_v, key_mask=None, row_keep=
     k = linear(inputs_k.contiguous().view(B * Nk, -1), pa.k)
     v = linear(inputs_v.contiguous().view(B * Nk, -1), pa.v)
     o = attention(q, k, v, B=B, H=pa.H, Nq=Nq, Nk=Nk, dqk=pa.dqk, dv=pa.dv, scale=pa.scale,
-                  key_mask=_u8(key_mask), row_keep=_u8(row_keep))
+                  key_mask=_u8(key_mask), row_keep=_u8(row_keep), general=general)
     return linear(o, pa.f).view(B, Nq, -1)
 
 

@@ -20,22 +20,32 @@ def load_golden(name):
     return params, inputs, meta, torch.from_numpy(z["output"])
 
 
+def load_golden_matrix(name):
+    """The attention matrix of a return_matrix fixture ([B,H,Nq,Nk] probabilities), or None."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return torch.from_numpy(z["output::matrix"]) if "output::matrix" in z.files else None
+
+
 def run_oracle(params, inputs, meta, dtype=torch.float32):
-    """Evaluate a golden case with the CPU oracle."""
+    """Evaluate a golden case with the CPU oracle.  Fixtures with meta return_matrix yield (matrix, output)."""
     from oracle import perceiver_oracle as O
     p = {k: v.to(dtype) if v.is_floating_point() else v for k, v in params.items()}
     x = {k: v.to(dtype) if v.is_floating_point() else v for k, v in inputs.items()}
     kind = meta["kind"]
+    general = dict(attention_bias=x.get("bias"), return_matrix=bool(meta.get("return_matrix", 0)))
+    if kind == "attention":
+        return O.attention(p, "", meta["num_heads"], x["q"], x["kv"], x["kv"], x.get("dense_mask"), **general)
     if kind == "cross":
-        mask = None
+        mask = x.get("dense_mask")
         b, nq, nk = x["q"].shape[0], x["q"].shape[1], x["kv"].shape[1]
         if "key_mask" in x:
             mask = O.make_cross_attention_mask(torch.ones(b, nq, dtype=torch.bool), x["key_mask"])
         if "query_mask" in x:
             mask = O.make_cross_attention_mask(x["query_mask"], torch.ones(b, nk, dtype=torch.bool))
-        return O.cross_attention(p, "", meta["num_heads"], bool(meta["use_query_residual"]), x["q"], x["kv"], mask)
+        return O.cross_attention(p, "", meta["num_heads"], bool(meta["use_query_residual"]), x["q"], x["kv"], mask,
+                                 **general)
     if kind == "self":
-        return O.self_attention(p, "", meta["num_heads"], x["x"])
+        return O.self_attention(p, "", meta["num_heads"], x["x"], x.get("dense_mask"), **general)
     if kind == "encoder":
         return O.encoder_forward(p, "", num_blocks=meta["num_blocks"],
                                  num_self_attends_per_block=meta["num_self_attends_per_block"],

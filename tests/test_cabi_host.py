@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.pio_abi_version() == 5
+    assert lib.pio_abi_version() == 6
 
 
 @pytest.mark.parametrize("struct,cname", [("LayerNormArgs", "pio_layernorm_args"), ("GemmArgs", "pio_gemm_args"),
@@ -157,9 +157,18 @@ def test_mask_helper_matches_reference_semantics():
     dense = m.clone()  # no attached factors: must be recovered from the dense matrix
     rk, k2 = _factor_mask(dense)
     assert torch.equal(k2, km) and torch.equal(rk, qm)
-    dense[0, 0, 2] = True  # no longer an outer product
-    with pytest.raises(NotImplementedError):
-        _factor_mask(dense)
+    dense[0, 0, 2] = True  # no longer an outer product: not factorable, routed to the general (dense-mask) path
+    assert _factor_mask(dense) is None
+    from perceiverio_pytorch_b200.primitives import _route_mask
+    rk, k2, general = _route_mask(dense, None, False, B=1, H=2, Nq=3, Nk=4, device="cpu")
+    assert rk is None and k2 is None and general.dense_mask.dtype == torch.uint8
+    assert torch.equal(general.dense_mask.bool(), dense) and general.bias is None and general.matrix is None
+    # an additive bias is carried as a stride-0 broadcast view; return_matrix allocates [B, H, Nq, Nk]
+    rk, k2, general = _route_mask(m, torch.zeros(1, 1, 3, 4), True, B=1, H=2, Nq=3, Nk=4, device="cpu")
+    assert general.bias.shape == (1, 2, 3, 4) and general.bias.stride(1) == 0
+    assert general.matrix.shape == (1, 2, 3, 4)
+    rk, k2, general = _route_mask(m, None, False, B=1, H=2, Nq=3, Nk=4, device="cpu")
+    assert general is None and torch.equal(k2, km)
 
 
 def test_swap_hot_path_on_live_reference_keeps_state_dict():

@@ -5,7 +5,7 @@ import json
 import pytest
 import torch
 
-from golden_util import golden_names, load_golden, rel_err, run_oracle
+from golden_util import golden_names, load_golden, load_golden_matrix, rel_err, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -27,17 +27,24 @@ def _run_ours(module, inputs, meta):
     import perceiverio_pytorch_b200 as pio
     x = {k: v.cuda() for k, v in inputs.items()}
     kind = meta["kind"]
+    general = {}
+    if "bias" in x:
+        general["attention_bias"] = x["bias"]
+    if meta.get("return_matrix", 0):
+        general["return_matrix"] = True
     with torch.inference_mode():
+        if kind == "attention":
+            return module(x["q"], x["kv"], x["kv"], attention_mask=x.get("dense_mask"), **general)
         if kind == "cross":
             b, nq, nk = x["q"].shape[0], x["q"].shape[1], x["kv"].shape[1]
-            mask = None
+            mask = x.get("dense_mask")
             if "key_mask" in x:
                 mask = pio.make_cross_attention_mask(torch.ones(b, nq, dtype=torch.bool, device="cuda"), x["key_mask"])
             if "query_mask" in x:
                 mask = pio.make_cross_attention_mask(x["query_mask"], torch.ones(b, nk, dtype=torch.bool, device="cuda"))
-            return module(x["q"], x["kv"], attention_mask=mask)
+            return module(x["q"], x["kv"], attention_mask=mask, **general)
         if kind == "self":
-            return module(x["x"])
+            return module(x["x"], attention_mask=x.get("dense_mask"), **general)
         if kind == "encoder":
             return module(x["inputs"], module.latents(x["inputs"]), input_mask=x.get("input_mask"))
         if kind == "decoder":
@@ -51,7 +58,16 @@ def test_cuda_path_matches_reference_golden(name):
     m = _build_ours(meta)
     m.load_state_dict(params, strict=True)
     m = m.cuda()
-    got = _run_ours(m, inputs, meta).float().cpu()
+    got = _run_ours(m, inputs, meta)
+    expected_matrix = load_golden_matrix(name)
+    if expected_matrix is not None:     # return_matrix fixtures: (probabilities [B,H,Nq,Nk], block output)
+        matrix, got = got
+        matrix = matrix.float().cpu()
+        assert matrix.shape == expected_matrix.shape
+        # probabilities are compared absolutely (they live in [0, 1]; bf16 operand rounding moves logits by ~1e-2)
+        assert float((matrix - expected_matrix).abs().max()) <= 2e-2, name
+        assert float((matrix.sum(-1) - 1).abs().max()) <= 1e-4
+    got = got.float().cpu()
     assert got.shape == expected.shape
     emax, el2 = rel_err(got, expected)
     assert emax <= CASE_TOL.get(name, BF16_TOL), (name, emax, el2)

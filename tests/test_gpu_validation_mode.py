@@ -5,7 +5,7 @@ import json
 import pytest
 import torch
 
-from golden_util import golden_names, load_golden, rel_err
+from golden_util import golden_names, load_golden, load_golden_matrix, rel_err
 from test_gpu_parity import CONFIGS, _build_ours, _oracle_enc_dec, _perturb, _run_ours
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,12 @@ def test_validation_mode_matches_reference_golden(name):
     m = _build_ours(meta)
     m.load_state_dict(params, strict=True)
     m = m.cuda()
-    got = _run_ours(m, inputs, meta).float().cpu()
+    got = _run_ours(m, inputs, meta)
+    expected_matrix = load_golden_matrix(name)
+    if expected_matrix is not None:
+        matrix, got = got
+        assert float((matrix.float().cpu() - expected_matrix).abs().max()) <= VAL_TOL, name
+    got = got.float().cpu()
     emax, el2 = rel_err(got, expected)
     print(f"{name}: max {emax:.3e} l2 {el2:.3e}")
     assert emax <= CASE_TOL.get(name, VAL_TOL), (name, emax, el2)
