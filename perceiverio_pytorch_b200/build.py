@@ -19,7 +19,7 @@ SOURCES = ["pio_host.cu", "pio_simt.cu", "pio_gemm.cu", "pio_gemm2.cu", "pio_fla
 HEADERS = ["pio_common.cuh", "pio_host.h", os.path.join("..", "..", "include", "pio_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"] + os.environ.get("PIO_NVCC_EXTRA", "").split()
 
 
 def _stale() -> bool:

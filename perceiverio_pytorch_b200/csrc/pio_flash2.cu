@@ -23,6 +23,23 @@
 
 namespace pio {
 
+// Developer aid (compiled out unless -DPIO_FLASH2_TRACE): CTA 0 records (tag, clock64) pairs at the pipeline's
+// hand-off points; the first launch prints them to stderr.  Tags: 1xx MMA issuer, 2xx softmax A, 3xx softmax B.
+#ifdef PIO_FLASH2_TRACE
+// fire-and-forget stores into a per-warp slice (no atomics: a returning atomic would stall the traced warp)
+__device__ unsigned long long g_f2_trace[12 * 2 * 512];
+#define F2T(tag)                                                                        \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && lane == 0 && f2n < 512) {                                    \
+      g_f2_trace[(warp * 512 + f2n) * 2] = (unsigned long long)(tag);                   \
+      g_f2_trace[(warp * 512 + f2n) * 2 + 1] = (unsigned long long)clock64();           \
+      ++f2n;                                                                            \
+    }                                                                                   \
+  } while (0)
+#else
+#define F2T(tag)
+#endif
+
 struct Flash2Params {
   int B, H, Nq, Nk, dqk, dv;
   int q_bcast;
@@ -33,12 +50,14 @@ struct Flash2Params {
   int q_pairs;    // ceil(Nq / 256)
   int items;      // B * H * q_pairs
   int kv_tiles;   // ceil(Nk / BN)
+  int staged;     // epilogue through shared memory + TMA store (see the epilogue)
 };
 
 template <int NQC, int NVC, int BN>
 struct Flash2Cfg {
   static constexpr int Q_TILE_BYTES = NQC * 16384;            // 128 rows x 64-column chunks
-  static constexpr int Q_BYTES = 2 * Q_TILE_BYTES;
+  static constexpr int Q_SLOTS = 3;                           // tile t of this CTA (t = 2 * item + x) lives in slot t % 3
+  static constexpr int Q_BYTES = Q_SLOTS * Q_TILE_BYTES;
   static constexpr int CHUNK_BYTES = BN * 128;                // one 64-column chunk of a K or V tile
   static constexpr int K_BYTES = NQC * CHUNK_BYTES;
   static constexpr int V_BYTES = NVC * CHUNK_BYTES;
@@ -57,28 +76,35 @@ struct Flash2Cfg {
 template <int NQC, int NVC, int BN>
 __global__ void __launch_bounds__(384, 1)
 pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                  const __grid_constant__ CUtensorMap tmap_v, const Flash2Params p) {
+                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                  const Flash2Params p) {
   using Cfg = Flash2Cfg<NQC, NVC, BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                   // [2 tiles][NQC chunks][128 x 128 B]
+  uint8_t* sQ = smem;                                   // [3 slots][NQC chunks][128 x 128 B]
   uint8_t* sK = sQ + Cfg::Q_BYTES;                      // [STAGES][NQC][BN x 128 B]
   uint8_t* sV = sK + STAGES * Cfg::K_BYTES;             // [STAGES][NVC][BN x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * Cfg::V_BYTES);
-  uint64_t* q_full = bars;                              // TMA -> MMA
-  uint64_t* q_empty = bars + 1;                         // MMA (last S of the item retired) -> TMA
-  uint64_t* k_full = bars + 2;                          // [STAGES]
+  uint64_t* q_full = bars;                              // [3]  TMA -> MMA, one per Q slot
+  uint64_t* q_empty = bars + 3;                         // [3]  MMA (last S of the tile retired) -> TMA
+  uint64_t* k_full = bars + 6;                          // [STAGES]
   uint64_t* k_empty = k_full + STAGES;
   uint64_t* v_full = k_empty + STAGES;
   uint64_t* v_empty = v_full + STAGES;
   uint64_t* s_full = v_empty + STAGES;                  // [2]  S_X ready                  (MMA -> softmax X)
-  uint64_t* p_full = s_full + 2;                        // [2]  P_X in TMEM, O_X rescaled  (softmax X -> MMA), 128 arrivals
-  uint64_t* pv_done = p_full + 2;                       // [2]  O_X += P_X V retired        (MMA -> softmax X)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* p_full = s_full + 2;                        // [2 tiles][2 halves]  P_X (one half of the key tile) in TMEM, O_X
+                                                        //      rescaled  (softmax X -> MMA), 128 arrivals each
+  uint64_t* pv_done = p_full + 4;                       // [2]  O_X += P_X V retired        (MMA -> softmax X)
+  uint64_t* o_ready = pv_done + 2;                      // [2]  staged output tile X is in shared memory (softmax X -> warp 3)
+  uint64_t* epi_done = o_ready + 2;                     // [2]  ... and has left it again          (warp 3 -> TMA producer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 2);
 
   // the shuffle makes the warp index provably warp-uniform, so role code can use the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+#ifdef PIO_FLASH2_TRACE
+  int f2n = 0;
+#endif
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_flash2_kernel: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
@@ -87,10 +113,13 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int s = 0; s < Cfg::Q_SLOTS; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -99,8 +128,11 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[2 * i], 128);
+      mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&o_ready[i], 128);
+      mbar_init(&epi_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -127,39 +159,64 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // ================= TMA producer =================
       // (all 32 lanes run the schedule so that addresses / coordinates stay in uniform registers; one lane issues)
       const bool leader = (lane == 0);
+      // Q tile t = 2 * it + x of this CTA goes to slot t % 3: tile A of the NEXT item is prefetched a whole item ahead
+      // and tile B as soon as the slot of the previous item's tile A is released, so an item never starts with a Q wait.
+      // Program order follows the order in which the MMA warp releases things (S_B(T-2), S_A(T-1), PV_B(T-2),
+      // S_B(T-1), PV_B(T-1) of the previous item), so no wait here delays a load that could already go.
+      auto load_q = [&](int item, int it_, int x) {
+        const int qp = item % p.q_pairs;
+        const int bh = item / p.q_pairs;
+        const int h = bh % p.H, b = bh / p.H;
+        const uint32_t t = 2u * (uint32_t)it_ + (uint32_t)x;
+        const int slot = (int)(t % 3u);
+        F2T(440 + x);
+        mbar_wait(&q_empty[slot], ((t / 3u) & 1u) ^ 1u);
+        F2T(450 + x);
+        if (leader) {
+          mbar_arrive_expect_tx(&q_full[slot], Cfg::Q_TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < NQC; ++c)
+            tma_load_3d(sQ + (slot * NQC + c) * 16384, &tmap_q, &q_full[slot], h * p.dqk + c * 64, qp * 256 + x * 128,
+                        p.q_bcast ? 0 : b);
+        }
+      };
       uint32_t kv = 0;
       int it = 0;
+      if ((int)blockIdx.x < p.items) load_q(blockIdx.x, 0, 0);
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int qp = item % p.q_pairs;
         const int bh = item / p.q_pairs;
         const int h = bh % p.H, b = bh / p.H;
-        mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1u);
-        if (leader) {
-          mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-#pragma unroll
-          for (int x = 0; x < 2; ++x)
-#pragma unroll
-            for (int c = 0; c < NQC; ++c)
-              tma_load_3d(sQ + (x * NQC + c) * 16384, &tmap_q, q_full, h * p.dqk + c * 64, qp * 256 + x * 128,
-                          p.q_bcast ? 0 : b);
-        }
+        (void)qp;
+        const int jq = T > 1 ? 1 : 0;   // the next item's tile A is requested after this key tile
         for (int j = 0; j < T; ++j, ++kv) {
           const int stage = kv % STAGES;
           const uint32_t ph = (kv / STAGES) & 1u;
+          F2T(400 + j);
+          // staged epilogue: tile A of the previous item parked its output in the K stage of that item's last key tile
+          // (= this stage when j == STAGES - 1), tile B in the V stage
+          const bool after_epilogue = p.staged && it > 0 && j == STAGES - 1;
+          if (after_epilogue) mbar_wait(&epi_done[0], (uint32_t)(it - 1) & 1u);
           mbar_wait(&k_empty[stage], ph ^ 1u);
+          F2T(410 + j);
           if (leader) {
             mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
 #pragma unroll
             for (int c = 0; c < NQC; ++c)
               tma_load_3d(sK + (stage * NQC + c) * Cfg::CHUNK_BYTES, &tmap_k, &k_full[stage], h * p.dqk + c * 64, j * BN, b);
           }
+          if (j == 0) load_q(item, it, 1);
+          F2T(420 + j);
+          if (after_epilogue) mbar_wait(&epi_done[1], (uint32_t)(it - 1) & 1u);
           mbar_wait(&v_empty[stage], ph ^ 1u);
+          F2T(430 + j);
           if (leader) {
             mbar_arrive_expect_tx(&v_full[stage], Cfg::V_BYTES);
 #pragma unroll
             for (int c = 0; c < NVC; ++c)
               tma_load_3d(sV + (stage * NVC + c) * Cfg::CHUNK_BYTES, &tmap_v, &v_full[stage], h * p.dv + c * 64, j * BN, b);
           }
+          if (j == jq && item + (int)gridDim.x < p.items) load_q(item + gridDim.x, it + 1, 0);
         }
       }
     }
@@ -179,9 +236,9 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const uint32_t q_lo = (uint32_t)dq0, q_hi = (uint32_t)(dq0 >> 32);
       const uint32_t k_lo = (uint32_t)dk0, k_hi = (uint32_t)(dk0 >> 32);
       const uint32_t v_lo = (uint32_t)dv0, v_hi = (uint32_t)(dv0 >> 32);
-      auto issue_s = [&](int x, int stage) {
+      auto issue_s = [&](int x, int stage, int qslot) {
         const uint32_t d = tmem_base + x * BN;
-        const uint32_t a0 = q_lo + (uint32_t)((x * Cfg::Q_TILE_BYTES) >> 4);
+        const uint32_t a0 = q_lo + (uint32_t)((qslot * Cfg::Q_TILE_BYTES) >> 4);
         const uint32_t b0 = k_lo + (uint32_t)((stage * Cfg::K_BYTES) >> 4);
         if (dqk_steps == 4 * NQC) {   // full-width heads: no per-instruction bound check in the issue stream
 #pragma unroll
@@ -203,63 +260,95 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       };
-      auto issue_pv = [&](int x, int stage, bool accum) {
+      // P_x reaches the tensor pipe in two halves of BN / 2 keys: the PV MMAs of the first half run while the softmax
+      // warps still exponentiate the second half (the chain S -> softmax -> PV -> S' of a tile is what bounds a step)
+      auto issue_pv = [&](int x, int stage, bool accum, int half) {
         const uint32_t a = tmem_base + x * BN;          // P_x overlays the first BN/2 columns of S_x
         const uint32_t d = tmem_o + x * (NVC * 64);
         const uint32_t b0 = v_lo + (uint32_t)((stage * Cfg::V_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {
+        for (int k2 = 0; k2 < BN / 32; ++k2) {
+          const int ks = half * (BN / 32) + k2;
           if (elect_one())
             umma_ts_lh(d, a + ks * 8, b0 + (uint32_t)((ks * 2048) >> 4), v_hi, idesc_pv, (accum || ks != 0) ? 1u : 0u);
         }
       };
-      uint32_t kv = 0;
-      uint32_t pcount[2] = {0, 0};
-      int it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        mbar_wait(q_full, (uint32_t)(it & 1));
-        {
-          const int stage = kv % STAGES;
-          mbar_wait(&k_full[stage], (kv / STAGES) & 1u);
-          tc_fence_after();
-          issue_s(0, stage);
-          if (leader) umma_commit(&s_full[0]);
-          issue_s(1, stage);
-          if (leader) umma_commit(&s_full[1]);
-          if (leader) umma_commit(&k_empty[stage]);
-          if (T == 1 && leader) umma_commit(q_empty);
-        }
-        for (int j = 0; j < T; ++j) {
-          const uint32_t g = kv + j;
-          const int stage = g % STAGES;
-          mbar_wait(&v_full[stage], (g / STAGES) & 1u);
-          const int nstage = (g + 1) % STAGES;
-          const uint32_t nph = ((g + 1) / STAGES) & 1u;
+      // The CTA's items form ONE stream of key-tile steps g = it * T + j: S_x(g+1) is issued right behind PV_x(g) also
+      // across an item boundary (the next item's Q tiles and first K tile are prefetched), so the tensor pipe never
+      // drains between items; only the epilogue of a tile sits between its last PV and its next softmax.
+      const int my_items = ((int)blockIdx.x < p.items) ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const uint32_t G = (uint32_t)my_items * (uint32_t)T;
+      // S_x of step g: waits for what it reads (K tile always; the tile's Q slot on the first key tile of an item)
+      auto s_step = [&](int x, uint32_t g) {
+        const uint32_t it = g / (uint32_t)T, j = g - it * (uint32_t)T;
+        const int stage = (int)(g % STAGES);
+        const uint32_t t = 2u * it + (uint32_t)x;
+        const int qslot = (int)(t % 3u);
+        if (x == 0) mbar_wait(&k_full[stage], (g / STAGES) & 1u);
+        if (j == 0) mbar_wait(&q_full[qslot], (t / 3u) & 1u);
+        tc_fence_after();
+        issue_s(x, stage, qslot);
+        if (leader) umma_commit(&s_full[x]);
+        if ((int)j + 1 == T && leader) umma_commit(&q_empty[qslot]);   // the tile's last S: its Q slot is free
+        if (x == 1 && leader) umma_commit(&k_empty[stage]);
+      };
+      if (G > 0) {
+        F2T(100);
+        s_step(0, 0);
+        s_step(1, 0);
+        F2T(103);
+      }
+      for (uint32_t g = 0; g < G; ++g) {
+        const int stage = (int)(g % STAGES);
+        const int j = (int)(g % (uint32_t)T);
+        mbar_wait(&v_full[stage], (g / STAGES) & 1u);
+        F2T(110 + j);
 #pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            mbar_wait(&p_full[x], pcount[x] & 1u);
-            ++pcount[x];
-            tc_fence_after();
-            issue_pv(x, stage, j > 0);
-            if (leader) umma_commit(&pv_done[x]);
-            if (x == 1 && leader) umma_commit(&v_empty[stage]);
-            if (j + 1 < T) {
-              if (x == 0) {
-                mbar_wait(&k_full[nstage], nph);
-                tc_fence_after();
-              }
-              issue_s(x, nstage);   // in-order after PV_x(j): P_x(j) has been consumed before S_x is overwritten
-              if (leader) umma_commit(&s_full[x]);
-              if (x == 1) {
-                if (leader) umma_commit(&k_empty[nstage]);
-                if (j + 2 == T && leader) umma_commit(q_empty);
-              }
-            }
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&p_full[2 * x], g & 1u);
+          F2T(120 + 10 * x + j);
+          tc_fence_after();
+          issue_pv(x, stage, j > 0, 0);
+          mbar_wait(&p_full[2 * x + 1], g & 1u);
+          tc_fence_after();
+          issue_pv(x, stage, j > 0, 1);
+          if (leader) umma_commit(&pv_done[x]);
+          if (x == 1 && leader) umma_commit(&v_empty[stage]);
+          if (g + 1 < G) {
+            s_step(x, g + 1);   // in-order after PV_x(g): P_x(g) has been consumed before S_x is overwritten
+            F2T(140 + 10 * x + j);
           }
         }
-        kv += T;
       }
     }
+  }
+  else if (warp == 3 && p.staged) {
+    // ================= output store (staged epilogue) =================
+    const bool leader = (lane == 0);
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int qp = item % p.q_pairs;
+      const int bh = item / p.q_pairs;
+      const int h = bh % p.H, b = bh / p.H;
+      g += (uint32_t)T;
+      const uint32_t last_stage = (g - 1u) % STAGES;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&o_ready[x], (uint32_t)it & 1u);
+        if (leader) {
+          const uint8_t* stg = (x == 0) ? sK + last_stage * Cfg::K_BYTES : sV + last_stage * Cfg::V_BYTES;
+#pragma unroll
+          for (int c = 0; c < NVC; ++c)
+            tma_store_3d(&tmap_o, stg + c * 16384, h * p.dv + c * 64, qp * 256 + x * 128, b);   // clips rows >= Nq
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(&epi_done[x]);
+        }
+        __syncwarp();
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
@@ -281,7 +370,9 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       float l = 0.f;        // running sum of exp2(t - m)
       for (int j = 0; j < T; ++j, ++g) {
         const int k0 = j * BN;
+        if (quarter == 0) F2T(200 + 100 * x + 10 * j);
         mbar_wait(&s_full[x], g & 1u);
+        if (quarter == 0) F2T(201 + 100 * x + 10 * j);
         tc_fence_after();
         const bool tail = (k0 + BN > p.Nk) || (km != nullptr);
         // ---- the whole S row of this tile (BN fp32 values) moves to registers with one wait ----
@@ -289,6 +380,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tmem_wait_ld();
+        if (quarter == 0) F2T(202 + 100 * x + 10 * j);
         if (tail) {
           // masked / out-of-range keys become -inf: they drop out of the max and exp2 turns them into exact zeros
 #pragma unroll
@@ -337,6 +429,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         l *= alpha;
         m = m_use;
+        if (quarter == 0) F2T(203 + 100 * x + 10 * j);
         const float msub = (m == -INFINITY) ? 0.0f : m;
         // ---- p = exp2(scale * s - m) -> bf16 pairs written over S in TMEM (two values per 32-bit column); the row sum
         //      uses the bf16-rounded values the tensor core will multiply, so P and l stay consistent ----
@@ -352,12 +445,21 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                                       sc2, nm2);
             float t0, t1;
             unpack_f32x2(t2, t0, t1);
-            w[i] = pack_bf16x2(ex2_approx(t0), ex2_approx(t1));
-            const uint64_t pr = pack_f32x2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+            w[i] = pack_bf16x2(e0, e1);
+            // the row sum takes the un-rounded exponentials: round-to-nearest is unbiased, so l differs from the sum of
+            // the bf16 values the tensor core multiplies by ~2^-9 / sqrt(Nk) relative, and rebuilding the rounded values
+            // cost two integer instructions per pair in a loop that is issue-bound (one warp per scheduler)
+            const uint64_t pr = pack_f32x2(e0, e1);
             if (i & 1) lb = fadd2(lb, pr);
             else la = fadd2(la, pr);
           }
           tmem_st16(t_s + c * 16, w);
+          if (c == BN / 64 - 1) {   // first half of the key tile is in TMEM
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[2 * x]);
+          }
         }
         float lsum;
         {
@@ -369,21 +471,65 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         l += lsum;
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
+        mbar_arrive(&p_full[2 * x + 1]);
+        if (quarter == 0) F2T(204 + 100 * x + 10 * j);
       }
       // ---- epilogue of the item: O_x / l -> bf16 ----
       mbar_wait(&pv_done[x], (g - 1u) & 1u);
+      if (quarter == 0) F2T(250 + 100 * x);
       tc_fence_after();
       const bool keep = (q < p.Nq) && (p.row_keep == nullptr || p.row_keep[(long long)b * p.stride_rk + q] != 0);
       const float inv = (keep && l > 0.f) ? 1.0f / l : 0.0f;
       __nv_bfloat16* orow = p.O + (long long)b * p.strideO + (long long)q * p.ldo + (long long)h * p.dv;
+      if (p.staged) {
+        // Every lane owns a different output row (rows are ldo apart), so direct stores cost one pass of the store
+        // path per lane and instruction (~2200 cycles per tile, and they delay the MMA warp's barrier traffic).
+        // Instead the tile is parked in shared memory that is idle right now — tile A: the K stage of the item's last
+        // key tile (S_B of that tile retired before PV_A did), tile B: its V stage (PV_B retired) — in the 128-byte
+        // swizzled layout, and one thread hands it to TMA; the producer refills those stages only after epi_done.
+        const uint32_t last_stage = (g - 1u) % STAGES;
+        uint8_t* stg = (x == 0) ? sK + last_stage * Cfg::K_BYTES : sV + last_stage * Cfg::V_BYTES;
+#pragma unroll 1
+        for (int c = 0; c < NVC * 64; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_o + c, r);
+          tmem_wait_ld();
+          uint8_t* chunk = stg + (c >> 6) * 16384;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(r[8 * gq]) * inv, __uint_as_float(r[8 * gq + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv);
+            *reinterpret_cast<uint4*>(chunk + sw128_offset((uint32_t)row, (uint32_t)(((c & 63) >> 3) + gq))) = w;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&o_ready[x]);   // warp 3 hands the tile to TMA; this thread goes straight on to the next item
+        if (quarter == 0) F2T(251 + 100 * x);
+        continue;
+      }
       for (int c = 0; c < dv_n; c += 32) {
         uint32_t r[32];
         tmem_ld32(t_o + c, r);
         tmem_wait_ld();
         if (q < p.Nq) {
           __nv_bfloat16* op = orow + c;
-          if (c + 32 <= p.dv && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+          if (c + 32 <= p.dv && ((reinterpret_cast<uintptr_t>(op) & 31u) == 0)) {
+            // 32-byte stores: every lane writes its own row (rows are ldo apart), so the store path handles one lane
+            // per pass — halving the instruction count halves the epilogue
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16x2(__uint_as_float(r[16 * gq + 2 * i]) * inv, __uint_as_float(r[16 * gq + 2 * i + 1]) * inv);
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + 16 * gq), "r"(w[0]),
+                           "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                           : "memory");
+            }
+          } else if (c + 32 <= p.dv && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
               uint4 w;
@@ -400,6 +546,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       }
+      if (quarter == 0) F2T(251 + 100 * x);
       // the next item's first p_full arrival (after tc_fence_before) orders these O reads before PV_x overwrites O_x
     }
   }
@@ -441,7 +588,22 @@ static int launch_flash2_cfg(const pio_attention_args* a, const DeviceInfo& dev,
     int rc = encode_tmap_bf16(&tv, a->V, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   }
+  // staged epilogue: whole 64-column chunks per head, an output the tensor map can address, O tile no larger than a
+  // K stage, and at least STAGES key tiles per item (so the stage a tile parks its output in is refilled by a known
+  // load of the next item)
+  const int kv_tiles = (a->Nk + BN - 1) / BN;
+  const bool staged = BN == 128 && NVC <= NQC && a->dv == NVC * 64 && kv_tiles >= Cfg::STAGES && aligned16(a->O) &&
+                      a->ldo % 8 == 0 && (a->B == 1 || a->strideO % 8 == 0);
+  CUtensorMap to = tq;
+  if (staged) {
+    const uint64_t dims[3] = {(uint64_t)a->H * a->dv, (uint64_t)a->Nq, (uint64_t)a->B};
+    const uint64_t strides[2] = {(uint64_t)a->ldo * 2, (uint64_t)(a->B == 1 ? a->ldo * (int64_t)a->Nq : a->strideO) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = encode_tmap_bf16(&to, a->O, 3, dims, strides, box);
+    if (rc != PIO_OK) return rc;
+  }
   Flash2Params p;
+  p.staged = staged ? 1 : 0;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.dqk = a->dqk; p.dv = a->dv;
   p.q_bcast = q_bcast;
   p.scale_log2 = a->scale * 1.4426950408889634f;
@@ -465,8 +627,24 @@ static int launch_flash2_cfg(const pio_attention_args* a, const DeviceInfo& dev,
   {
     ProfileScope prof(KF_FLASH, 2.0 * a->B * a->H * (double)a->Nq * a->Nk * (a->dqk + a->dv), 0.0, stream);
     PIO_CUDA_OK(launch_kernel(pio_flash2_kernel<NQC, NVC, BN>, dim3((unsigned)grid, 1, 1), dim3(384, 1, 1), Cfg::SMEM_BYTES,
-                              stream, 1, tq, tk, tv, p));
+                              stream, 1, tq, tk, tv, to, p));
   }
+#ifdef PIO_FLASH2_TRACE
+  {
+    static bool dumped = false;
+    if (!dumped) {
+      dumped = true;
+      cudaDeviceSynchronize();
+      static unsigned long long host[12 * 2 * 512];
+      cudaMemcpyFromSymbol(host, g_f2_trace, sizeof(host));
+      unsigned long long t0 = ~0ull;
+      for (unsigned i = 0; i < 12 * 512; ++i)
+        if (host[2 * i] != 0 && host[2 * i + 1] < t0) t0 = host[2 * i + 1];
+      for (unsigned i = 0; i < 12 * 512; ++i)
+        if (host[2 * i] != 0) fprintf(stderr, "F2T %llu %llu\n", host[2 * i], host[2 * i + 1] - t0);
+    }
+  }
+#endif
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;

@@ -300,7 +300,7 @@ def test_fused_layernorm_tower_matches_oracle_and_unfused_path():
     torch.manual_seed(0)
     enc = pio.PerceiverEncoder(**dict(cfg["enc"], num_self_attends_per_block=3, num_blocks=2)).eval()
     _perturb(enc, 7)
-    B, Nk = 4, 3000
+    B, Nk = 8, 3000
     inputs = torch.randn(B, Nk, 261)
     pe = {k: v.detach() for k, v in enc.state_dict().items()}
     from oracle import perceiver_oracle as O
@@ -321,7 +321,8 @@ def test_fused_layernorm_tower_matches_oracle_and_unfused_path():
     print(f"fused tower: max {ef[0]:.3e} l2 {ef[1]:.3e}; unfused: max {ep[0]:.3e} l2 {ep[1]:.3e}; "
           f"fused vs unfused {rel_err(z_fused, z_plain)[0]:.3e}")
     assert ef[0] <= BF16_TOL, ef
-    assert rel_err(z_fused, z_plain)[0] <= 5e-3
+    # two independent bf16 evaluations, each ~5e-3 from the oracle: their mutual distance is bounded by the sum
+    assert rel_err(z_fused, z_plain)[0] <= 8e-3
 
 
 def test_encode_once_latent_cache():
