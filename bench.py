@@ -371,7 +371,7 @@ def run_gpu_arm(args):
                      # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), averaged over the four GEMM
                      # shapes of a tower layer, from the committed `ncu --set full` capture; their algorithmic bytes
                      # (operands + fp32 residual in/out + raw bf16 rows) average 305 MB per launch
-                     "traffic": 2.60e8, "traffic_source": "profiles/r01h_ncu_full_encoder_and_tower_summary.csv",
+                     "traffic": 2.62e8, "traffic_source": "profiles/r01k_ncu_full_encoder_and_tower_summary.csv",
                      "share_of_step": shares.get("gemm")},
         "model": {"flops_per_sample_reference_algorithm": mf,
                   "tflops_reference_algorithm": mf * value / 1e12,
