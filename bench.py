@@ -182,7 +182,7 @@ def run_reference_arm(args):
     sec = time_cpu(batch, args.warmup, args.steps)
     v = batch / sec
     sample = f"{batch} sample(s) of the 64-sample batch per step, fp32, torch CPU ops, {torch.get_num_threads()} threads"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "samples/sec per forward", "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -190,7 +190,29 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
+
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at communicator
+# creation), so file descriptor 1 points at stderr for the whole run and only _emit() writes to the real stdout.
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -390,7 +412,7 @@ def run_gpu_arm(args):
         except Exception as ex:  # the baseline must never take the GPU number down
             result["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                       "sample": f"failed: {ex}"}
-    print(json.dumps(result))
+    _emit(result)
     if world > 1:
         dist.destroy_process_group()
 
@@ -406,6 +428,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    _guard_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
