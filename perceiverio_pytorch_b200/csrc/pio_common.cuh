@@ -82,6 +82,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel lets the next grid in the stream start its prologue early
+// (launch_dependents) and then waits for the previous grid's results before touching global memory (wait).
+// Both are no-ops unless the launch carries the programmatic-serialization attribute (pio_host.h: launch_kernel).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -118,6 +118,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * BN;
+  pdl_sync();   // barriers / TMEM are set up; Q, K, V of the previous kernel are read from here on
 
   // number of 16-wide k-steps of the QK^T contraction in chunk c, and N extent of the PV product
   const int dqk_steps_total = (p.dqk + 15) / 16;

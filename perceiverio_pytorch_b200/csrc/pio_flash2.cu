@@ -145,6 +145,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * BN;
+  pdl_sync();   // barriers / TMEM are set up; Q, K, V of the previous kernel are read from here on
 
   const int T = p.kv_tiles;
   const int dqk_steps = (p.dqk + 15) / 16;

@@ -103,6 +103,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // barriers / TMEM are set up; operands and residuals of the previous kernel are read from here on
 
   if (warp == 0) {
     if (lane == 0) {

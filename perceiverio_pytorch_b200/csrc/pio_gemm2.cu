@@ -125,6 +125,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // barriers / TMEM are set up; operands and residuals of the previous kernel are read from here on
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================

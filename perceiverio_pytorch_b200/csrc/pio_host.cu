@@ -11,6 +11,20 @@ namespace pio {
 thread_local char g_last_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
 
+int pdl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("PIO_PDL");
+    if (!e || !*e) return 1;
+    return (e[0] == '0') ? 0 : (e[0] == '2' ? 2 : 1);
+  }();
+  return mode;
+}
+
+int pdl_sm_count() {
+  DeviceInfo d;
+  return get_device_info(&d) == PIO_OK ? d.sm_count : 0;
+}
+
 int get_device_info(DeviceInfo* out) {
   static std::mutex mu;
   static DeviceInfo cache[64];

@@ -80,9 +80,15 @@ int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t str
 bool flash2_eligible(const pio_attention_args* a);
 int launch_flash2(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream);
 
-// cudaLaunchKernelEx with an optional cluster width.  (Programmatic dependent launch was tried for these kernels and
-// measured slower — 33.1 vs 31.7 ms per bench step: every kernel fills all SMs with one large-smem CTA, so a dependent
-// grid can only overlap its prologue with the predecessor's last wave — and is not used.)
+// cudaLaunchKernelEx with an optional cluster width and programmatic dependent launch.
+// PDL: a grid that leaves SMs idle (fewer CTAs than SMs: the batch-1 towers, 40 .. 128 CTAs per kernel, 7 kernels per
+// layer) is launched with programmatic stream serialization, so its CTAs are scheduled and run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch) while the previous kernel drains; every kernel calls pdl_sync() before it
+// touches global memory.  Grids that fill the machine keep plain serialization: for the batch-64 recipe, where every
+// kernel occupies all SMs with one large-smem CTA, PDL measured slower (33.1 vs 31.7 ms per bench step).
+// PIO_PDL=0 disables it, PIO_PDL=2 forces it for every launch.
+int pdl_mode();
+int pdl_sm_count();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  int cluster_x, Args&&... args) {
@@ -91,13 +97,20 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int n = 0;
   if (cluster_x > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
     attr[n].val.clusterDim.x = cluster_x;
     attr[n].val.clusterDim.y = 1;
     attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  const int mode = pdl_mode();
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  if (mode == 2 || (mode == 1 && ctas < pdl_sm_count())) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
   }
   cfg.attrs = attr;

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, long long rows, int C,
                                                                 int mode, float eps) {
+  pdl_sync();
   const int normalize = mode & 1;
   const int lane = threadIdx.x & 31;
   // Rows are walked from the END of the array: x was just written front-to-back by the producing GEMM (or H2D copy),
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows, int C,
                                                             int mode, float eps) {
+  pdl_sync();
   // This path is instruction-issue bound (ncu: 72 % issue-active at 365 instructions per row in its first form), so
   // each warp walks many row groups with the affine parameters held in registers and as little per-element control
   // flow as possible.
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(LNB_THREADS) pio_layernorm_bulk_kernel(const f
                                                                          const float* __restrict__ beta,
                                                                          long long ngroups, int R, int C, int normalize,
                                                                          float eps) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t lnb_smem[];
   const uint32_t in_bytes = (uint32_t)R * (uint32_t)C * 4u;          // multiple of 16 (R % 4 == 0)
   const uint32_t in_pitch = (in_bytes + 127u) & ~127u;
@@ -325,6 +328,7 @@ static const lnb_kernel_t* lnb_kernel_table(std::integer_sequence<int, I...>) {
 // L1/L2 (<= 208 KB).  Masked keys are excluded; an all-masked or wiped row is written as zeros.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
+  pdl_sync();
   __shared__ float red[8];
   __shared__ float bcast;
   const long long row_id = blockIdx.x;
@@ -402,6 +406,7 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
 // ------------------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256) pio_softmax_warp_kernel(pio_softmax_args a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row_id = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row_id >= (long long)a.batch * a.rows) return;
@@ -458,6 +463,7 @@ __global__ void __launch_bounds__(256) pio_softmax_warp_kernel(pio_softmax_args 
 // Merge partial attention results: one warp per (b, h, query row).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)a.B * a.H * a.Nq;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -538,6 +544,7 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
 
 // More than 16 parts (deep local key splits): the general loop over one local buffer.
 __global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)a.B * a.H * a.Nq;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -598,6 +605,7 @@ __global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args 
 // ------------------------------------------------------------------------------------------------------------
 template <int NOUT>
 __global__ void __launch_bounds__(256) pio_linear_f32_kernel(pio_linear_f32_args a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= a.M) return;
