@@ -302,8 +302,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       l *= alpha;
       m = m_use;
       const float msub = (m == -INFINITY) ? 0.0f : m;
-      // ---- p = exp2(scale * s - m) -> bf16 P tile in swizzled smem; the row sum uses the bf16-rounded values the
-      //      tensor core will multiply, so P and l stay consistent ----
+      // ---- p = exp2(scale * s - m) -> bf16 P written over S in TMEM; the row sum takes the un-rounded exponentials ----
       const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
       const uint64_t nm2 = pack_f32x2(-msub, -msub);
       uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);
@@ -316,8 +315,9 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                     sc2, nm2);
           float t0, t1;
           unpack_f32x2(t2, t0, t1);
-          w[i] = pack_bf16x2(ex2_approx(t0), ex2_approx(t1));
-          const uint64_t pr = pack_f32x2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+          const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+          w[i] = pack_bf16x2(e0, e1);
+          const uint64_t pr = pack_f32x2(e0, e1);   // un-rounded: RN is unbiased, see pio_flash2.cu
           if (i & 1) lb = fadd2(lb, pr);
           else la = fadd2(la, pr);
         }

@@ -80,6 +80,9 @@ class PerceiverEncoder(nn.Module):
 
     def forward(self, inputs, latents, *, input_mask=None):
         """inputs fp32 [B, Nk, C_in] (this rank's key slice when `key_shard` is set), latents [B, Nlat, C]."""
+        ops._need_cuda(inputs, latents)
+        if latents.shape[0] == 0 or latents.shape[1] == 0:   # empty batch / no latents: nothing to launch
+            return latents.new_empty(latents.shape)
         key_mask = None
         row_keep = None
         if input_mask is not None:
@@ -176,8 +179,11 @@ class PerceiverDecoder(nn.Module):
             nn.init.constant_(self.final_layer.bias, 0)
 
     def forward(self, query, latents, *, query_mask=None):
+        ops._need_cuda(query, latents)
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
         n_out = self._output_num_channels
+        if query.shape[0] == 0 or query.shape[1] == 0:   # empty batch / no output queries: nothing to launch
+            return query.new_empty(query.shape[0], query.shape[1], n_out if self._final_project else query.shape[2])
         # the wide final projection consumes bf16 rows: let the MLP's last GEMM write them next to the fp32 result
         want16 = (self._final_project and n_out > 16 and engine.PRECISION == "bf16"
                   and self.query_channels % 16 == 0)

@@ -134,6 +134,9 @@ class Attention(nn.Module):
         ops._need_cuda(inputs_q, inputs_k, inputs_v)
         B, Nq, Cq = inputs_q.shape
         Nk = inputs_k.shape[1]
+        if B == 0 or Nq == 0:   # empty batch / no queries: nothing to launch
+            y = inputs_q.new_empty(B, Nq, self.final.out_features)
+            return (inputs_q.new_empty(B, self._num_heads, Nq, Nk), y) if return_matrix else y
         pa = engine.prepared(self, "plain", lambda: engine.PreparedAttention(self, self_attention=False,
                                                                              allow_fold=False))
         row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix, B=B, H=pa.H, Nq=Nq,
@@ -220,6 +223,9 @@ class SelfAttention(nn.Module):
         _check_inference(self, *self._dropout_probs)
         ops._need_cuda(inputs)
         B, N, _ = inputs.shape
+        if B == 0 or N == 0:   # empty batch: nothing to launch
+            y = inputs.new_empty(inputs.shape)
+            return (inputs.new_empty(B, self.attention._num_heads, N, N), y) if return_matrix else y
         row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix, B=B,
                                                   H=self.attention._num_heads, Nq=N, Nk=N, device=inputs.device)
         if engine.PRECISION == "bf16x3":
@@ -271,6 +277,10 @@ class CrossAttention(nn.Module):
 
     def forward(self, inputs_q, inputs_kv, *, attention_mask=None, attention_bias=None, return_matrix: bool = False):
         ops._need_cuda(inputs_q, inputs_kv)
+        if inputs_q.shape[0] == 0 or inputs_q.shape[1] == 0:   # empty batch / no queries: nothing to launch
+            y = inputs_q.new_empty(inputs_q.shape)
+            m = inputs_q.new_empty(inputs_q.shape[0], self.attention._num_heads, inputs_q.shape[1], inputs_kv.shape[1])
+            return (m, y) if return_matrix else y
         row_keep, key_mask, general = _route_mask(attention_mask, attention_bias, return_matrix,
                                                   B=inputs_q.shape[0], H=self.attention._num_heads,
                                                   Nq=inputs_q.shape[1], Nk=inputs_kv.shape[1], device=inputs_q.device)

@@ -346,3 +346,50 @@ def test_encode_once_latent_cache():
         enc.cross_attend.attention.proj_q.bias.add_(0.5)  # parameter update
         enc(x + 1.0, enc.latents(x))
         assert _lib.launch_count() > n1
+
+
+def test_empty_batch_and_empty_query_sets_return_empty_outputs():
+    """The reference's modules accept an empty batch / an empty query array (every op is a no-op on them); the drop-in
+    returns tensors of the same shapes without launching anything."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import _lib
+    enc = pio.PerceiverEncoder(num_input_channels=37, num_self_attends_per_block=1, num_blocks=1, num_latents=16,
+                               num_latent_channels=64, num_self_attend_heads=4).eval().cuda()
+    dec = pio.PerceiverDecoder(query_channels=48, final_project_out_channels=10, num_latent_channels=64).eval().cuda()
+    sa = pio.SelfAttention(in_channels=64, widening_factor=1, num_heads=4).eval().cuda()
+    n0 = _lib.launch_count()
+    with torch.inference_mode():
+        x0 = torch.zeros(0, 100, 37, device="cuda")
+        z0 = enc(x0, enc.latents(x0))
+        assert z0.shape == (0, 16, 64)
+        assert dec(torch.zeros(0, 7, 48, device="cuda"), z0).shape == (0, 7, 10)
+        z = torch.randn(2, 16, 64, device="cuda")
+        assert dec(torch.zeros(2, 0, 48, device="cuda"), z).shape == (2, 0, 10)
+        assert sa(torch.zeros(0, 16, 64, device="cuda")).shape == (0, 16, 64)
+        m, y = sa(torch.zeros(0, 16, 64, device="cuda"), return_matrix=True)
+        assert m.shape == (0, 4, 16, 16) and y.shape == (0, 16, 64)
+    assert _lib.launch_count() == n0
+
+
+@pytest.mark.parametrize("nk,nq", [(1, 1), (63, 129), (257, 5), (1000, 1)])
+def test_ragged_sizes_match_oracle(nk, nq):
+    """Key / query counts that are not multiples of any tile (down to a single key and a single query)."""
+    import perceiverio_pytorch_b200 as pio
+    from oracle import perceiver_oracle as O
+    torch.manual_seed(nk * 1000 + nq)
+    enc = pio.PerceiverEncoder(num_input_channels=37, num_self_attends_per_block=1, num_blocks=1, num_latents=24,
+                               num_latent_channels=64, num_self_attend_heads=4).eval()
+    dec = pio.PerceiverDecoder(query_channels=50, final_project_out_channels=10, num_latent_channels=64).eval()
+    _perturb(enc, 3)
+    _perturb(dec, 4)
+    inputs, query = torch.randn(3, nk, 37), torch.randn(3, nq, 50)
+    z_ref, out_ref = _oracle_enc_dec(enc, dec, dict(num_blocks=1, num_self_attends_per_block=1, num_cross_attend_heads=1,
+                                                    num_self_attend_heads=4, use_query_residual=True),
+                                     dict(num_heads=1, use_query_residual=False, final_project=True), inputs, query)
+    enc, dec = enc.cuda(), dec.cuda()
+    with torch.inference_mode():
+        xi = inputs.cuda()
+        z = enc(xi, enc.latents(xi))
+        out = dec(query.cuda(), z)
+    assert rel_err(z.cpu(), z_ref)[0] <= BF16_TOL
+    assert rel_err(out.cpu(), out_ref)[0] <= BF16_TOL
