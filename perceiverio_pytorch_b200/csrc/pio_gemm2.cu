@@ -43,6 +43,17 @@ struct Gemm2Params {
 
 enum { G2_BF16 = 0, G2_F32 = 1 };
 
+// fp32-output kind: operand stages vs depth of the per-warp residual prefetch ring (both live in shared memory)
+#ifndef G2_F32_STAGES
+#define G2_F32_STAGES 4
+#endif
+#ifndef G2_F32_RES_SLOTS
+#define G2_F32_RES_SLOTS 2
+#endif
+#ifndef G2_F32_OUT_SLOTS
+#define G2_F32_OUT_SLOTS 2
+#endif
+
 template <int KIND>
 struct Gemm2Cfg {
   static constexpr int BM = 128;       // rows per CTA (256 per pair)
@@ -51,16 +62,16 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (KIND == G2_F32) ? 4 : 5;
+  static constexpr int STAGES = (KIND == G2_F32) ? G2_F32_STAGES : 5;
   static constexpr int EPI_WARPS = 8;
   // staging slots: bf16 output 32 rows x 64 columns (128-byte rows, SWIZZLE_128B); fp32 32 rows x 16 columns (64-byte
   // rows, SWIZZLE_64B) so that two residual + two output slots per warp leave room for the fifth operand stage
   static constexpr int SLOT_BYTES = (KIND == G2_F32) ? 2048 : 4096;
-  static constexpr int RES_SLOTS = (KIND == G2_F32) ? 2 : 0;
-  static constexpr int OUT_SLOTS = 2;
+  static constexpr int RES_SLOTS = (KIND == G2_F32) ? G2_F32_RES_SLOTS : 0;
+  static constexpr int OUT_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 2;
   // fused-LayerNorm producer: raw bf16 copy of the fp32 output, 32 rows x 16 columns (32-byte rows, no swizzle)
   static constexpr int RAW_SLOT_BYTES = 1024;
-  static constexpr int RAW_SLOTS = (KIND == G2_F32) ? 2 : 0;
+  static constexpr int RAW_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 0;
   static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES + RAW_SLOTS * RAW_SLOT_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
   static constexpr int BAR_BYTES = 512;
@@ -82,8 +93,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + Cfg::STAGES;     // [STAGES]  MMA -> TMA producer of each CTA (multicast commit)
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;    // [2]       MMA -> epilogue of each CTA (multicast commit)
   uint64_t* tmem_empty = tmem_full + 2;             // [2]       epilogue warps of both CTAs -> MMA (leader's)
-  uint64_t* res_full = tmem_empty + 2;              // [EPI_WARPS][2]  residual TMA -> epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::EPI_WARPS * 2);
+  constexpr int RS = Cfg::RES_SLOTS > 0 ? Cfg::RES_SLOTS : 1;
+  uint64_t* res_full = tmem_empty + 2;              // [EPI_WARPS][RES_SLOTS]  residual TMA -> epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::EPI_WARPS * RS);
 
   // the shuffle makes the warp index provably warp-uniform, so the role code can use the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -113,7 +125,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);   // one arrival per epilogue warp of either CTA
     }
-    for (int i = 0; i < Cfg::EPI_WARPS * 2; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < Cfg::EPI_WARPS * RS; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -195,14 +207,14 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my = epi_base + ew * Cfg::WARP_EPI_BYTES;
     uint8_t* my_out = my + Cfg::RES_SLOTS * Cfg::SLOT_BYTES;
     uint8_t* my_raw = my_out + Cfg::OUT_SLOTS * Cfg::SLOT_BYTES;
-    uint64_t* my_res_full = res_full + ew * 2;
+    uint64_t* my_res_full = res_full + ew * RS;
     const bool has_res = (KIND == G2_F32) && p.has_residual;
     constexpr int CHUNK_COLS = (KIND == G2_F32) ? 16 : 64;
     constexpr int CHUNKS = 128 / CHUNK_COLS;           // chunks of this warp's column half per tile
     const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
 
-    // residual prefetch cursor (lane 0): the stream of (tile, chunk) boxes this warp will consume, two ahead
+    // residual prefetch cursor (lane 0): the stream of (tile, chunk) boxes this warp will consume, RES_SLOTS ahead
     int pf_t = pair_id, pf_c = 0;
     uint32_t pf_idx = 0;
     auto issue_res = [&]() {
@@ -212,15 +224,14 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int z = pf_t / (p.tiles_n * p.m_pairs);
       const int row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
       const int col = nt * Cfg::BN + half * 128 + pf_c * CHUNK_COLS;
-      const uint32_t slot = pf_idx & 1u;
+      const uint32_t slot = pf_idx % (uint32_t)RS;
       mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
       tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, p.r_bcast ? 0 : z);
       ++pf_idx;
       if (++pf_c == CHUNKS) { pf_c = 0; pf_t += num_pairs; }
     };
     if (has_res && lane == 0) {
-      issue_res();
-      issue_res();
+      for (int i = 0; i < RS; ++i) issue_res();
     }
     uint32_t use_idx = 0;
     int it = 0;
@@ -312,8 +323,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if constexpr (KIND == G2_F32) {
           if (has_res) {
-            const uint32_t slot = use_idx & 1u;
-            mbar_wait(&my_res_full[slot], (use_idx >> 1) & 1u);
+            const uint32_t slot = use_idx % (uint32_t)RS;
+            mbar_wait(&my_res_full[slot], (use_idx / (uint32_t)RS) & 1u);
             const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -330,9 +341,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 st_sq = fmaf(v[j], v[j], st_sq);
               }
           }
-          uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
-          uint8_t* slot_raw = my_raw + (use_idx & 1u) * Cfg::RAW_SLOT_BYTES;
-          if (lane == 0) bulk_wait_read<1>();   // the stores issued two chunks ago used these slots
+          uint8_t* slot_out = my_out + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::SLOT_BYTES;
+          uint8_t* slot_raw = my_raw + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::RAW_SLOT_BYTES;
+          if (lane == 0) bulk_wait_read<Cfg::OUT_SLOTS - 1>();   // the stores issued OUT_SLOTS chunks ago used these slots
           __syncwarp();
           if (p.raw_bf16 != nullptr) {
             // bf16 copy of the un-normalised row segment (32 bytes per row) for the fused LayerNorm of the consumer
