@@ -30,8 +30,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 CFG = dict(
-    workload="ClassificationPerceiver ImageNet-pixels hot path: 50176x261 inputs -> 512x1024 latents, 8x6 self-attends, "
-             "1000-query decoder + final 1024->1000",
+    workload="ClassificationPerceiver ImageNet-pixels forward: 224x224 images -> 50176x261 inputs (pixels + Fourier "
+             "positions) -> 512x1024 latents, 8x6 self-attends, 1000-query decoder + final 1024->1000",
     batch_per_gpu=64, num_inputs=50176, input_channels=261, num_latents=512, latent_channels=1024,
     num_blocks=8, self_attends_per_block=6, num_queries=1000, num_classes=1000)
 
@@ -149,11 +149,14 @@ def cpu_forward_factory(batch):
     pe = {k: v.detach() for k, v in enc.state_dict().items()}
     pd = {k: v.detach() for k, v in dec.state_dict().items()}
     g = torch.Generator().manual_seed(3)
-    inputs = torch.randn(batch, CFG["num_inputs"], CFG["input_channels"], generator=g)
+    images = torch.randn(batch, 3, 224, 224, generator=g)
     query = 0.02 * torch.randn(1, CFG["num_queries"], 1024, generator=g).expand(batch, -1, -1)
 
     def fwd():
         with torch.inference_mode():
+            # the reference rebuilds the Fourier table and the concatenated array on every forward
+            # (preprocessors.py:180-199, position_encoding.py:173-183)
+            inputs = O.image_inputs_pixels(images, 64, (224, 224), 1)
             z = O.encoder_forward(pe, "", num_blocks=8, num_self_attends_per_block=6, num_cross_attend_heads=1,
                                   num_self_attend_heads=8, inputs=inputs)
             return O.decoder_forward(pd, "", num_heads=1, use_query_residual=True, final_project=True, query=query,
@@ -265,29 +268,27 @@ def run_gpu_arm(args):
     perturb(dec, 2)
     enc, dec = enc.to(dev), dec.to(dev)
     g = torch.Generator().manual_seed(3 + rank)
-    host_inputs = torch.empty(B, CFG["num_inputs"], CFG["input_channels"]).normal_(generator=g).pin_memory()
-    inputs = host_inputs.to(dev)
+    H = W = 224
+    host_images = torch.empty(B, 3, H, W).normal_(generator=g).pin_memory()
+    table = pio.fourier_position_table((H, W), 64, device=dev)          # [50176, 258], device-resident like the weights
     # the decoder query of the classification recipe is a trainable [1000, 1024] array broadcast over the batch and
     # materialised by torch.cat in PerceiverIO.decoder_query (perceiver.py:353-364): device-resident, like the weights
     query = (0.02 * torch.randn(1, CFG["num_queries"], 1024, generator=torch.Generator().manual_seed(5))).to(dev) \
         .expand(B, -1, -1).contiguous()
     host_out = torch.empty(B, CFG["num_classes"]).pin_memory()
 
-    def step_eager(x):
+    def step_image(img):
+        """Images -> pixels + Fourier table (fused into the encoder's LayerNorm) -> encoder -> decoder."""
+        with torch.inference_mode():
+            pin = pio.PositionedInput(img.movedim(-3, -1).reshape(B, H * W, 3), table)
+            z = enc(pin, enc.latents(pin))
+            return dec(query, z)
+
+    def step_dense(x):
+        """The narrower boundary of the earlier rounds: the preprocessed [B, 50176, 261] fp32 array as input."""
         with torch.inference_mode():
             z = enc(x, enc.latents(x))
             return dec(query, z)
-
-    if args.no_graph:
-        step = step_eager
-    else:
-        # the whole forward (several hundred launches) is captured once; `inputs` is the graph's input buffer
-        from perceiverio_pytorch_b200.graph import GraphedForward
-        graphed = GraphedForward(step_eager, [inputs], warmup=2)
-        inputs = graphed.inputs[0]
-
-        def step(x):
-            return graphed(x)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -295,31 +296,79 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        out = step(inputs)
-    sync_all()
+    from perceiverio_pytorch_b200.graph import GraphedForward
 
-    # ---- timed region 1: device-resident inputs ----
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        out = step(inputs)
-    e1.record()
-    sync_all()
-    wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(wall0, wall1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    def measure(step_eager, host_in, steps, e2e_steps, sampler=None):
+        """value (inputs resident in HBM) and e2e (pinned host input -> H2D -> forward -> logits D2H) of one boundary."""
+        inputs = host_in.to(dev)
+        if args.no_graph:
+            step, bufs, runners = step_eager, [inputs, inputs.clone()], [step_eager, step_eager]
+        else:
+            # the whole forward (several hundred launches) is captured once per input buffer
+            g1 = GraphedForward(step_eager, [inputs], warmup=2)
+            g2 = GraphedForward(step_eager, [inputs], warmup=1)
+            inputs = g1.inputs[0]
+            step, bufs, runners = g1, [g1.inputs[0], g2.inputs[0]], [g1, g2]
+        for _ in range(max(args.warmup, 3)):
+            step(inputs)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.start()
+            for _ in range(2):
+                step(inputs)
+        sync_all()
+        wall0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            step(inputs)
+        e1.record()
+        sync_all()
+        wall1 = time.time()
+        clocks = sampler.stop(wall0, wall1) if sampler is not None else None
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / steps
+        # end to end, software-pipelined as a serving loop would run it: two device input buffers (each with its own
+        # captured graph); the H2D copy of step i+1 runs on a copy stream while step i computes.  Every step's H2D copy
+        # from pinned memory and D2H read of the logits are inside the timed region, including the first copy.
+        copy_stream = torch.cuda.Stream()
+        main_stream = torch.cuda.current_stream()
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def run_e2e(n):
+            for i in range(n):
+                k = i & 1
+                with torch.cuda.stream(copy_stream):
+                    if i >= 2:
+                        copy_stream.wait_event(consumed[k])       # the graph that read this buffer has finished
+                    bufs[k].copy_(host_in, non_blocking=True)
+                    copied[k].record(copy_stream)
+                main_stream.wait_event(copied[k])
+                o = runners[k](bufs[k])
+                consumed[k].record(main_stream)
+                host_out.copy_(o[:, 0, :], non_blocking=True)     # what ClassificationPostprocessor keeps (postprocessors.py:187)
+
+        run_e2e(2)
+        sync_all()
+        e0.record()
+        run_e2e(e2e_steps)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / e2e_steps
+        return dict(ms_per_step=ms_step, value=world * B / (ms_step * 1e-3), e2e_ms=e2e_ms,
+                    e2e_value=world * B / (e2e_ms * 1e-3), clocks=clocks, h2d=host_in.numel() * 4, inputs=inputs)
+
+    e2e_steps = max(2, args.e2e_steps)
+    # ---- primary boundary: the call a user of the reference makes, ClassificationPerceiver(img) ----
+    prim = measure(step_image, host_images, args.steps, e2e_steps, sampler=ClockSampler(local))
+    ms_per_step, value, clocks = prim["ms_per_step"], prim["value"], prim["clocks"]
+    e2e_ms, e2e_value = prim["e2e_ms"], prim["e2e_value"]
 
     # ---- per-kernel device times: the same step launched eagerly with the library's own CUDA events around every
     #      kernel launch (events cannot be read back from inside a replayed graph; the kernels, their arguments and
@@ -329,56 +378,21 @@ def run_gpu_arm(args):
     _lib.profile_enable(True)
     n0 = _lib.launch_count()
     for _ in range(prof_steps):
-        step_eager(inputs)
+        step_image(prim["inputs"])
     sync_all()
     _lib.profile_enable(False)
     launches = (_lib.launch_count() - n0) // prof_steps * args.steps
     kern = {k: dict(v, ms_per_step=v["ms"] / prof_steps, launches_per_step=v["launches"] / prof_steps)
             for k, v in _lib.profile_read().items() if v["launches"] > 0}
 
-    # ---- timed region 2: end to end through the module API with host buffers ----
-    # Software-pipelined input feed, as a serving loop would run it: two device input buffers (each with its own
-    # captured graph); the H2D copy of step i+1 runs on a copy stream while step i computes.  Every step's H2D copy
-    # (3.35 GB from pinned memory) and D2H read of the logits are inside the timed region, including the
-    # un-overlapped first copy.
-    e2e_steps = max(2, args.e2e_steps)
-    if args.no_graph:
-        bufs = [inputs, inputs.clone()]
-        runners = [step_eager, step_eager]
-    else:
-        graphed2 = GraphedForward(step_eager, [inputs], warmup=1)
-        bufs = [graphed.inputs[0], graphed2.inputs[0]]
-        runners = [graphed, graphed2]
-    copy_stream = torch.cuda.Stream()
-    main_stream = torch.cuda.current_stream()
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def run_e2e(n):
-        for i in range(n):
-            k = i & 1
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(consumed[k])       # the graph that read this buffer has finished
-                bufs[k].copy_(host_inputs, non_blocking=True)
-                copied[k].record(copy_stream)
-            main_stream.wait_event(copied[k])
-            o = runners[k](bufs[k])
-            consumed[k].record(main_stream)
-            # what ClassificationPostprocessor keeps (postprocessors.py:187)
-            host_out.copy_(o[:, 0, :], non_blocking=True)
-
-    run_e2e(2)
-    sync_all()
-    e0.record()
-    run_e2e(e2e_steps)
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
-    e2e_value = world * B / (e2e_ms * 1e-3)
+    # ---- secondary boundary (earlier rounds' definition): the preprocessed dense array as the input ----
+    dense = None
+    if not args.no_dense_boundary:
+        del prim["inputs"]
+        host_dense = torch.cat([host_images.movedim(-3, -1).reshape(B, H * W, 3),
+                                table.cpu()[None].expand(B, -1, -1)], dim=-1).contiguous().pin_memory()
+        dense = measure(step_dense, host_dense, max(3, args.steps // 2), max(2, e2e_steps // 2))
+        dense.pop("inputs")
 
     if rank != 0:
         if world > 1:
@@ -403,14 +417,18 @@ def run_gpu_arm(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": dict(CFG, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world} (batch axis, no collective)",
-                       l2="inputs (3.35 GB fp32 per step) are larger than L2; no flush needed",
+                       boundary="images [B,3,224,224] -> ImagePreprocessor glue (pixels + 258 Fourier channels, fused into "
+                                "the encoder LayerNorm: SURVEY.md section 8(f) N2) -> PerceiverEncoder -> PerceiverDecoder -> "
+                                "logits; the dense-array boundary of the earlier rounds is reported under dense_boundary",
+                       l2="per step the kernels stream 80 GB through HBM (activations of 48 layers, 1.7 GB of normalised "
+                          "inputs): far larger than L2; no flush needed",
                        precision="bf16 MMA operands, fp32 residual stream / LayerNorm / softmax statistics / accumulators"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "h2d_bytes_per_step": host_inputs.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                "h2d_bytes_per_step": prim["h2d"], "d2h_bytes_per_step": host_out.numel() * 4,
                 "host_numa_node": numa_node,
-                "note": "pinned host input -> H2D (copy stream, double-buffered: overlaps the previous step's compute) -> "
-                        "PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H; PCIe-bound (3.35 GB per step)"},
+                "note": "pinned host images -> H2D (copy stream, double-buffered: overlaps the previous step's compute) -> "
+                        "fused input glue + PerceiverEncoder/PerceiverDecoder forward -> logits[:,0,:] D2H"},
         "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
         "roofline": {"bound": "tensor", "kernel": "pio_gemm2_kernel / pio_gemm_kernel (tcgen05 GEMMs with fused epilogue), all GEMM launches of the step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
@@ -426,6 +444,12 @@ def run_gpu_arm(args):
         "kernels": detail, "kernel_share_of_step": shares,
         "kernel_timing": f"library-side CUDA events around each launch, {prof_steps} eager step(s) after the timed region",
     }
+    if dense is not None:
+        result["dense_boundary"] = {
+            "value": dense["value"], "ms_per_step": dense["ms_per_step"], "unit": "samples/s",
+            "e2e": {"value": dense["e2e_value"], "ms_per_step": dense["e2e_ms"], "h2d_bytes_per_step": dense["h2d"]},
+            "note": "inputs = the preprocessed [B, 50176, 261] fp32 array (3.35 GB per step: its end-to-end leg is "
+                    "PCIe-bound); the definition of value / e2e before the input glue moved onto the device"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = 1
@@ -433,7 +457,8 @@ def run_gpu_arm(args):
             result["cpu_baseline"] = {"value": cb / sec, "unit": "samples/s", "cores": torch.get_num_threads(),
                                       "kind": "port",
                                       "sample": f"{cb} sample of the 64-sample batch, fp32 oracle port of the reference "
-                                                f"forward, 1 warm-up + 2 timed runs, {sec:.2f} s per run"}
+                                                f"forward incl. its input preprocessing, 1 warm-up + 2 timed runs, "
+                                                f"{sec:.2f} s per run"}
         except Exception as ex:  # the baseline must never take the GPU number down
             result["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                       "sample": f"failed: {ex}"}
@@ -452,6 +477,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-dense-boundary", action="store_true", help="skip the secondary (dense input array) measurement")
     args = ap.parse_args()
     _guard_stdout()
     if args.impl == "reference":

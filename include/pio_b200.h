@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 6
+#define PIO_ABI_VERSION 7
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -209,6 +209,28 @@ typedef struct pio_linear_f32_args {
   int32_t N, K;
 } pio_linear_f32_args;
 int pio_linear_f32(const pio_linear_f32_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Input-side glue fused into the encoder's LayerNorm.  The reference's preprocessors build
+ * the encoder input as cat([features [B, N, Cf], broadcast(pos [N, Cp])], -1) (io_processors/preprocessors.py:180-199;
+ * the Fourier table is batch-invariant: position_encoding.py:173-183 uses pos[0] only) and CrossAttention then
+ * normalises it (transformer_primitives.py:379).  This entry point reads the per-sample features (any strides, e.g.
+ * the NCHW image itself) and the [N, Cp] table and writes LayerNorm(cat(...)) as bf16 rows directly: the [B, N, C]
+ * fp32 array (3.35 GB for the ImageNet-pixels recipe at batch 64) is never materialised.
+ *   y[b*N + n, c] = bf16(((x_c - mean) * rstd) * gamma[c] + beta[c]),  x = [feat[b, n, :Cf] | pos[n, :Cp]],
+ *   columns Cf+Cp .. ldy-1 are zeros.  The table part of the statistics is accumulated once per position
+ *   (sum and sum of squares), the feature part per row; mean / variance are combined in fp32.
+ * Needs N % 4 == 0, Cf + Cp <= 1208, ldy = pad8(Cf + Cp), 16-byte aligned pos / y.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_layernorm_concat_args {
+  const float* feat; int64_t feat_stride_b; int64_t feat_stride_n; int64_t feat_stride_c;   /* elements */
+  const float* pos;                      /* [N, Cp] contiguous */
+  void* y; int64_t ldy;                  /* bf16 [B * N, ldy] contiguous rows */
+  const float* gamma; const float* beta; /* [Cf + Cp] or NULL */
+  int32_t B, N, Cf, Cp;
+  float eps;
+} pio_layernorm_concat_args;
+int pio_layernorm_concat_bf16(const pio_layernorm_concat_args* a, void* stream);
 
 /* Per-launch device timing (bench.py's roofline): while enabled, every entry point brackets its kernel launch with
  * CUDA events on the launching stream.  pio_profile_read drains the records into out[family*4 + {ms, flops, bytes,

@@ -193,6 +193,43 @@ def decoder_forward(p: Mapping[str, Tensor], prefix: str, *, num_heads: int, use
 
 
 # ---------------------------------------------------------------------------------------------
+# Input-side glue of the pixels recipe: what the reference's ImagePreprocessor builds as the
+# encoder input.  Restated so that the CPU baseline covers the same boundary as the fused CUDA input path.
+# ---------------------------------------------------------------------------------------------
+
+def linear_positions(index_dims) -> Tensor:
+    """`build_linear_positions` (position_encoding.py:70-89): grid in [-1, 1]^d, shape [prod(index_dims), d]."""
+    ranges = [torch.linspace(-1.0, 1.0, steps=int(n), dtype=torch.float32) for n in index_dims]
+    grid = torch.meshgrid(*ranges, indexing="ij")
+    return torch.stack(grid, dim=-1).reshape(-1, len(index_dims))
+
+
+def fourier_features(pos: Tensor, num_bands: int, max_resolution, concat_pos: bool = True,
+                     sine_only: bool = False) -> Tensor:
+    """`generate_fourier_features` (position_encoding.py:19-67): [n, d] positions -> [n, d (+ 2) * ...] features ordered
+    [pos, sin(pi f x) for every dim and band, cos(pi f x) ...]; bands are linspace(1, res / 2, num_bands)."""
+    freq = torch.stack([torch.linspace(1.0, res / 2, steps=num_bands) for res in max_resolution], dim=0)
+    per_pos = (pos[:, :, None] * freq[None, :, :]).reshape(pos.shape[0], -1)
+    if sine_only:
+        feats = torch.sin(math.pi * per_pos)
+    else:
+        feats = torch.cat([torch.sin(math.pi * per_pos), torch.cos(math.pi * per_pos)], dim=-1)
+    return torch.cat([pos, feats], dim=-1) if concat_pos else feats
+
+
+def image_inputs_pixels(images: Tensor, num_bands: int = 64, max_resolution=(224, 224),
+                        spatial_downsample: int = 1) -> Tensor:
+    """`ImagePreprocessor(prep_type="pixels", concat)` (io_processors/preprocessors.py:239-258 and :180-199): channels
+    last, crude strided downsampling, flatten the index dims, concatenate the (batch-broadcast) Fourier features.
+    images [B, C, H, W] -> [B, H' * W', C + n_pos]."""
+    x = images.movedim(-3, -1)[:, ::spatial_downsample, ::spatial_downsample]
+    b, h, w, c = x.shape
+    feats = x.reshape(b, h * w, c)
+    pos = fourier_features(linear_positions((h, w)), num_bands, max_resolution)
+    return torch.cat([feats, pos[None].expand(b, -1, -1).to(feats.dtype)], dim=-1)
+
+
+# ---------------------------------------------------------------------------------------------
 # Key-axis sharding identity used by the multi-GPU encoder path (SURVEY.md §8e).  The oracle states it
 # on the CPU so the gloo tests can check the host-side combine.
 # ---------------------------------------------------------------------------------------------

@@ -4,6 +4,8 @@ in JOBR0/PerceiverIO_Pytorch.  See DESIGN.md and INTEGRATION.md."""
 from .primitives import Attention, CrossAttention, MLP, SelfAttention, make_cross_attention_mask  # noqa: F401
 from .perceiver import PerceiverDecoder, PerceiverEncoder, TrainablePositionEncoding  # noqa: F401
 from .engine import set_precision  # noqa: F401
+from .inputs import PositionedInput, fourier_position_table, positioned_image_input, perceiver_io_forward  # noqa: F401
 
 __all__ = ["Attention", "MLP", "SelfAttention", "CrossAttention", "make_cross_attention_mask",
-           "PerceiverEncoder", "PerceiverDecoder", "TrainablePositionEncoding", "set_precision"]
+           "PerceiverEncoder", "PerceiverDecoder", "TrainablePositionEncoding", "set_precision",
+           "PositionedInput", "fourier_position_table", "positioned_image_input", "perceiver_io_forward"]

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     "pio_profile_enable", "pio_profile_read",
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
-    "pio_linear_f32",
+    "pio_linear_f32", "pio_layernorm_concat_bf16",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -26,6 +26,12 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 class LayerNormArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
                 ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32), ("split", i32)]
+
+
+class LayerNormConcatArgs(C.Structure):
+    _fields_ = [("feat", vp), ("feat_stride_b", i64), ("feat_stride_n", i64), ("feat_stride_c", i64),
+                ("pos", vp), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
+                ("B", i32), ("N", i32), ("Cf", i32), ("Cp", i32), ("eps", f32)]
 
 
 class GemmArgs(C.Structure):
@@ -106,7 +112,8 @@ def load(build_if_missing: bool = True):
         lib.pio_launch_count.restype = C.c_int64
         for name, argt in (("pio_layernorm_bf16", LayerNormArgs), ("pio_gemm_bf16", GemmArgs),
                            ("pio_softmax_bf16", SoftmaxArgs), ("pio_attention_fwd", AttentionArgs),
-                           ("pio_attention_combine", CombineArgs), ("pio_linear_f32", LinearF32Args)):
+                           ("pio_attention_combine", CombineArgs), ("pio_linear_f32", LinearF32Args),
+                           ("pio_layernorm_concat_bf16", LayerNormConcatArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
@@ -118,7 +125,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 6:
+        if lib.pio_abi_version() != 7:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

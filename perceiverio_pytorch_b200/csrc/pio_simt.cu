@@ -315,6 +315,206 @@ __global__ void __launch_bounds__(LNB_THREADS) pio_layernorm_bulk_kernel(const f
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm of cat([features | position table]) without the concatenated array (pio_layernorm_concat_bf16).
+// A CTA takes groups of R consecutive positions: the R table rows arrive with one bulk copy, the features of all B
+// samples for those positions are gathered into shared memory (with their sums), and then every warp walks the samples
+// for its two positions, writing each normalised row straight from registers.  The table is read once per position
+// group, not once per sample; per row only the Cf feature values and a few scalars change:
+//   y_c = x_c * (gamma_c * rstd) + (beta_c - mean * rstd * gamma_c),  x_c * gamma_c precomputed for the table part,
+//   mean = (S_pos + S_feat) / C,  var = ((Q_pos + Q_feat) - mean (S_pos + S_feat)) / C   (S: sums, Q: sums of squares).
+// HBM-write bound: 2 * ldy bytes per row out, the table and the image are read from L2.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LNC_MAX_FEAT_BYTES = 48 * 1024;
+constexpr int LNC_THREADS = 256;     // 8 warps, two rows of a 16-position group each
+constexpr int LNC_STAGES = 2;        // table stages: one load per R * B output rows, depth hardly matters
+constexpr int LNC_MAX_NP = 18;       // up to 64 * 19 = 1216 columns
+
+// NP = C / 64 pair slots of a lane are always inside the row: slot i holds columns 2 lane + 64 i and the next one, so a
+// warp writes 128 contiguous bytes per instruction straight from registers (no staging, no barrier, no TMA descriptor
+// per 1 KB of output — 1-KB bulk stores capped the first version at one store per ~80 cycles and SM).
+template <int NP>
+__global__ void __launch_bounds__(LNC_THREADS, 3) pio_layernorm_concat_kernel(pio_layernorm_concat_args a, int R,
+                                                                              int ngroups) {
+  pdl_sync();
+  extern __shared__ __align__(128) uint8_t lnb_smem[];
+  const int Cf = a.Cf, Cp = a.Cp, C = Cf + Cp, ldy = (int)a.ldy, B = a.B;
+  const uint32_t in_bytes = (uint32_t)R * (uint32_t)Cp * 4u;         // multiple of 16 (R % 4 == 0)
+  const uint32_t in_pitch = (in_bytes + 127u) & ~127u;
+  const uint32_t feat_bytes = ((uint32_t)B * (uint32_t)R * (uint32_t)Cf * 4u + 127u) & ~127u;
+  uint8_t* in_buf = lnb_smem;
+  float* feat = reinterpret_cast<float*>(in_buf + LNC_STAGES * in_pitch);   // [B][R][Cf]
+  float2* fstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(feat) + feat_bytes);   // [B][R] (sum, sum of squares)
+  uint64_t* full = reinterpret_cast<uint64_t*>(fstat + (size_t)B * R);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int my_groups = (ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto issue_load = [&](int i) {
+    const long long g = blockIdx.x + (long long)i * gridDim.x;
+    const int s = i % LNC_STAGES;
+    mbar_arrive_expect_tx(&full[s], in_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(in_buf + s * in_pitch)), "l"(reinterpret_cast<uint64_t>(a.pos) + (uint64_t)g * in_bytes),
+                 "r"(in_bytes), "r"(smem_u32(&full[s]))
+                 : "memory");
+  };
+  if (tid == 0) {
+    for (int s = 0; s < LNC_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    if (my_groups > 0) issue_load(0);
+  }
+  // pair slot i of a lane: columns c0 = 2 lane + 64 i and c0 + 1 of the concatenated row — a feature (c < Cf), table
+  // column c - Cf, or zero pad (C <= c < ldy: gamma = beta = 0)
+  float g[NP + 1][2], bt[NP + 1][2];
+#pragma unroll
+  for (int i = 0; i <= NP; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 2 * lane + 64 * i + e;
+      g[i][e] = (c < C) ? (a.gamma ? __ldg(a.gamma + c) : 1.f) : 0.f;
+      bt[i][e] = (a.beta && c < C) ? __ldg(a.beta + c) : 0.f;
+    }
+  uint64_t g2[NP + 1], bt2[NP + 1];
+#pragma unroll
+  for (int i = 0; i <= NP; ++i) {
+    g2[i] = pack_f32x2(g[i][0], g[i][1]);
+    bt2[i] = pack_f32x2(bt[i][0], bt[i][1]);
+  }
+  const bool few_feat = Cf <= 64;          // the usual case (3 pixel channels): only slot 0 can hold features
+  const float inv_c = 1.0f / (float)C;
+  const bool t_out = 64 * NP + 2 * lane < ldy;
+  __syncthreads();
+  for (int it = 0; it < my_groups; ++it) {
+    const int s = it % LNC_STAGES;
+    const long long n0 = (blockIdx.x + (long long)it * gridDim.x) * R;
+    // One thread per (sample, position): consecutive threads read consecutive positions of one channel, and the
+    // feature part of the row statistics is formed here, off the sample loop.
+    if (Cf <= 4) {
+      // up to 16 loads of a thread are in flight before the first one is consumed
+      for (int idx0 = tid; idx0 < B * R; idx0 += 4 * LNC_THREADS) {
+        float f[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = idx0 + u * LNC_THREADS;
+          const int r = idx % R, b = idx / R;
+          const float* src = a.feat + (long long)b * a.feat_stride_b + (n0 + r) * a.feat_stride_n;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            f[u][c] = (idx < B * R && c < Cf) ? __ldg(src + (long long)c * a.feat_stride_c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = idx0 + u * LNC_THREADS;
+          if (idx < B * R) {
+            float sf = 0.f, qf = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < Cf) feat[(long long)idx * Cf + c] = f[u][c];
+              sf += f[u][c];
+              qf = fmaf(f[u][c], f[u][c], qf);
+            }
+            fstat[idx] = make_float2(sf, qf);
+          }
+        }
+      }
+    } else {
+      for (int idx = tid; idx < B * R; idx += LNC_THREADS) {
+        const int r = idx % R, b = idx / R;
+        const float* src = a.feat + (long long)b * a.feat_stride_b + (n0 + r) * a.feat_stride_n;
+        float* dst = feat + (long long)idx * Cf;
+        float sf = 0.f, qf = 0.f;
+        for (int c = 0; c < Cf; ++c) {
+          const float f = __ldg(src + (long long)c * a.feat_stride_c);
+          dst[c] = f;
+          sf += f;
+          qf = fmaf(f, f, qf);
+        }
+        fstat[idx] = make_float2(sf, qf);
+      }
+    }
+    if (tid == 0 && it + 1 < my_groups) issue_load(it + 1);   // its stage was last read in iteration it - 1
+    mbar_wait(&full[s], (uint32_t)((it / LNC_STAGES) & 1));
+    __syncthreads();
+    const float* in = reinterpret_cast<const float*>(in_buf + s * in_pitch);
+    // this warp's rows of the group: r = 2 warp, 2 warp + 1 (R <= 16); the table part of the rows (times gamma) and its
+    // statistics stay in registers across the sample loop
+    constexpr int MAXROWS = 2;
+    const int r0 = 2 * warp;
+    const bool active = r0 < R;          // R is a multiple of 4
+    float pg[MAXROWS][NP + 1][2];
+    float s_pos[MAXROWS], q_pos[MAXROWS];
+#pragma unroll
+    for (int k = 0; k < MAXROWS; ++k) {
+      const int r = r0 + k;
+      float sp = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i <= NP; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * lane + 64 * i + e;
+          const float p = (active && c >= Cf && c < C) ? in[r * Cp + (c - Cf)] : 0.f;
+          sp += p;
+          sq = fmaf(p, p, sq);
+          pg[k][i][e] = p * g[i][e];
+        }
+      s_pos[k] = warp_sum(sp);
+      q_pos[k] = warp_sum(sq);
+    }
+    uint64_t pg2[MAXROWS][NP + 1];
+#pragma unroll
+    for (int k = 0; k < MAXROWS; ++k)
+#pragma unroll
+      for (int i = 0; i <= NP; ++i) pg2[k][i] = pack_f32x2(pg[k][i][0], pg[k][i][1]);
+    if (active) {
+      for (int b = 0; b < B; ++b) {
+#pragma unroll
+        for (int k = 0; k < MAXROWS; ++k) {
+          const int r = r0 + k;
+          const float* fr = feat + ((long long)b * R + r) * Cf;
+          // mean and variance from the two partial (sum, sum of squares) pairs: sum (x - mean)^2 = Q - mean S
+          const float2 fs = fstat[b * R + r];
+          const float ssum = s_pos[k] + fs.x;
+          const float mean = ssum * inv_c;
+          const float var = ((q_pos[k] + fs.y) - mean * ssum) * inv_c;
+          const float rstd = rsqrtf(fmaxf(var, 0.f) + a.eps);
+          const float nmr = -mean * rstd;
+          uint32_t* yr = reinterpret_cast<uint32_t*>(y + ((long long)b * a.N + n0 + r) * ldy) + lane;
+          const uint64_t nmr2 = pack_f32x2(nmr, nmr), rstd2 = pack_f32x2(rstd, rstd);
+#pragma unroll
+          for (int i = 0; i <= NP; ++i) {
+            if (i < NP || t_out) {
+              uint64_t x2 = pg2[k][i];
+              if (i == 0 || !few_feat) {   // slots that can hold features
+                const int c = 2 * lane + 64 * i;
+                if (c < Cf) {
+                  float x0, x1;
+                  unpack_f32x2(x2, x0, x1);
+                  x0 = fr[c] * g[i][0];
+                  if (c + 1 < Cf) x1 = fr[c + 1] * g[i][1];
+                  x2 = pack_f32x2(x0, x1);
+                }
+              }
+              // two packed fp32x2 FMAs per column pair: x * rstd + (-mean * rstd * gamma + beta)
+              float y0, y1;
+              unpack_f32x2(ffma2(x2, rstd2, ffma2(nmr2, g2[i], bt2[i])), y0, y1);
+              yr[32 * i] = pack_bf16x2(y0, y1);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with this group's table stage and features
+  }
+}
+
+using lnc_kernel_t = void (*)(pio_layernorm_concat_args, int, int);
+template <int... I>
+static const lnc_kernel_t* lnc_kernel_table(std::integer_sequence<int, I...>) {
+  static const lnc_kernel_t table[] = {pio_layernorm_concat_kernel<I>...};
+  return table;
+}
+
 using lnb_kernel_t = void (*)(const float*, __nv_bfloat16*, int, const float*, const float*, long long, int, int, int, float);
 constexpr int LNB_MAX_NFULL = 36;
 template <int... I>
@@ -770,6 +970,58 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     else if (need <= 40) PIO_LN_LAUNCH(40, 1);
     else PIO_LN_LAUNCH(64, 1);
 #undef PIO_LN_LAUNCH
+  }
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
+}
+
+extern "C" int pio_layernorm_concat_bf16(const pio_layernorm_concat_args* a, void* stream_) {
+  using namespace pio;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PIO_REQUIRE(a && a->feat && a->pos && a->y, "pio_layernorm_concat_bf16: null pointer");
+  PIO_REQUIRE(a->B > 0 && a->N > 0 && a->Cf > 0 && a->Cp > 0, "pio_layernorm_concat_bf16: bad shape");
+  const int C = a->Cf + a->Cp;
+  PIO_REQUIRE(a->ldy == (C + 7) / 8 * 8, "pio_layernorm_concat_bf16: ldy must be pad8(Cf + Cp)");
+  PIO_REQUIRE(C / 64 <= LNC_MAX_NP && a->ldy <= 64 * (C / 64 + 1),
+              "pio_layernorm_concat_bf16: at most %d channels", 64 * (LNC_MAX_NP + 1) - 8);
+  PIO_REQUIRE(a->N % 4 == 0, "pio_layernorm_concat_bf16: the number of positions must be a multiple of 4 (got %d)", a->N);
+  PIO_REQUIRE(aligned16(a->pos) && aligned16(a->y), "pio_layernorm_concat_bf16: pos / y must be 16-byte aligned");
+  DeviceInfo dev;
+  int rc = get_device_info(&dev);
+  if (rc != PIO_OK) return rc;
+  // rows per position group: divides N, at most 16 (four per warp), table stage <= ~17 KB, feature gather <= 48 KB
+  int R = 16;
+  while (R > 4 && (a->N % R != 0 || (long long)R * a->Cp * 4 > 17 * 1024 ||
+                   (long long)a->B * R * a->Cf * 4 > LNC_MAX_FEAT_BYTES))
+    R -= 4;
+  PIO_REQUIRE(a->N % R == 0 && (long long)a->B * R * a->Cf * 4 <= LNC_MAX_FEAT_BYTES && (long long)R * a->Cp * 4 <= 40 * 1024,
+              "pio_layernorm_concat_bf16: batch x features (%d x %d) or table width (%d) too large for one position group",
+              a->B, a->Cf, a->Cp);
+  const int ngroups = a->N / R;
+  const size_t in_pitch = ((size_t)R * a->Cp * 4 + 127) & ~(size_t)127;
+  const size_t feat_bytes = ((size_t)a->B * R * a->Cf * 4 + 127) & ~(size_t)127;
+  const size_t smem = LNC_STAGES * in_pitch + feat_bytes + (size_t)a->B * R * 8 + 64;
+  PIO_REQUIRE(smem <= 200 * 1024, "pio_layernorm_concat_bf16: shared memory budget exceeded (%zu bytes)", smem);
+  const lnc_kernel_t kern = lnc_kernel_table(std::make_integer_sequence<int, LNC_MAX_NP + 1>{})[C / 64];
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    const lnc_kernel_t* table = lnc_kernel_table(std::make_integer_sequence<int, LNC_MAX_NP + 1>{});
+    for (int i = 0; i <= LNC_MAX_NP && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(layernorm_concat) failed: %s", cudaGetErrorString(attr_err));
+  int ctas_per_sm = (int)(200 * 1024 / (smem + 1024));
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  long long blocks = (long long)dev.sm_count * ctas_per_sm;
+  if (blocks > ngroups) blocks = ngroups;
+  {
+    ProfileScope prof(KF_LAYERNORM, 0.0,
+                      (double)a->B * a->N * (4.0 * a->Cf + 2.0 * a->ldy) + (double)a->N * a->Cp * 4.0, stream);
+    PIO_CUDA_OK(launch_kernel(kern, dim3((unsigned)blocks), dim3(LNC_THREADS), smem, stream, 1, *a, R, ngroups));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());

@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from .inputs import PositionedInput
 from .ops import BF16, pad8
 
 # Arithmetic mode: "bf16" (default: bf16 MMA operands, fp32 everything else) or "bf16x3" (validation precision: bf16 x 2
@@ -462,10 +463,20 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     B, Nq, Cq = inputs_q.shape
     Nk, Ck = inputs_kv.shape[1], inputs_kv.shape[2]
     q_bcast = B > 1 and inputs_q.stride(0) == 0
-    if inputs_kv.stride(2) != 1 or inputs_kv.stride(0) != Nk * inputs_kv.stride(1):
-        inputs_kv = inputs_kv.contiguous()
-    kvn = ops.layernorm_bf16(inputs_kv.view(B * Nk, Ck) if inputs_kv.is_contiguous()
-                             else inputs_kv.reshape(B * Nk, Ck), ln_kv.weight, ln_kv.bias)
+    if isinstance(inputs_kv, PositionedInput):
+        # features + batch-invariant position table: normalised without building the concatenated array (inputs.py)
+        cf, cp = inputs_kv.features.shape[2], inputs_kv.pos.shape[1]
+        if ops.layernorm_concat_supported(B, Nk, cf, cp):
+            kvn = ops.layernorm_concat_bf16(inputs_kv.features, inputs_kv.pos, ln_kv.weight, ln_kv.bias, eps=ln_kv.eps)
+        else:
+            inputs_kv = inputs_kv.dense()
+    if isinstance(inputs_kv, PositionedInput):
+        pass
+    else:
+        if inputs_kv.stride(2) != 1 or inputs_kv.stride(0) != Nk * inputs_kv.stride(1):
+            inputs_kv = inputs_kv.contiguous()
+        kvn = ops.layernorm_bf16(inputs_kv.view(B * Nk, Ck) if inputs_kv.is_contiguous()
+                                 else inputs_kv.reshape(B * Nk, Ck), ln_kv.weight, ln_kv.bias)
     q_src = inputs_q[0] if q_bcast else (inputs_q if inputs_q.is_contiguous() else inputs_q.contiguous()).view(B * Nq, Cq)
     if q_src.stride(-1) != 1:
         q_src = q_src.contiguous()

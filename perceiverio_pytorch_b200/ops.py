@@ -65,6 +65,33 @@ def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optiona
     return out
 
 
+def layernorm_concat_supported(B: int, N: int, Cf: int, Cp: int) -> bool:
+    """Shapes pio_layernorm_concat_bf16 covers (include/pio_b200.h)."""
+    if N % 4 != 0 or Cf <= 0 or Cp <= 0 or Cf + Cp > 1208:
+        return False
+    r = 16
+    while r > 4 and (N % r != 0 or r * Cp * 4 > 17 * 1024 or B * r * Cf * 4 > 48 * 1024):
+        r -= 4
+    return N % r == 0 and B * r * Cf * 4 <= 48 * 1024 and r * Cp * 4 <= 40 * 1024
+
+
+def layernorm_concat_bf16(feat: torch.Tensor, pos: torch.Tensor, gamma: Optional[torch.Tensor],
+                          beta: Optional[torch.Tensor], *, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm(cat([feat [B, N, Cf] (any strides), pos [N, Cp] broadcast over the batch], -1)) -> bf16
+    [B * N, pad8(Cf + Cp)] without materialising the concatenated array."""
+    _need_cuda(feat, pos, gamma, beta)
+    assert feat.dtype == torch.float32 and pos.dtype == torch.float32 and feat.dim() == 3 and pos.dim() == 2
+    B, N, Cf = feat.shape
+    assert pos.shape[0] == N and pos.is_contiguous()
+    Cp = pos.shape[1]
+    ldy = pad8(Cf + Cp)
+    out = torch.empty((B * N, ldy), dtype=BF16, device=feat.device)
+    a = _lib.LayerNormConcatArgs(_ptr(feat), feat.stride(0), feat.stride(1), feat.stride(2), _ptr(pos), _ptr(out), ldy,
+                                 _ptr(gamma), _ptr(beta), B, N, Cf, Cp, eps)
+    _lib.check(_lib.load().pio_layernorm_concat_bf16(C.byref(a), _stream()), "pio_layernorm_concat_bf16")
+    return out
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int = 1, b_mn_major: bool = False,
          strideA: int = 0, strideB: int = 0, lda: Optional[int] = None, ldb: Optional[int] = None,
          bias: Optional[torch.Tensor] = None, bias_mode: int = 1, act: int = 0, alpha: float = 1.0,

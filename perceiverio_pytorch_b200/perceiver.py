@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import engine, ops, validate
+from .inputs import PositionedInput
 from .primitives import CrossAttention, SelfAttention, lecun_normal_, make_cross_attention_mask  # noqa: F401
 
 
@@ -83,6 +84,8 @@ class PerceiverEncoder(nn.Module):
         ops._need_cuda(inputs, latents)
         if latents.shape[0] == 0 or latents.shape[1] == 0:   # empty batch / no latents: nothing to launch
             return latents.new_empty(latents.shape)
+        if isinstance(inputs, PositionedInput) and (engine.PRECISION != "bf16" or self.cache_latents):
+            inputs = inputs.dense()   # the validation precision and the latent cache work on the dense array
         key_mask = None
         row_keep = None
         if input_mask is not None:

@@ -111,3 +111,23 @@ def test_key_shard_combine_identity():
     parts = [O.attend_partial(q, k[:, s], v[:, s], km[:, s]) for s in (slice(0, 25), slice(25, 37), slice(37, 50))]
     merged = O.combine_partials(parts).permute(0, 2, 1, 3).reshape(2, 9, 10)
     assert float((merged - full).abs().max()) < 1e-12
+
+
+def test_oracle_image_preprocessing_matches_reference():
+    """The input-side glue of the pixels recipe restated in the oracle."""
+    ref = ref_shim.load_wrappers()
+    if ref is None:
+        pytest.skip("reference tree not mounted")
+    import importlib
+    prep_mod = importlib.import_module("perceiver_io.io_processors.preprocessors")
+    pe = importlib.import_module("perceiver_io.position_encoding")
+    torch.manual_seed(0)
+    for (h, w), sd in (((16, 12), 1), ((224, 224), 1), ((32, 32), 2)):
+        prep = prep_mod.ImagePreprocessor(img_size=(h, w), input_channels=3, prep_type="pixels", spatial_downsample=sd,
+                                          position_encoding_type=pe.PosEncodingType.FOURIER,
+                                          fourier_position_encoding_kwargs=dict(concat_pos=True, max_resolution=(224, 224),
+                                                                                num_bands=64, sine_only=False))
+        img = torch.randn(2, 3, h, w)
+        want, want_nopos = prep(img)
+        got = O.image_inputs_pixels(img, 64, (224, 224), sd)
+        assert got.shape == want.shape and torch.equal(got, want)
