@@ -184,7 +184,8 @@ def run_reference_arm(args):
     batch = 1
     sec = time_cpu(batch, args.warmup, args.steps)
     v = batch / sec
-    sample = f"{batch} sample(s) of the 64-sample batch per step, fp32, torch CPU ops, {torch.get_num_threads()} threads"
+    sample = (f"{batch} sample(s) of the 64-sample batch per step, fp32, torch CPU ops, {torch.get_num_threads()} threads; "
+              "each step rebuilds the Fourier table and the concatenated input array as the reference does")
     _emit({
         "impl": "reference", "metric": "samples/sec per forward", "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
