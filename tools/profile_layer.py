@@ -1,4 +1,4 @@
-"""ncu target: the encoder cross-attend and two latent-tower layers (the LayerNorm-fused path) at the ImageNet-recipe
+"""ncu target: the fused input LayerNorm, the encoder cross-attend and two latent-tower layers (the LayerNorm-fused path) at the ImageNet-recipe
 shapes, launched eagerly twice.  Run plain first, then under `ncu --set full -k regex:pio_`."""
 import os
 import sys
@@ -12,9 +12,12 @@ torch.manual_seed(0)
 B = int(os.environ.get("PIO_PROFILE_BATCH", "64"))
 enc = pio.PerceiverEncoder(num_input_channels=261, num_self_attends_per_block=2, num_blocks=1, num_latents=512,
                            num_latent_channels=1024).eval().cuda()
-inputs = torch.randn(B, 50176, 261, device="cuda")
+images = torch.randn(B, 3, 224, 224, device="cuda")
+table = pio.fourier_position_table((224, 224), 64, device="cuda")
 with torch.inference_mode():
     for _ in range(2):
+        # the image boundary of bench.py: pixels + Fourier table fused into the encoder's LayerNorm
+        inputs = pio.PositionedInput(images.movedim(-3, -1).reshape(B, 224 * 224, 3), table)
         z = enc(inputs, enc.latents(inputs))
 torch.cuda.synchronize()
 print("ok", float(z.abs().mean()))
