@@ -93,15 +93,12 @@ def fourier_position_table(index_dims: Sequence[int], num_bands: int, max_resolu
     return feats.to(device) if device is not None else feats
 
 
-_TABLE_CACHE = {}
-
-
 def positioned_image_input(preprocessor, images: torch.Tensor, pos=None) -> Optional[PositionedInput]:
     """`PositionedInput` for a reference ``ImagePreprocessor`` (io_processors/preprocessors.py:57-258) and a batch of
     images already on the device, or None when the preprocessor's configuration is not a plain concatenation of
     per-sample features with a batch-invariant table (``concat_or_add_pos == "add"``, extra position MLPs).  The
     features are produced by the preprocessor's own layers (:216-253); the table by its own position-encoding module,
-    once per (module, device) when ``pos`` is None."""
+    once per (module, device) when ``pos`` is None and the encoding has no parameters."""
     if getattr(preprocessor, "_concat_or_add_pos", None) != "concat" or getattr(preprocessor, "_n_extra_pos_mlp", 0) != 0:
         return None
     prep = preprocessor._prep_type
@@ -124,8 +121,20 @@ def positioned_image_input(preprocessor, images: torch.Tensor, pos=None) -> Opti
             x = x[:, ::td, ::sd, ::sd]
         else:
             raise ValueError("Unsupported data format for pixels.")
+    elif prep == "patches":
+        # the preprocessor module's own space_to_depth (processor_utils.py:21-40) and optional projection (:243-249)
+        import sys
+        s2d = getattr(sys.modules.get(type(preprocessor).__module__), "space_to_depth", None)
+        if s2d is None:
+            return None
+        x = s2d(x.movedim(-3, -1), temporal_block_size=preprocessor._temporal_downsample,
+                spatial_block_size=preprocessor._spatial_downsample)
+        if x.ndim == 5 and x.shape[1] == 1:
+            x = torch.squeeze(x, dim=1)
+        if preprocessor._conv_after_patching:
+            x = preprocessor._conv_after_patch_layer(x)
     else:
-        return None   # "patches" goes through einops space_to_depth in the reference: left to the reference's own path
+        return None
     batch = x.shape[0]
     n = 1
     for d in preprocessor.index_dims:
@@ -134,13 +143,13 @@ def positioned_image_input(preprocessor, images: torch.Tensor, pos=None) -> Opti
     enc = preprocessor._positional_encoding
     # the encodings are batch-invariant by construction (position_encoding.py:119-121, :173-184 use pos[0] only)
     static = pos is None and not any(True for _ in enc.parameters())
-    key = (id(enc), str(feats.device))
-    table = _TABLE_CACHE.get(key) if static else None
+    cache = enc.__dict__.setdefault("_pio_position_table", {}) if static else None   # lives and dies with the module
+    table = cache.get(str(feats.device)) if static else None
     if table is None:
         with torch.no_grad():
             table = enc(batch_size=1, pos=pos)[0].to(feats.device).float().contiguous()
         if static:
-            _TABLE_CACHE[key] = table
+            cache[str(feats.device)] = table
     return PositionedInput(feats, table)
 
 

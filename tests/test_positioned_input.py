@@ -94,6 +94,46 @@ def test_whole_wrapper_glue_on_live_reference():
         assert torch.allclose(got, want, atol=1e-6, rtol=1e-6) and torch.equal(got, got2)
 
 
+def test_positioned_image_input_matches_reference_preprocessors():
+    """Every single-modality image preprocessor configuration with a concatenated position encoding: the two parts of
+    the PositionedInput, densified, are exactly what the reference's ImagePreprocessor returns."""
+    from oracle import ref_shim
+    if ref_shim.load_wrappers() is None:
+        pytest.skip("reference tree not mounted")
+    import importlib
+    prep_mod = importlib.import_module("perceiver_io.io_processors.preprocessors")
+    pe = importlib.import_module("perceiver_io.position_encoding")
+    four = dict(position_encoding_type=pe.PosEncodingType.FOURIER,
+                fourier_position_encoding_kwargs=dict(concat_pos=True, max_resolution=(32, 32), num_bands=8,
+                                                      sine_only=False))
+    train = dict(position_encoding_type=pe.PosEncodingType.TRAINABLE,
+                 trainable_position_encoding_kwargs=dict(init_scale=0.02, num_channels=24))
+    torch.manual_seed(0)
+    cases = [
+        (dict(img_size=(32, 32), prep_type="pixels", spatial_downsample=1, **four), (2, 3, 32, 32)),
+        (dict(img_size=(32, 32), prep_type="pixels", spatial_downsample=2, **four), (2, 3, 32, 32)),
+        (dict(img_size=(32, 32), prep_type="conv1x1", spatial_downsample=1, num_channels=16, **train), (2, 3, 32, 32)),
+        (dict(img_size=(32, 32), prep_type="conv", spatial_downsample=4, num_channels=16, **four), (2, 3, 32, 32)),
+        # the optical-flow recipe: 3x3 patches of two frames stacked in the channel axis, projected (flow_perceiver.py:47-66)
+        (dict(img_size=(16, 24), input_channels=27, prep_type="patches", spatial_downsample=1,
+              temporal_downsample=2, conv_after_patching=True, num_channels=64, **four), (2, 2, 27, 16, 24)),
+    ]
+    for kw, shape in cases:
+        prep = prep_mod.ImagePreprocessor(**kw).eval()
+        x = torch.randn(*shape)
+        with torch.inference_mode():
+            want, want_nopos = prep(x)
+            pin = pio.positioned_image_input(prep, x)
+        assert pin is not None, kw["prep_type"]
+        assert pin.shape == want.shape
+        assert torch.equal(pin.dense(), want), kw["prep_type"]
+        assert torch.equal(pin.features, want_nopos)
+    add = prep_mod.ImagePreprocessor(img_size=(32, 32), prep_type="pixels", spatial_downsample=1, concat_or_add_pos="add",
+                                     position_encoding_type=pe.PosEncodingType.TRAINABLE,
+                                     trainable_position_encoding_kwargs=dict(init_scale=0.02, num_channels=3))
+    assert pio.positioned_image_input(add, torch.randn(1, 3, 32, 32)) is None     # not a concatenation: left to the reference
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,W,Cf,Cp", [(3, 8, 12, 3, 258), (2, 16, 16, 3, 10), (1, 4, 8, 64, 258), (5, 6, 6, 7, 29)])
 def test_fused_concat_layernorm_matches_dense_path(B, H, W, Cf, Cp):
