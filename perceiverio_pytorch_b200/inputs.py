@@ -154,10 +154,15 @@ def positioned_image_input(preprocessor, images: torch.Tensor, pos=None) -> Opti
 
 
 def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_points=None, input_mask=None,
-                         query_mask=None):
+                         query_mask=None, only_needed_queries: bool = False):
     """`PerceiverIO.forward` (perceiver.py:287-325) for a single image modality with the input glue fused: the
     preprocessor's features and position table reach the encoder as a `PositionedInput`.  Falls back to the module's
-    own forward whenever the configuration is not covered (several modalities, channel padding, modality masking)."""
+    own forward whenever the configuration is not covered (several modalities, channel padding, modality masking).
+
+    only_needed_queries (off by default): the classification wrapper decodes 1000 output
+    queries and its postprocessor keeps query 0 only (postprocessors.py:187).  Decoder rows do not interact (each query
+    attends over the latents and goes through the MLP and the final projection on its own), so decoding just the kept
+    row gives the same logits for 1/1000 of the decoder work."""
     mp = perceiver._multi_preprocessor
     preps = getattr(mp, "_preprocessors", None) if mp is not None else None
     if (type(inputs) is not torch.Tensor or preps is None or list(preps.keys()) != ["__default"]
@@ -173,6 +178,12 @@ def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_p
     decoder_query, query_sizes = perceiver.decoder_query(pin, sizes, {"__default": pin.features},
                                                          subsampled_points=subsampled_output_points)
     latents = perceiver._encoder(pin, encoder_query, input_mask=input_mask)
+    posts = perceiver._output_postprocessors
+    if (only_needed_queries and posts and list(posts.keys()) == ["__default"]
+            and type(posts["__default"]).__name__ == "ClassificationPostprocessor" and decoder_query.shape[1] >= 1):
+        decoder_query = decoder_query[:, :1]
+        query_mask = None if query_mask is None else query_mask[:, :1]
+        query_sizes = {"__default": 1}
     outputs = perceiver._decoder(decoder_query, latents, query_mask=query_mask)
     if perceiver._output_postprocessors:
         if type(outputs) is torch.Tensor:

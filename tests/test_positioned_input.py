@@ -92,6 +92,11 @@ def test_whole_wrapper_glue_on_live_reference():
         assert seen == ["PositionedInput", "PositionedInput"], seen
         assert got.shape == want.shape
         assert torch.allclose(got, want, atol=1e-6, rtol=1e-6) and torch.equal(got, got2)
+        with torch.inference_mode():   # N3: decode only the query row the postprocessor keeps
+            pruned = pin_mod.perceiver_io_forward(model.perceiver, img, only_needed_queries=True)
+        # same modules, one query row instead of 1000: only the BLAS re-association differs
+        assert pruned.shape == want.shape
+        assert float((pruned - want).abs().max()) <= 2e-5 * float(want.abs().max()), float((pruned - want).abs().max())
 
 
 def test_positioned_image_input_matches_reference_preprocessors():
