@@ -79,8 +79,18 @@ def _decoder_from_reference(dec: nn.Module) -> _perceiver.PerceiverDecoder:
     return new.to(next(dec.parameters()).device).eval()
 
 
-def swap_hot_path(model: nn.Module) -> nn.Module:
-    """Replace every reference PerceiverEncoder / PerceiverDecoder inside `model` by its B200 drop-in."""
+def swap_hot_path(model: nn.Module, fuse_input: bool = False) -> nn.Module:
+    """Replace every reference PerceiverEncoder / PerceiverDecoder inside `model` by its B200 drop-in.
+
+    fuse_input: additionally route every `PerceiverIO.forward` inside `model` through `inputs.perceiver_io_forward`, which
+    keeps the preprocessor's features and position table apart whenever the configuration
+    allows it and otherwise calls the module's own forward — `model(img)` keeps working unchanged either way."""
+    if fuse_input:
+        import functools
+        from . import inputs as _inputs
+        for m in model.modules():
+            if type(m).__name__ == "PerceiverIO" and "forward" not in m.__dict__:
+                m.forward = functools.partial(_inputs.perceiver_io_forward, m)
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             cls = type(child).__name__

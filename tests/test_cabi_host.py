@@ -182,6 +182,7 @@ def test_swap_hot_path_on_live_reference_keeps_state_dict():
     torch.manual_seed(0)
     model = ns.language.LanguagePerceiver(num_self_attends_per_block=2, num_latents=32, num_latent_channels=64).eval()
     before = {k: v.clone() for k, v in model.state_dict().items()}
+    enc_ref, dec_ref = model.perceiver._encoder, model.perceiver._decoder
     install.swap_hot_path(model)
     assert isinstance(model.perceiver._encoder, pio.PerceiverEncoder)
     assert isinstance(model.perceiver._decoder, pio.PerceiverDecoder)
@@ -189,3 +190,15 @@ def test_swap_hot_path_on_live_reference_keeps_state_dict():
     assert list(after.keys()) == list(before.keys())
     for k in before:
         assert torch.equal(before[k], after[k]), k
+    # fuse_input patches PerceiverIO.forward on the instance only; the language model's embedding preprocessor is not an
+    # image preprocessor, so the patched forward must fall back to the class's own forward (no recursion)
+    install.swap_hot_path(model, fuse_input=True)
+    assert "forward" in model.perceiver.__dict__ and list(model.state_dict().keys()) == list(before.keys())
+    model.perceiver._encoder, model.perceiver._decoder = enc_ref, dec_ref      # reference modules back: runs on CPU
+    with torch.inference_mode():
+        ids = torch.randint(6, 262, (1, 2048))          # the recipe's fixed sequence length (language_perceiver.py:24-46)
+        mask = torch.ones(1, 2048, dtype=torch.bool)
+        out_patched = model(ids, mask)
+        del model.perceiver.__dict__["forward"]
+        out_plain = model(ids, mask)
+    assert torch.equal(out_patched, out_plain)
