@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 7
+#define PIO_ABI_VERSION 8
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -114,6 +114,9 @@ typedef struct pio_gemm_args {
   const float* ln_colsum;     /* [N], required with row_stats_in */
   int32_t ln_channels;
   float ln_eps;
+  /* Walk the output tiles from the last M rows to the first (CTA-pair kernel; ignored by the single-CTA kernel).  A
+   * consumer that starts where its producer finished finds that producer's last-written rows still in L2. */
+  int32_t reverse_tiles;
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 

@@ -46,7 +46,8 @@ class GemmArgs(C.Structure):
                 ("out_f32", vp), ("ldo32", i64), ("strideO32", i64),
                 ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
                 ("tile_n", i32), ("max_ctas", i32), ("cluster_m", i32), ("kernel", i32),
-                ("row_stats_out", vp), ("row_stats_in", vp), ("ln_colsum", vp), ("ln_channels", i32), ("ln_eps", f32)]
+                ("row_stats_out", vp), ("row_stats_in", vp), ("ln_colsum", vp), ("ln_channels", i32), ("ln_eps", f32),
+                ("reverse_tiles", i32)]
 
 
 class SoftmaxArgs(C.Structure):
@@ -125,7 +126,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 7:
+        if lib.pio_abi_version() != 8:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

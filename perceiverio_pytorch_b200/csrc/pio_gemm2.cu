@@ -31,6 +31,7 @@ struct Gemm2Params {
   float alpha;
   int has_residual;
   int b_swap;                    // debug: which CTA of the pair stages which half of the B tile
+  int reverse;                   // walk the tiles from the last M rows to the first (pio_gemm_args.reverse_tiles)
   // LayerNorm fusion (pio_gemm_args): producer side ...
   float* row_stats_out;          // [M][2] += (sum, sum of squares) of the final fp32 rows
   __nv_bfloat16* raw_bf16;       // bf16 copy of the fp32 output (un-normalised rows), row pitch ld_raw
@@ -144,7 +145,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // (the whole warp runs the schedule and waits; one elected lane issues — keeps coordinates in uniform registers)
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = pair_id; t < total_tiles; t += num_pairs) {
+    for (int seq = pair_id; seq < total_tiles; seq += num_pairs) {
+      const int t = p.reverse ? total_tiles - 1 - seq : seq;
       const int nt = t % p.tiles_n;
       const int mp = (t / p.tiles_n) % p.m_pairs;
       const int z = t / (p.tiles_n * p.m_pairs);
@@ -219,9 +221,10 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t pf_idx = 0;
     auto issue_res = [&]() {
       if (pf_t >= total_tiles) return;
-      const int nt = pf_t % p.tiles_n;
-      const int mp = (pf_t / p.tiles_n) % p.m_pairs;
-      const int z = pf_t / (p.tiles_n * p.m_pairs);
+      const int t = p.reverse ? total_tiles - 1 - pf_t : pf_t;
+      const int nt = t % p.tiles_n;
+      const int mp = (t / p.tiles_n) % p.m_pairs;
+      const int z = t / (p.tiles_n * p.m_pairs);
       const int row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
       const int col = nt * Cfg::BN + half * 128 + pf_c * CHUNK_COLS;
       const uint32_t slot = pf_idx % (uint32_t)RS;
@@ -235,7 +238,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     uint32_t use_idx = 0;
     int it = 0;
-    for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+    for (int seq = pair_id; seq < total_tiles; seq += num_pairs, ++it) {
+      const int t = p.reverse ? total_tiles - 1 - seq : seq;
       const int nt = t % p.tiles_n;
       const int mp = (t / p.tiles_n) % p.m_pairs;
       const int z = t / (p.tiles_n * p.m_pairs);
@@ -467,6 +471,7 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.bias = a->bias; p.bias_mode = a->bias ? a->bias_mode : 0;
   p.act = a->act; p.alpha = a->alpha;
   p.has_residual = a->residual != nullptr;
+  p.reverse = a->reverse_tiles ? 1 : 0;
   p.row_stats_out = (KIND == G2_F32) ? a->row_stats_out : nullptr;
   p.raw_bf16 = (KIND == G2_F32) ? reinterpret_cast<__nv_bfloat16*>(a->out_bf16) : nullptr;
   p.ld_raw = a->ldo16;

@@ -38,6 +38,8 @@ def set_precision(mode: str) -> None:
 FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
 FUSE_LN_MIN_ROWS = 4096
 
+REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"
+
 # Flags (module-level so tests / bench can flip them)
 ENABLE_FOLDING = True      # single-head cross-attention: K == V == LN(x)
 ENCODER_KEY_SPLITS = 0     # 0 = auto
@@ -169,8 +171,10 @@ def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torc
              row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2)
     y = torch.empty((M, C), dtype=torch.float32, device=dev)
     yb = torch.empty((M, C), dtype=BF16, device=dev) if st_out is not None else None
+    # fc2 walks its tiles back to front: fc1 and the out-projection wrote h and x1 front to back, so their last rows are
+    # what L2 still holds; and the rows fc2 writes last (the first ones) are where the next QKV projection starts
     ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, residual=x1, ldr=C, out_f32=y, ldo32=C,
-             out_bf16=yb, ldo16=C if yb is not None else 0, row_stats_out=st_out)
+             out_bf16=yb, ldo16=C if yb is not None else 0, row_stats_out=st_out, reverse_tiles=REVERSE_FC2)
     return y, yb
 
 

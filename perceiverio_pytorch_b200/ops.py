@@ -100,7 +100,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          out_bf16: Optional[torch.Tensor] = None, ldo16: int = 0, strideO16: int = 0,
          tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None,
          row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None,
-         ln_colsum: Optional[torch.Tensor] = None, ln_channels: int = 0, ln_eps: float = 1e-5) -> None:
+         ln_colsum: Optional[torch.Tensor] = None, ln_channels: int = 0, ln_eps: float = 1e-5,
+         reverse_tiles: bool = False) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
     assert A.dtype == BF16 and B.dtype == BF16
@@ -112,7 +113,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       _ptr(out_bf16), ldo16, strideO16, tile_n, max_ctas,
                       GEMM_CLUSTER_M if cluster_m is None else cluster_m,
                       GEMM_KERNEL if kernel is None else kernel,
-                      _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps)
+                      _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps,
+                      1 if reverse_tiles else 0)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 

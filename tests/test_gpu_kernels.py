@@ -248,3 +248,24 @@ def test_gemm_fused_layernorm_epilogues():
     with pytest.raises(RuntimeError, match="fused-LayerNorm"):
         ops.gemm(xb, wp, M=M // 2, N=N, K=C, batch=2, strideA=(M // 2) * C, strideB=0, bias=bias, out_bf16=y, ldo16=N,
                  strideO16=(M // 2) * N, row_stats_in=st, ln_colsum=colsum, ln_channels=C)
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(1000, 520, 200, 1), (2048, 1024, 512, 1), (300, 256, 64, 3)])
+def test_gemm_pair_kernel_reverse_tile_order_gives_identical_results(M, N, K, batch):
+    """pio_gemm_args.reverse_tiles only changes the order in which the CTA pairs walk the output tiles."""
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(7)
+    ldk = ops.pad8(K)
+    A = torch.randn(batch, M, ldk, device="cuda").to(torch.bfloat16)
+    W = torch.randn(batch, N, ldk, device="cuda").to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(batch, M, N, device="cuda")
+    outs = []
+    for rev in (False, True):
+        o = torch.zeros(batch, M, N, device="cuda")
+        ops.gemm(A, W, M=M, N=N, K=K, batch=batch, strideA=M * ldk, strideB=N * ldk, lda=ldk, ldb=ldk, bias=bias,
+                 residual=res, ldr=N, strideR=M * N, out_f32=o, ldo32=N, strideO32=M * N, kernel=2, reverse_tiles=rev)
+        outs.append(o)
+    ref = A[:, :, :K].float() @ W[:, :, :K].float().transpose(1, 2) + bias + res
+    assert _rel(outs[0], ref) < 2e-3
+    assert torch.equal(outs[0], outs[1])
