@@ -249,7 +249,7 @@ def _bind_to_gpu_numa_node(local):
 def run_gpu_arm(args):
     import torch.distributed as dist
     import perceiverio_pytorch_b200 as pio
-    from perceiverio_pytorch_b200 import _lib, ops
+    from perceiverio_pytorch_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

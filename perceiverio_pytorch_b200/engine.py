@@ -467,6 +467,7 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     B, Nq, Cq = inputs_q.shape
     Nk, Ck = inputs_kv.shape[1], inputs_kv.shape[2]
     q_bcast = B > 1 and inputs_q.stride(0) == 0
+    kvn = None
     if isinstance(inputs_kv, PositionedInput):
         # features + batch-invariant position table: normalised without building the concatenated array (inputs.py)
         cf, cp = inputs_kv.features.shape[2], inputs_kv.pos.shape[1]
@@ -474,9 +475,7 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
             kvn = ops.layernorm_concat_bf16(inputs_kv.features, inputs_kv.pos, ln_kv.weight, ln_kv.bias, eps=ln_kv.eps)
         else:
             inputs_kv = inputs_kv.dense()
-    if isinstance(inputs_kv, PositionedInput):
-        pass
-    else:
+    if kvn is None:
         if inputs_kv.stride(2) != 1 or inputs_kv.stride(0) != Nk * inputs_kv.stride(1):
             inputs_kv = inputs_kv.contiguous()
         kvn = ops.layernorm_bf16(inputs_kv.view(B * Nk, Ck) if inputs_kv.is_contiguous()

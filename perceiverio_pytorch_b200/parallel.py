@@ -20,7 +20,7 @@ produce and merge the partials are the sm_100a ones.
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

@@ -6,7 +6,6 @@ multi-GPU partitioning of SURVEY.md §8(e) hooks in (`parallel.py`).
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.nn as nn

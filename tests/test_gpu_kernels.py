@@ -1,7 +1,6 @@
 """Per-kernel numerics on the B200: every C-ABI entry point against a plain PyTorch fp32 evaluation of the same op
 (the floating-point kernels' own reference; the oracle covers the composed path in test_gpu_parity.py).
 Tolerances: fp32 outputs of bf16-operand products 2e-3 of the output range, bf16 outputs 1e-2 (bf16 rounding)."""
-import math
 
 import pytest
 import torch

@@ -5,7 +5,7 @@ import json
 import pytest
 import torch
 
-from golden_util import golden_names, load_golden, load_golden_matrix, rel_err, run_oracle
+from golden_util import golden_names, load_golden, load_golden_matrix, rel_err
 
 pytestmark = pytest.mark.gpu
 

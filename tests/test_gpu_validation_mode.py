@@ -1,6 +1,5 @@
 """Validation precision (`set_precision("bf16x3")`: bf16 x 2 split operands, three tcgen05 MMAs per product): the CUDA
 path must agree with the reference's fp32 forward to max|d| / max|ref| <= 1e-4 (BASELINE.json north_star)."""
-import json
 
 import pytest
 import torch
