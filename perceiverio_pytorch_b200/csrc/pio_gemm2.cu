@@ -286,11 +286,31 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
         }
+        bool bias_done = false;
         if constexpr (KIND == G2_BF16) {
           if (p.row_stats_in != nullptr) {
             // v = rstd * (acc - mean * colsum[n])   (bias, which already holds W.beta, is added below)
             const float nm = -ln_mean;
-            if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) & 15u) == 0)) {
+            if (p.bias_mode == 1 && col0 + CHUNK_COLS <= p.N &&
+                (((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) | reinterpret_cast<uintptr_t>(p.bias + col0)) & 15u) == 0)) {
+              // the usual case, one instruction per element: v = acc * rstd + ((-mean * rstd) * colsum[n] + bias[n]) as two
+              // packed fp32x2 FMAs per column pair (this epilogue runs next to the mainloop's issue stream; the three
+              // scalar operations per element it replaces cost 8 % of the kernel)
+              const float nmr = nm * ln_rstd;
+              const uint64_t nmr2 = pack_f32x2(nmr, nmr), rstd2 = pack_f32x2(ln_rstd, ln_rstd);
+#pragma unroll
+              for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                const uint64_t lo = ffma2(pack_f32x2(v[4 * j], v[4 * j + 1]), rstd2,
+                                          ffma2(nmr2, pack_f32x2(cs.x, cs.y), pack_f32x2(bq.x, bq.y)));
+                const uint64_t hi = ffma2(pack_f32x2(v[4 * j + 2], v[4 * j + 3]), rstd2,
+                                          ffma2(nmr2, pack_f32x2(cs.z, cs.w), pack_f32x2(bq.z, bq.w)));
+                unpack_f32x2(lo, v[4 * j], v[4 * j + 1]);
+                unpack_f32x2(hi, v[4 * j + 2], v[4 * j + 3]);
+              }
+              bias_done = true;
+            } else if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) & 15u) == 0)) {
 #pragma unroll
               for (int j = 0; j < CHUNK_COLS / 4; ++j) {
                 const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
@@ -308,7 +328,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
-        if (p.bias_mode == 1) {
+        if (p.bias_mode == 1 && !bias_done) {
           if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < CHUNK_COLS / 4; ++j) {
