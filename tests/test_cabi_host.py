@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol(lib):
 
 @pytest.mark.parametrize("struct,cname", [("LayerNormArgs", "pio_layernorm_args"), ("GemmArgs", "pio_gemm_args"),
                                           ("SoftmaxArgs", "pio_softmax_args"), ("AttentionArgs", "pio_attention_args"),
-                                          ("CombineArgs", "pio_combine_args"), ("LinearF32Args", "pio_linear_f32_args")])
+                                          ("CombineArgs", "pio_combine_args"), ("LinearF32Args", "pio_linear_f32_args"),
+                                          ("LayerNormConcatArgs", "pio_layernorm_concat_args")])
 def test_ctypes_structs_follow_the_header(struct, cname):
     from perceiverio_pytorch_b200 import _lib
     body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), _header(), flags=re.S).group(1)
@@ -63,6 +64,23 @@ def test_argument_validation_without_gpu(lib):
     assert lib.pio_attention_supported(1024, 1024) == -2
     assert lib.pio_attention_key_tile(128, 128, 0) == 128
     assert lib.pio_attention_key_tile(322, 322, 1) == 64
+    c = _lib.LayerNormConcatArgs()
+    assert lib.pio_layernorm_concat_bf16(ctypes.byref(c), None) == -1 and b"null pointer" in lib.pio_last_error()
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    c = _lib.LayerNormConcatArgs(ptr, 0, 0, 0, ptr, ptr, 264, None, None, 1, 50177, 3, 258, 1e-5)
+    assert lib.pio_layernorm_concat_bf16(ctypes.byref(c), None) == -1 and b"multiple of 4" in lib.pio_last_error()
+    c = _lib.LayerNormConcatArgs(ptr, 0, 0, 0, ptr, ptr, 261, None, None, 1, 50176, 3, 258, 1e-5)
+    assert lib.pio_layernorm_concat_bf16(ctypes.byref(c), None) == -1 and b"pad8" in lib.pio_last_error()
+
+
+def test_layernorm_concat_supported_shapes():
+    from perceiverio_pytorch_b200 import ops
+    assert ops.layernorm_concat_supported(64, 50176, 3, 258)        # ImageNet pixels
+    assert ops.layernorm_concat_supported(1, 182528, 64, 258)       # optical flow
+    assert not ops.layernorm_concat_supported(1, 50177, 3, 258)     # positions not a multiple of 4
+    assert not ops.layernorm_concat_supported(1, 1024, 3, 1300)     # too wide
+    assert not ops.layernorm_concat_supported(4096, 1024, 64, 258)  # batch x features beyond one position group
 
 
 def test_product_path_never_imports_the_oracle():
