@@ -39,6 +39,7 @@ FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
 FUSE_LN_MIN_ROWS = 4096
 
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"
+REVERSE_FC1 = os.environ.get("PIO_REVERSE_FC1", "1") != "0"   # fc1 too: the out-projection wrote its operand front to back
 
 # Flags (module-level so tests / bench can flip them)
 ENABLE_FOLDING = True      # single-head cross-attention: K == V == LN(x)
@@ -168,7 +169,7 @@ def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torc
              out_bf16=x1b, ldo16=C, row_stats_out=st_mid)
     h = torch.empty((M, pad8(pf.hidden)), dtype=BF16, device=dev)
     ops.gemm(x1b, pf.w1, M=M, N=pf.hidden, K=C, bias=pf.b1, act=1, out_bf16=h, ldo16=h.stride(0),
-             row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2)
+             row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2, reverse_tiles=REVERSE_FC1)
     y = torch.empty((M, C), dtype=torch.float32, device=dev)
     yb = torch.empty((M, C), dtype=BF16, device=dev) if st_out is not None else None
     # fc2 walks its tiles back to front: fc1 and the out-projection wrote h and x1 front to back, so their last rows are
