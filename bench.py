@@ -41,11 +41,19 @@ DEC_KW = dict(query_channels=1024, final_project_out_channels=1000, num_latent_c
               num_heads=1, final_project=True)
 
 
-def model_flops_per_sample() -> float:
-    """Reference-algorithm FLOPs of the hot path per sample (SURVEY.md §8d formula): 418.7 GFLOP."""
+def model_flops_per_sample(executed: bool = False) -> float:
+    """FLOPs of the hot path per sample.  Reference algorithm (SURVEY.md §8d formula): 418.7 GFLOP.  `executed`: what
+    the kernels actually run — the single-head encoder cross-attend is folded (the per-token K/V
+    projections 2*Nk*Ck*(QK+V) disappear, two small query-side products 2*Nq*QK*Ck + 2*Nq*Ck*V appear, and the input
+    rows enter both attention products padded to 272 channels)."""
     def blk(nq, nk, cq, ck, qk, v, o):
         return 2 * nq * cq * qk + 2 * nk * ck * (qk + v) + 2 * nq * nk * (qk + v) + 2 * nq * v * o + 4 * nq * o * o
     enc = blk(512, 50176, 1024, 261, 261, 261, 1024)
+    if executed:
+        enc = (2 * 512 * 1024 * 261            # (LN(q) Wq^T + bq) Wk, folded into one [Cq -> Ck] product
+               + 2 * 512 * 50176 * (272 + 272)  # S = q' LN(x)^T and O = P LN(x), rows padded to 272
+               + 2 * 512 * 261 * 1024           # out = O (Wf Wv)^T
+               + 4 * 512 * 1024 * 1024)         # MLP
     tower = 48 * blk(512, 512, 1024, 1024, 1024, 1024, 1024)
     dec = blk(1000, 512, 1024, 1024, 1024, 1024, 1024) + 2 * 1000 * 1024 * 1000
     return float(enc + tower + dec)
@@ -164,9 +172,22 @@ def cpu_forward_factory(batch):
     return fwd
 
 
-def time_cpu(batch, warmup, steps):
+CPU_SAMPLE_BATCH = 8      # samples per CPU step: the same batched forward the GPU arm runs, on a bounded slice of it
+CPU_BUDGET_S = 240.0      # the whole CPU arm (warm-up + timed steps) is sized to end within about this
+
+
+def time_cpu(warmup, steps, batch=CPU_SAMPLE_BATCH, budget_s=CPU_BUDGET_S):
+    """Times the oracle port of the reference forward on `batch` samples per step with all host threads.  One
+    single-sample forward is timed first; if `warmup + steps` steps of `batch` samples would not fit the budget the
+    batch is reduced (never below 1).  Returns (seconds per step, samples per step)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    fwd = cpu_forward_factory(batch)
+    probe = cpu_forward_factory(1)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    t1 = time.perf_counter() - t0
+    batch = max(1, min(batch, int(budget_s / max(1e-3, t1 * (warmup + steps)))))
+    fwd = cpu_forward_factory(batch) if batch > 1 else probe
     for _ in range(warmup):
         fwd()
     ts = []
@@ -174,27 +195,98 @@ def time_cpu(batch, warmup, steps):
         t0 = time.perf_counter()
         fwd()
         ts.append(time.perf_counter() - t0)
-    return sum(ts) / len(ts)
+    return sum(ts) / len(ts), batch
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1
-    sec = time_cpu(batch, args.warmup, args.steps)
+    sec, batch = time_cpu(args.warmup, args.steps)
     v = batch / sec
-    sample = (f"{batch} sample(s) of the 64-sample batch per step, fp32, torch CPU ops, {torch.get_num_threads()} threads; "
-              "each step rebuilds the Fourier table and the concatenated input array as the reference does")
+    sample = (f"{batch} samples of the 64-sample batch per step (one batched forward), fp32, torch CPU ops, "
+              f"{torch.get_num_threads()} threads; each step rebuilds the Fourier table and the concatenated input array "
+              "as the reference does")
     _emit({
         "impl": "reference", "metric": "samples/sec per forward", "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(CFG, sample=sample),
+        "config": dict(CFG, batch_per_gpu=batch, global_batch=batch, parallelism="host CPU cores (reference arm)",
+                       sample=sample),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
+
+
+def parity_of_timed_batch(enc, dec, host_images, query, gpu_logits):
+    """Checker leg: sample 0 of the batch the GPU arm timed, through the fp32 CPU oracle port, against the logits the
+    CUDA path produced for it (max|d| / max|ref| and relative L2 over the [1000 queries x 1000 classes] output)."""
+    from oracle import perceiver_oracle as O
+    pe = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
+    pd = {k: v.detach().float().cpu() for k, v in dec.state_dict().items()}
+    with torch.inference_mode():
+        inputs = O.image_inputs_pixels(host_images[:1].float(), 64, (224, 224), 1)
+        z = O.encoder_forward(pe, "", num_blocks=8, num_self_attends_per_block=6, num_cross_attend_heads=1,
+                              num_self_attend_heads=8, inputs=inputs)
+        ref = O.decoder_forward(pd, "", num_heads=1, use_query_residual=True, final_project=True,
+                                query=query[:1].float().cpu(), latents=z).double()
+    got = gpu_logits[:1].double().cpu()
+    return {"max_rel": float((got - ref).abs().max() / ref.abs().max()),
+            "rel_l2": float((got - ref).norm() / ref.norm()), "tolerance": 1e-2,
+            "vs": "fp32 CPU oracle port of the reference forward (pinned to the live reference at this size by "
+                  "tests/golden/full/classification.npz), sample 0 of the timed batch, all 1000 x 1000 logits"}
+
+
+def graph_gap_profile(runner, inputs, replays=3):
+    """Where a replayed step's time goes on the device: start / end timestamps of every kernel of `replays` graph
+    replays (CUPTI activity records through torch.profiler; not inside any timed region).  Returns per-step sums of
+    kernel time, of the idle gaps between consecutive kernels, and the span from the first start to the last end."""
+    import tempfile
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(replays):
+                runner(inputs)
+            torch.cuda.synchronize()
+        with tempfile.NamedTemporaryFile(suffix=".json") as f:
+            prof.export_chrome_trace(f.name)
+            trace = json.load(open(f.name))
+        evs = sorted(((e["ts"], e["ts"] + e.get("dur", 0.0), e.get("name", "?")) for e in trace.get("traceEvents", [])
+                      if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")),
+                     key=lambda t: t[0])
+        if not evs:
+            return {"unavailable": "no device activity records in the trace"}
+        busy = sum(e[1] - e[0] for e in evs)
+        gaps = [max(0.0, evs[i + 1][0] - evs[i][1]) for i in range(len(evs) - 1)]
+        # gaps between replays (host launch of the next graph) are not node-to-node latency: drop the replays-1 largest
+        inner = sorted(gaps)[:len(gaps) - (replays - 1)] if replays > 1 else gaps
+        by = {}
+        for s, e, n in evs:
+            k = n.split("(")[0].replace("void ", "").replace("pio::", "")
+            by[k] = by.get(k, 0.0) + (e - s)
+        top = sorted(by.items(), key=lambda kv: -kv[1])[:8]
+        return {"replays": replays, "kernels_per_step": len(evs) / replays,
+                "kernel_ms_per_step": busy / replays / 1e3, "gap_ms_per_step": sum(inner) / replays / 1e3,
+                "median_gap_us": statistics.median(inner) if inner else 0.0,
+                "by_kernel_ms_per_step": {k: round(v / replays / 1e3, 4) for k, v in top},
+                "source": "CUPTI kernel activity records of the replayed CUDA graph (torch.profiler), outside the timed region"}
+    except Exception as ex:   # attribution must never take the measurement down
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+
+
+def roofline_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the newest committed
+    `ncu --set full` capture (profiles/roofline_traffic.json, written by tools/ncu_extract.py together with the commit it
+    was captured at)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get("traffic_bytes_per_launch"), {k: d.get(k) for k in ("source", "commit", "algorithmic_bytes_per_launch",
+                                                                         "kernels")}
+    except Exception:
+        return None, {"source": "profiles/roofline_traffic.json missing"}
 
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at communicator
@@ -391,7 +483,19 @@ def run_gpu_arm(args):
                 for k, v in _lib.profile_read().items() if v["launches"] > 0}
         return launches, kern
 
-    prim = measure(step_image, host_images, args.steps, e2e_steps, sampler=ClockSampler(local), after_timed=kernel_profile)
+    extras = {}
+
+    def after_timed(inputs):
+        out = kernel_profile(inputs)
+        if rank == 0:
+            # the replayed graph's own timeline: per-kernel activity records -> kernel time vs node-to-node gaps
+            g = GraphedForward(step_image, [inputs], warmup=1)
+            extras["graph_timeline"] = graph_gap_profile(g, g.inputs[0])
+            extras["logits"] = g(g.inputs[0])[:1].clone()
+            del g
+        return out
+
+    prim = measure(step_image, host_images, args.steps, e2e_steps, sampler=ClockSampler(local), after_timed=after_timed)
     ms_per_step, value, clocks = prim["ms_per_step"], prim["value"], prim["clocks"]
     e2e_ms, e2e_value = prim["e2e_ms"], prim["e2e_value"]
     launches, kern = prim["mid"]
@@ -421,6 +525,18 @@ def run_gpu_arm(args):
             d["gbs"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
         detail[k] = d
     mf = model_flops_per_sample()
+    mf_exec = model_flops_per_sample(executed=True)
+    traffic, traffic_info = roofline_traffic()
+    timeline = extras.get("graph_timeline")
+    if timeline and "kernel_ms_per_step" in timeline:
+        timeline["kernel_share_of_step"] = round(timeline["kernel_ms_per_step"] / ms_per_step, 4)
+        timeline["gap_share_of_step"] = round(timeline["gap_ms_per_step"] / ms_per_step, 4)
+    parity = None
+    if not args.no_parity and "logits" in extras:
+        try:
+            parity = parity_of_timed_batch(enc, dec, host_images, query, extras["logits"])
+        except Exception as ex:
+            parity = {"unavailable": f"{type(ex).__name__}: {ex}"}
     result = {
         "metric": "samples/sec per forward", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -442,14 +558,19 @@ def run_gpu_arm(args):
         "roofline": {"bound": "tensor", "kernel": "pio_gemm2_kernel / pio_gemm_kernel (tcgen05 GEMMs with fused epilogue), all GEMM launches of the step",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "peak_kind": "sustained bf16 cuBLAS GEMM, " + pk["source"],
-                     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), averaged over the four GEMM
-                     # shapes of a tower layer, from the committed `ncu --set full` capture; their algorithmic bytes
-                     # (operands + fp32 residual in/out + raw bf16 rows) average 305 MB per launch
-                     "traffic": 2.62e8, "traffic_source": "profiles/r01n_ncu_full_encoder_and_tower_summary.csv",
+                     "frac_of_burst_peak": achieved / pk["tflops_burst"],
+                     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) averaged over the GEMM launches
+                     # of a tower layer, read from the newest committed `ncu --set full` capture
+                     "traffic": traffic, "traffic_info": traffic_info,
                      "share_of_step": shares.get("gemm")},
         "model": {"flops_per_sample_reference_algorithm": mf,
                   "tflops_reference_algorithm": mf * value / 1e12,
-                  "frac_of_sustained_peak": mf * value / 1e12 / (pk["tflops"] * world)},
+                  "frac_of_sustained_peak": mf * value / 1e12 / (pk["tflops"] * world),
+                  "flops_per_sample_executed": mf_exec,
+                  "tflops_executed": mf_exec * value / 1e12,
+                  "frac_of_sustained_peak_executed": mf_exec * value / 1e12 / (pk["tflops"] * world)},
+        "parity": parity,
+        "graph_timeline": timeline,
         "kernels": detail, "kernel_share_of_step": shares,
         "kernel_timing": f"library-side CUDA events around each launch, {prof_steps} eager step(s) right after the timed "
                          "region, each queued behind a 25 ms device-side spin so that no event pair contains a wait for "
@@ -462,15 +583,31 @@ def run_gpu_arm(args):
             "e2e": {"value": dense["e2e_value"], "ms_per_step": dense["e2e_ms"], "h2d_bytes_per_step": dense["h2d"]},
             "note": "inputs = the preprocessed [B, 50176, 261] fp32 array (3.35 GB per step: its end-to-end leg is "
                     "PCIe-bound); the definition of value / e2e before the input glue moved onto the device"}
+    if world == 1 and not args.no_other_configs:
+        # the other BASELINE.json configs at full size (language B=1, flow B=1, one multimodal chunk call): replayed CUDA
+        # graphs, per subsystem, against the sustained bf16 peak — builder-side numbers of the previous rounds, now on
+        # the driver's record (outside the headline's timed region)
+        del l2_flush
+        torch.cuda.empty_cache()
+        result["other_configs"] = {}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            for name in ("language", "flow", "multimodal"):
+                r = bench_configs.measure_config(name, iters=10, eager=False)
+                result["other_configs"][name] = {k: r[k] for k in ("B", "inputs", "latents", "queries", "ms_graph", "tflops",
+                                                                   "frac_of_sustained_bf16_peak", "samples_per_s_graph",
+                                                                   "launches_per_forward")}
+        except Exception as ex:
+            result["other_configs"]["error"] = f"{type(ex).__name__}: {ex}"
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = 1
-            sec = time_cpu(cb, 1, 2)
+            sec, cb = time_cpu(1, 2, budget_s=60.0)
             result["cpu_baseline"] = {"value": cb / sec, "unit": "samples/s", "cores": torch.get_num_threads(),
                                       "kind": "port",
-                                      "sample": f"{cb} sample of the 64-sample batch, fp32 oracle port of the reference "
-                                                f"forward incl. its input preprocessing, 1 warm-up + 2 timed runs, "
-                                                f"{sec:.2f} s per run"}
+                                      "sample": f"{cb} samples of the 64-sample batch per run (one batched forward), fp32 "
+                                                f"oracle port of the reference forward incl. its input preprocessing, "
+                                                f"1 warm-up + 2 timed runs, {sec:.2f} s per run"}
         except Exception as ex:  # the baseline must never take the GPU number down
             result["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                       "sample": f"failed: {ex}"}
@@ -488,6 +625,9 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["batch_per_gpu"])
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle check of sample 0 of the timed batch")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the per-subsystem numbers of the language / flow / multimodal configs (N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-dense-boundary", action="store_true", help="skip the secondary (dense input array) measurement")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 8
+#define PIO_ABI_VERSION 9
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -102,21 +102,24 @@ typedef struct pio_gemm_args {
                            output / residual rows) */
   /* LayerNorm fused into the projections around it (CTA-pair kernel, batch == 1; SelfAttention :281 / :292):
    *  - producer side (the GEMM that writes the fp32 residual stream x): additionally writes out_bf16 = bf16(x), the
-   *    UN-normalised rows, and accumulates row_stats_out[m] += (sum_n x[m,n], sum_n x[m,n]^2) with atomics (the caller
-   *    zeroes the buffer; every N tile of a row contributes);
+   *    UN-normalised rows, and stores the partial statistics (sum_n x[m,n], sum_n x[m,n]^2) of every 128-column
+   *    half-tile of the row into its own slot: row_stats_out[m][2 * (n / 256) + (n % 256) / 128] (plain stores: no
+   *    atomics, nothing to zero, bit-reproducible; the caller passes row_stats_parts = 2 * ceil(N / 256));
    *  - consumer side (the GEMM that multiplies LN(x) by W): A is that bf16(x), B is W' = W * diag(gamma), and the
    *    epilogue applies the normalisation per output row:
    *        v = rstd_m * (alpha * acc - mean_m * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k],
+   *        (sum, sumsq) = the row's row_stats_parts partials added in index order,
    *        mean_m = sum / ln_channels, rstd_m = rsqrt(sumsq / ln_channels - mean_m^2 + ln_eps)
    *    (bias must already contain W * beta). */
-  float* row_stats_out;       /* [M][2] or NULL */
-  const float* row_stats_in;  /* [M][2] or NULL */
+  float* row_stats_out;       /* [M][row_stats_parts][2] or NULL */
+  const float* row_stats_in;  /* [M][row_stats_parts][2] or NULL */
   const float* ln_colsum;     /* [N], required with row_stats_in */
   int32_t ln_channels;
   float ln_eps;
   /* Walk the output tiles from the last M rows to the first (CTA-pair kernel; ignored by the single-CTA kernel).  A
    * consumer that starts where its producer finished finds that producer's last-written rows still in L2. */
   int32_t reverse_tiles;
+  int32_t row_stats_parts;    /* partial statistics per row in row_stats_out / row_stats_in (see above) */
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 
@@ -234,6 +237,15 @@ typedef struct pio_layernorm_concat_args {
   float eps;
 } pio_layernorm_concat_args;
 int pio_layernorm_concat_bf16(const pio_layernorm_concat_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Order-independent 128-bit content hash of a device buffer of 32-bit words: out2[0..1] += hash (the caller zeroes
+ * out2; hashes of several buffers accumulate when given different seeds).  The encode-once latent cache of
+ * PerceiverEncoder (the reference's chunked decoders re-run the encoder on identical inputs,
+ * multimodal_perceiver.py:146-161) keys on it instead of keeping and comparing a private copy of the input array.
+ * HBM-bound: 4 bytes read per word.  data must be 16-byte aligned.
+ * --------------------------------------------------------------------------------------------------------- */
+int pio_hash_words(const void* data, int64_t n_words, uint64_t seed, uint64_t* out2, void* stream);
 
 /* Per-launch device timing (bench.py's roofline): while enabled, every entry point brackets its kernel launch with
  * CUDA events on the launching stream.  pio_profile_read drains the records into out[family*4 + {ms, flops, bytes,

@@ -175,6 +175,47 @@ def main():
         _save("xattn_bias_matrix", m, dict(kind="cross", num_heads=4, use_query_residual=0, return_matrix=1),
               dict(q=q, kv=kv, bias=bias), out, matrix=mat)
 
+        # ---- rows the reference wipes, on SINGLE-head blocks (the drop-in folds the K/V projections of those onto the
+        # query side, which assumes rows of P that sum to one: wiped rows are the exception, transformer_primitives.py:168-175)
+        # 13. single-head cross-attend with a query mask and a query residual
+        torch.manual_seed(113)
+        m = ref_shim.perturb_parameters(_build(P.CrossAttention, q_in_channels=48, kv_in_channels=40, num_heads=1), 13)
+        for lin in (m.attention.proj_v, m.attention.final):
+            lin.bias.mul_(20.0)      # make final.weight @ proj_v.bias (the term a wiped row must not receive) visible
+        q, kv = torch.randn(2, 70, 48), torch.randn(2, 90, 40)
+        qmask = torch.ones(2, 70, dtype=torch.bool)
+        qmask[0, 50:] = False
+        qmask[1, ::3] = False
+        mask = P.make_cross_attention_mask(qmask, torch.ones(2, 90, dtype=torch.bool))
+        _save("xattn_h1_querymask", m, dict(kind="cross", num_heads=1, use_query_residual=1),
+              dict(q=q, kv=kv, query_mask=qmask), m(q, kv, attention_mask=mask))
+
+        # 14. encoder with a single-head cross-attend where sample 1 has EVERY input masked
+        torch.manual_seed(114)
+        enc = ref_shim.perturb_parameters(_build(R.PerceiverEncoder, num_input_channels=37, num_self_attends_per_block=1,
+                                                 num_blocks=1, num_latents=40, num_latent_channels=64,
+                                                 num_cross_attend_heads=1, num_self_attend_heads=4), 14)
+        enc.cross_attend.attention.proj_v.bias.mul_(20.0)
+        x = torch.randn(2, 150, 37)
+        imask = torch.ones(2, 150, dtype=torch.bool)
+        imask[0, 100:] = False
+        imask[1, :] = False
+        _save("encoder_h1_sample_fully_masked", enc,
+              dict(kind="encoder", num_blocks=1, num_self_attends_per_block=1, num_cross_attend_heads=1,
+                   num_self_attend_heads=4, use_query_residual=1),
+              dict(inputs=x, input_mask=imask), enc(x, enc.latents(x), input_mask=imask))
+
+        # 15. single-head decoder (latent width <= 384) with a query mask, no query residual, final projection
+        torch.manual_seed(115)
+        dec = ref_shim.perturb_parameters(_build(R.PerceiverDecoder, query_channels=50, final_project_out_channels=10,
+                                                 num_latent_channels=64, use_query_residual=False, num_heads=1), 15)
+        dec.decoding_cross_attn.attention.proj_v.bias.mul_(20.0)
+        query, lat = torch.randn(2, 70, 50), torch.randn(2, 40, 64)
+        qmask = torch.ones(2, 70, dtype=torch.bool)
+        qmask[0, 33:] = False
+        _save("decoder_h1_querymask", dec, dict(kind="decoder", num_heads=1, use_query_residual=0, final_project=1),
+              dict(query=query, latents=lat, query_mask=qmask), dec(query, lat, query_mask=qmask))
+
 
 if __name__ == "__main__":
     main()

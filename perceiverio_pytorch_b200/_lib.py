@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     "pio_profile_enable", "pio_profile_read",
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
-    "pio_linear_f32", "pio_layernorm_concat_bf16",
+    "pio_linear_f32", "pio_layernorm_concat_bf16", "pio_hash_words",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -47,7 +47,7 @@ class GemmArgs(C.Structure):
                 ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
                 ("tile_n", i32), ("max_ctas", i32), ("cluster_m", i32), ("kernel", i32),
                 ("row_stats_out", vp), ("row_stats_in", vp), ("ln_colsum", vp), ("ln_channels", i32), ("ln_eps", f32),
-                ("reverse_tiles", i32)]
+                ("reverse_tiles", i32), ("row_stats_parts", i32)]
 
 
 class SoftmaxArgs(C.Structure):
@@ -118,6 +118,8 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
+        lib.pio_hash_words.restype = C.c_int
+        lib.pio_hash_words.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.pio_attention_supported.restype = C.c_int
         lib.pio_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_key_tile.restype = C.c_int
@@ -126,7 +128,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 8:
+        if lib.pio_abi_version() != 9:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -450,11 +450,10 @@ static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cuda
   p.partial = a->partial;
   p.O_part = a->O_part; p.m_part = a->m_part; p.l_part = a->l_part;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(pio_flash_kernel<NQC, NVC, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run(dev.device, [] {
+    return cudaFuncSetAttribute(pio_flash_kernel<NQC, NVC, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(flash<%d,%d,%d>) failed: %s", NQC, NVC, (int)SAME,

@@ -622,11 +622,10 @@ static int launch_flash2_cfg(const pio_attention_args* a, const DeviceInfo& dev,
   p.items = a->B * a->H * p.q_pairs;
   p.kv_tiles = (a->Nk + BN - 1) / BN;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(pio_flash2_kernel<NQC, NVC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run(dev.device, [] {
+    return cudaFuncSetAttribute(pio_flash2_kernel<NQC, NVC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(flash2<%d,%d,%d>) failed: %s", NQC, NVC, BN,

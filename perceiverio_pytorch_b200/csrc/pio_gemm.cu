@@ -393,11 +393,10 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   ep.out_f32 = a->out_f32; ep.ldo32 = a->ldo32; ep.strideO32 = a->strideO32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); ep.ldo16 = a->ldo16; ep.strideO16 = a->strideO16;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(pio_gemm_kernel<BN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run(dev.device, [] {
+    return cudaFuncSetAttribute(pio_gemm_kernel<BN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(gemm<%d>) failed: %s", BN, cudaGetErrorString(attr_err));

@@ -33,11 +33,12 @@ struct Gemm2Params {
   int b_swap;                    // debug: which CTA of the pair stages which half of the B tile
   int reverse;                   // walk the tiles from the last M rows to the first (pio_gemm_args.reverse_tiles)
   // LayerNorm fusion (pio_gemm_args): producer side ...
-  float* row_stats_out;          // [M][2] += (sum, sum of squares) of the final fp32 rows
+  float* row_stats_out;          // [M][stats_parts][2]: (sum, sum of squares) of this row over one 128-column half-tile
+  int stats_parts;               // partials per row: 2 * tiles_n on the producer side, whatever the producer wrote on the consumer side
   __nv_bfloat16* raw_bf16;       // bf16 copy of the fp32 output (un-normalised rows), row pitch ld_raw
   long long ld_raw;
   // ... consumer side
-  const float* row_stats_in;     // [M][2] of the A operand's rows
+  const float* row_stats_in;     // [M][stats_parts][2] of the A operand's rows
   const float* ln_colsum;        // [N]
   float ln_inv_c, ln_eps;
 };
@@ -251,9 +252,17 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // fused LayerNorm, consumer side: this row's mean / rstd from the statistics its producer accumulated
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (KIND == G2_BF16 && p.row_stats_in != nullptr && row < p.M) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(p.row_stats_in) + row);
-        ln_mean = st.x * p.ln_inv_c;
-        ln_rstd = rsqrtf(fmaxf(st.y * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        // the producer left one (sum, sum of squares) per 128-column half-tile: added up in a fixed order, so the
+        // statistics (and with them the whole tower) are bit-reproducible from run to run
+        const float2* sp = reinterpret_cast<const float2*>(p.row_stats_in) + (long long)row * p.stats_parts;
+        float s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < p.stats_parts; ++j) {
+          const float2 st = __ldg(sp + j);
+          s1 += st.x;
+          s2 += st.y;
+        }
+        ln_mean = s1 * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;   // producer side: this row's partial statistics over the tile
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -413,8 +422,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       if (KIND == G2_F32 && p.row_stats_out != nullptr && row < p.M) {
-        atomicAdd(p.row_stats_out + 2 * (long long)row, st_sum);
-        atomicAdd(p.row_stats_out + 2 * (long long)row + 1, st_sq);
+        // one slot per (row, 128-column half-tile): plain stores, no atomics, nothing to zero beforehand
+        reinterpret_cast<float2*>(p.row_stats_out)[(long long)row * p.stats_parts + nt * 2 + half] =
+            make_float2(st_sum, st_sq);
       }
     }
     if (lane == 0) bulk_wait_read<0>();   // staging slots must outlive the stores that read them
@@ -496,16 +506,19 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.raw_bf16 = (KIND == G2_F32) ? reinterpret_cast<__nv_bfloat16*>(a->out_bf16) : nullptr;
   p.ld_raw = a->ldo16;
   p.row_stats_in = (KIND == G2_BF16) ? a->row_stats_in : nullptr;
+  p.stats_parts = a->row_stats_parts > 0 ? a->row_stats_parts : 1;
+  if (p.row_stats_out != nullptr && p.stats_parts != 2 * p.tiles_n)
+    return fail(PIO_ERR_INVALID_ARGUMENT, "pio_gemm_bf16: row_stats_out needs row_stats_parts == 2 * ceil(N / 256) = %d (got %d)",
+                2 * p.tiles_n, a->row_stats_parts);
   p.ln_colsum = a->ln_colsum;
   p.ln_inv_c = a->ln_channels > 0 ? 1.0f / (float)a->ln_channels : 0.f;
   p.ln_eps = a->ln_eps;
   static const int b_swap = [] { const char* e = getenv("PIO_GEMM2_BSWAP"); return (e && e[0] == '1') ? 1 : 0; }();
   p.b_swap = b_swap;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(pio_gemm2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run(dev.device, [] {
+    return cudaFuncSetAttribute(pio_gemm2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(gemm2<%d>) failed: %s", KIND, cudaGetErrorString(attr_err));

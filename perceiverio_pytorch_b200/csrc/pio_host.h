@@ -118,6 +118,20 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs (a model moved
+// with .to("cuda:1"), or one process per node) must set it on each device it launches on.  One bit per device ordinal.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done{0};
+  template <typename F>
+  cudaError_t run(int device, F&& f) {
+    const uint64_t bit = 1ull << (device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    cudaError_t e = f();   // idempotent, so two racing threads may both run it
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace pio

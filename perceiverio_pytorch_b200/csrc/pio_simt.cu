@@ -841,7 +841,73 @@ __global__ void __launch_bounds__(256) pio_linear_f32_kernel(pio_linear_f32_args
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Content hash of a device buffer (the encode-once latent cache keys on it): every 32-bit word is mixed with its index
+// (splitmix64 finaliser) and the mixed values are SUMMED in two independent 64-bit lanes — integer addition commutes, so
+// the result does not depend on the order in which threads and blocks finish.  HBM-bound: 4 bytes read per word.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) pio_hash_kernel(const uint32_t* __restrict__ x, long long n_words,
+                                                      unsigned long long seed, unsigned long long* __restrict__ out) {
+  unsigned long long h0 = 0, h1 = 0;
+  const long long n4 = n_words >> 2;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(x4 + i);
+    const unsigned long long base = seed + (unsigned long long)i * 4ull;
+    const unsigned long long a = mix64((base + 0) * 0x9E3779B97F4A7C15ull ^ v.x);
+    const unsigned long long b = mix64((base + 1) * 0x9E3779B97F4A7C15ull ^ v.y);
+    const unsigned long long c = mix64((base + 2) * 0x9E3779B97F4A7C15ull ^ v.z);
+    const unsigned long long d = mix64((base + 3) * 0x9E3779B97F4A7C15ull ^ v.w);
+    h0 += a + b + c + d;
+    h1 += mix64(a ^ 0xD6E8FEB86659FD93ull) + mix64(b ^ 0xD6E8FEB86659FD93ull) + mix64(c ^ 0xD6E8FEB86659FD93ull) +
+          mix64(d ^ 0xD6E8FEB86659FD93ull);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_words & 3)) {   // tail words
+    const long long i = (n4 << 2) + threadIdx.x;
+    const unsigned long long a = mix64((seed + (unsigned long long)i) * 0x9E3779B97F4A7C15ull ^ __ldg(x + i));
+    h0 += a;
+    h1 += mix64(a ^ 0xD6E8FEB86659FD93ull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, h0);
+    atomicAdd(out + 1, h1);
+  }
+}
+
 }  // namespace pio
+
+extern "C" int pio_hash_words(const void* data, int64_t n_words, uint64_t seed, uint64_t* out2, void* stream_) {
+  using namespace pio;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PIO_REQUIRE(data && out2 && n_words >= 0, "pio_hash_words: null pointer / negative size");
+  PIO_REQUIRE(aligned16(data), "pio_hash_words: data must be 16-byte aligned");
+  DeviceInfo dev;
+  int rc = get_device_info(&dev);
+  if (rc != PIO_OK) return rc;
+  long long blocks = (n_words / 4 + 255) / 256;
+  if (blocks > (long long)dev.sm_count * 8) blocks = (long long)dev.sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  {
+    ProfileScope prof(KF_LAYERNORM, 0.0, 4.0 * (double)n_words, stream);
+    pio_hash_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(data), n_words,
+                                                          (unsigned long long)seed,
+                                                          reinterpret_cast<unsigned long long*>(out2));
+  }
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
+}
 
 extern "C" int pio_linear_f32(const pio_linear_f32_args* a, void* stream_) {
   using namespace pio;
@@ -932,12 +998,13 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     const size_t smem = lnb_smem_bytes(R, a->C, (int)a->ldy);
     const int nfull = a->C / 32;
     const lnb_kernel_t kern = lnb_kernel_table(std::make_integer_sequence<int, LNB_MAX_NFULL + 1>{})[nfull];
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
+    static PerDeviceOnce once;
+    const cudaError_t attr_err = once.run(dev.device, [] {
       const lnb_kernel_t* table = lnb_kernel_table(std::make_integer_sequence<int, LNB_MAX_NFULL + 1>{});
-      for (int i = 0; i <= LNB_MAX_NFULL && attr_err == cudaSuccess; ++i)
-        attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaError_t e = cudaSuccess;
+      for (int i = 0; i <= LNB_MAX_NFULL && e == cudaSuccess; ++i)
+        e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      return e;
     });
     if (attr_err != cudaSuccess)
       return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(layernorm_bulk) failed: %s", cudaGetErrorString(attr_err));
@@ -1004,12 +1071,13 @@ extern "C" int pio_layernorm_concat_bf16(const pio_layernorm_concat_args* a, voi
   const size_t smem = LNC_STAGES * in_pitch + feat_bytes + (size_t)a->B * R * 8 + 64;
   PIO_REQUIRE(smem <= 200 * 1024, "pio_layernorm_concat_bf16: shared memory budget exceeded (%zu bytes)", smem);
   const lnc_kernel_t kern = lnc_kernel_table(std::make_integer_sequence<int, LNC_MAX_NP + 1>{})[C / 64];
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run(dev.device, [] {
     const lnc_kernel_t* table = lnc_kernel_table(std::make_integer_sequence<int, LNC_MAX_NP + 1>{});
-    for (int i = 0; i <= LNC_MAX_NP && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i <= LNC_MAX_NP && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
   });
   if (attr_err != cudaSuccess)
     return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(layernorm_concat) failed: %s", cudaGetErrorString(attr_err));

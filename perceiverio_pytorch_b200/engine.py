@@ -37,6 +37,7 @@ def set_precision(mode: str) -> None:
 # atomics) against the 1e-2 bound with the fusion, 8.2e-3 without, so it stays on the exact two-pass LayerNorm.
 FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
 FUSE_LN_MIN_ROWS = 4096
+FUSE_LN_MAX_OFFSET = 1.0     # max |mean| / std of a residual-stream row the fused form accepts (perceiver.PerceiverEncoder)
 
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"
 REVERSE_FC1 = os.environ.get("PIO_REVERSE_FC1", "1") != "0"   # fc1 too: the out-projection wrote its operand front to back
@@ -82,6 +83,9 @@ class PreparedAttention:
             self.bq_fold = (wk64.t() @ bq.double()).float().contiguous()        # [Ck]
             self.wo_fold = _bf16_weight((wf64 @ wv64).float())                  # [O, Ck]
             bo = wf64 @ bv.double()
+            # rows the reference wipes (no valid key / masked query, :168-175) are zeroed BEFORE `final` and come out as
+            # final.bias alone; the folded bias assumes a row of P that sums to one, so those rows take this part back
+            self.wf_bv = bo.float().contiguous()
             if bf is not None:
                 bo = bo + bf.double()
             self.bo_fold = bo.float().contiguous()
@@ -90,7 +94,7 @@ class PreparedAttention:
             self.bqkv = torch.cat([bq, bk, bv], 0).float().contiguous()
         else:
             self.wq, self.bq = _bf16_weight(wq), bq.float().contiguous()
-            self.kv_fused = (self.QK % 8 == 0)
+            self.kv_fused = (self.QK % 8 == 0) and wk.shape[1] == wv.shape[1]   # k_in_channels may differ from v_in
             if self.kv_fused:
                 self.wkv = _bf16_weight(torch.cat([wk, wv], 0))
                 self.bkv = torch.cat([bk, bv], 0).float().contiguous()
@@ -150,8 +154,10 @@ class PreparedFusedLayer:
 def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torch.Tensor, st: torch.Tensor, *,
                                B: int, N: int, st_mid: torch.Tensor, st_out: Optional[torch.Tensor]):
     """SelfAttention.forward with fused LayerNorms.  x fp32 [M, C] (the residual stream), xb = bf16(x) [M, C],
-    st = per-row (sum, sum of squares) of x; st_mid / st_out are zeroed [M, 2] buffers for the two residual-stream
-    states this block produces (st_out None: the block's output feeds no further fused LayerNorm).
+    st = per-row partial (sum, sum of squares) of x, [M, parts, 2] (ops.empty_row_stats); st_mid / st_out are such
+    buffers for the two residual-stream states this block produces (st_out None: the block's output feeds no further
+    fused LayerNorm).  Each producer GEMM fills every slot with plain stores and each consumer adds a row's slots in
+    index order, so the tower is bit-reproducible.
     Returns (y fp32 [M, C], bf16(y) or None)."""
     M, C = x.shape
     dev = x.device
@@ -347,8 +353,8 @@ def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv
 
 def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False, stats_out=None):
     """x + fc2(gelu(fc1(LN(x)))) on a flat fp32 [M, C] matrix.  Returns (fp32 [M, cout], bf16 copy or None).
-    `stats_out` (zeroed fp32 [M, 2]) additionally receives the per-row (sum, sum of squares) of the result — the
-    producer side of the fused LayerNorm of the next block."""
+    `stats_out` (ops.empty_row_stats(M, cout)) additionally receives the per-row partial (sum, sum of squares) of the
+    result — the producer side of the fused LayerNorm of the next block."""
     xn = ops.layernorm_bf16(x_f32, ln_w, ln_b)
     _, h = ops.linear(xn, pm.cin, pm.w1, pm.hidden, pm.b1, act=1)
     if stats_out is None:
@@ -431,8 +437,9 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
     return o, pa.V
 
 
-def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual):
-    """Output projection (+ query residual) of a cross-attend: returns fp32 [B*Nq, O]."""
+def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual, row_keep=None):
+    """Output projection (+ query residual) of a cross-attend: returns fp32 [B*Nq, O].  `row_keep` (u8 [B, Nq]) marks the
+    rows the attention kernel did not wipe; it only matters on the folded path (see PreparedAttention.wf_bv)."""
     if pa.folded:
         w, b = pa.wo_fold, pa.bo_fold
     else:
@@ -448,6 +455,9 @@ def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B
         ops.gemm(o2, w, M=Nq, N=pa.O, K=width, batch=B, strideA=Nq * o2.shape[1], strideB=0, bias=b,
                  residual=residual, ldr=residual.stride(1), strideR=residual.stride(0) if B > 1 else 0,
                  out_f32=y, ldo32=ldy, strideO32=Nq * ldy)
+    if pa.folded and row_keep is not None:
+        wiped = (row_keep.reshape(B * Nq, 1) == 0).to(torch.float32)
+        y.addcmul_(wiped, pa.wf_bv[None, :], value=-1.0)
     return y
 
 
@@ -501,6 +511,6 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
         res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
     else:
         res = None
-    x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res)
+    x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk)
     y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
     return y32.view(B, Nq, -1), y16

@@ -153,7 +153,16 @@ def positioned_image_input(preprocessor, images: torch.Tensor, pos=None) -> Opti
     return PositionedInput(feats, table)
 
 
-def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_points=None, input_mask=None,
+def _query_reads_inputs(output_query) -> bool:
+    """Whether a reference output query hands the preprocessed inputs themselves back as (part of) the decoder query:
+    `BasicQuery.forward` returns `inputs` when it has no position encoding (output_queries.py:73-76 — the optical-flow
+    recipe's `FlowQuery`, :129-139), and `PerceiverIO.decoder_query` then reshapes / concatenates that tensor
+    (perceiver.py:353-360), which needs the dense array."""
+    return bool(getattr(output_query, "_concat_preprocessed_input", False)
+                and getattr(output_query, "_position_encoding", None) is None)
+
+
+def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_points=None, pos=None, input_mask=None,
                          query_mask=None, only_needed_queries: bool = False):
     """`PerceiverIO.forward` (perceiver.py:287-325) for a single image modality with the input glue fused: the
     preprocessor's features and position table reach the encoder as a `PositionedInput`.  Falls back to the module's
@@ -166,17 +175,21 @@ def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_p
     own = type(perceiver).forward     # the class's forward: `perceiver.forward` may be this very function (install.py)
     mp = perceiver._multi_preprocessor
     preps = getattr(mp, "_preprocessors", None) if mp is not None else None
-    if (type(inputs) is not torch.Tensor or preps is None or list(preps.keys()) != ["__default"]
-            or mp.padding_embeddings is not None or mp._mask_probs is not None):
-        return own(perceiver, inputs, subsampled_output_points=subsampled_output_points, input_mask=input_mask,
-                   query_mask=query_mask)
+    if (type(inputs) is not torch.Tensor or pos is not None or preps is None or list(preps.keys()) != ["__default"]
+            or mp.padding_embeddings is not None or mp._mask_probs is not None
+            or type(preps["__default"]).__name__ != "ImagePreprocessor"):
+        return own(perceiver, inputs, subsampled_output_points=subsampled_output_points, pos=pos,
+                   input_mask=input_mask, query_mask=query_mask)
     pin = positioned_image_input(preps["__default"], inputs)
     if pin is None:
-        return own(perceiver, inputs, subsampled_output_points=subsampled_output_points, input_mask=input_mask,
-                   query_mask=query_mask)
+        return own(perceiver, inputs, subsampled_output_points=subsampled_output_points, pos=pos,
+                   input_mask=input_mask, query_mask=query_mask)
     sizes = {"__default": pin.shape[1]}
     encoder_query = perceiver._encoder.latents(pin)
-    decoder_query, query_sizes = perceiver.decoder_query(pin, sizes, {"__default": pin.features},
+    # queries that pass the preprocessed inputs through (optical flow: the 182,528 inputs ARE the decoder queries) get the
+    # dense array — it is the decoder's operand there anyway; the encoder still takes the two parts separately
+    query_inputs = pin.dense() if any(_query_reads_inputs(q) for q in perceiver._output_queries.values()) else pin
+    decoder_query, query_sizes = perceiver.decoder_query(query_inputs, sizes, {"__default": pin.features},
                                                          subsampled_points=subsampled_output_points)
     latents = perceiver._encoder(pin, encoder_query, input_mask=input_mask)
     posts = perceiver._output_postprocessors

@@ -30,6 +30,17 @@ def empty_f32_rows(m: int, n: int, device) -> torch.Tensor:
     return t if n4 == n else t[:, :n]
 
 
+def stats_parts(n: int) -> int:
+    """Partial (sum, sum of squares) slots per row that a fused-LayerNorm producer GEMM with N = n output columns
+    writes: one per 128-column half of each 256-column tile (pio_gemm_args.row_stats_parts)."""
+    return 2 * ((n + 255) // 256)
+
+
+def empty_row_stats(m: int, n: int, device) -> torch.Tensor:
+    """[m, stats_parts(n), 2] fp32 buffer for pio_gemm_args.row_stats_out (every slot is written: no zeroing)."""
+    return torch.empty((m, stats_parts(n), 2), dtype=torch.float32, device=device)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -39,12 +50,41 @@ def _stream():
 
 
 def _need_cuda(*ts):
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("perceiverio_pytorch_b200: tensors must live on a CUDA (sm_100) device; "
                                "there is no CPU path")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"perceiverio_pytorch_b200: tensors of one call live on different devices "
+                               f"({dev} and {t.device})")
 
 
+def _device_guard(fn):
+    """Run the wrapped entry point with the tensors' device as the current CUDA device: the library launches on the
+    current device (stream, SM count, per-device kernel attributes), so a module moved with .to("cuda:1") must not
+    depend on what torch.cuda.current_device() happens to be."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+@_device_guard
 def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
                    normalize: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
                    split: int = 0) -> torch.Tensor:
@@ -75,6 +115,7 @@ def layernorm_concat_supported(B: int, N: int, Cf: int, Cp: int) -> bool:
     return N % r == 0 and B * r * Cf * 4 <= 48 * 1024 and r * Cp * 4 <= 40 * 1024
 
 
+@_device_guard
 def layernorm_concat_bf16(feat: torch.Tensor, pos: torch.Tensor, gamma: Optional[torch.Tensor],
                           beta: Optional[torch.Tensor], *, eps: float = 1e-5) -> torch.Tensor:
     """LayerNorm(cat([feat [B, N, Cf] (any strides), pos [N, Cp] broadcast over the batch], -1)) -> bf16
@@ -92,6 +133,7 @@ def layernorm_concat_bf16(feat: torch.Tensor, pos: torch.Tensor, gamma: Optional
     return out
 
 
+@_device_guard
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int = 1, b_mn_major: bool = False,
          strideA: int = 0, strideB: int = 0, lda: Optional[int] = None, ldb: Optional[int] = None,
          bias: Optional[torch.Tensor] = None, bias_mode: int = 1, act: int = 0, alpha: float = 1.0,
@@ -101,12 +143,16 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None,
          row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None,
          ln_colsum: Optional[torch.Tensor] = None, ln_channels: int = 0, ln_eps: float = 1e-5,
-         reverse_tiles: bool = False) -> None:
+         reverse_tiles: bool = False, row_stats_parts: int = 0) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
     assert A.dtype == BF16 and B.dtype == BF16
     lda = A.stride(-2) if lda is None else lda
     ldb = B.stride(-2) if ldb is None else ldb
+    st = row_stats_out if row_stats_out is not None else row_stats_in
+    if st is not None and not row_stats_parts:
+        assert st.dim() == 3 and st.shape[2] == 2 and st.is_contiguous(), "row statistics are [M, parts, 2] fp32"
+        row_stats_parts = st.shape[1]
     a = _lib.GemmArgs(_ptr(A), lda, strideA, _ptr(B), ldb, strideB, 1 if b_mn_major else 0,
                       M, N, K, batch, _ptr(bias), bias_mode if bias is not None else 0, act, alpha,
                       _ptr(residual), ldr, strideR, _ptr(out_f32), ldo32, strideO32,
@@ -114,7 +160,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       GEMM_CLUSTER_M if cluster_m is None else cluster_m,
                       GEMM_KERNEL if kernel is None else kernel,
                       _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps,
-                      1 if reverse_tiles else 0)
+                      1 if reverse_tiles else 0, row_stats_parts)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 
@@ -134,6 +180,7 @@ def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torc
     return y32, y16
 
 
+@_device_guard
 def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """y = x @ w^T + bias in fp32 on CUDA cores, for N <= 16 output channels (x fp32 [M, K], w fp32 [N, K])."""
     _need_cuda(x, w, bias)
@@ -146,6 +193,7 @@ def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -
     return y
 
 
+@_device_guard
 def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[torch.Tensor] = None,
                  row_keep: Optional[torch.Tensor] = None, split: bool = False, *,
                  dense_mask: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
@@ -181,6 +229,7 @@ def attention_supported(dqk: int, dv: int) -> bool:
     return _lib.load().pio_attention_supported(dqk, dv) == 0
 
 
+@_device_guard
 def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, H: int, Nq: int, Nk: int,
                   dqk: int, dv: int, strideQ: int, strideK: int, strideV: int,
                   ldq: int, ldk: int, ldv: int, scale: Optional[float] = None,
@@ -214,6 +263,7 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
     return O
 
 
+@_device_guard
 def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp: Optional[torch.Tensor], *,
                       row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                       part_stride_O: int = 0, part_stride_ml: int = 0, shape=None,
@@ -236,3 +286,29 @@ def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp
                          _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]), C.c_void_p(part_ptrs_dev) if part_ptrs_dev else None)
     _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
     return out
+
+
+def content_hash(*tensors: Optional[torch.Tensor]) -> tuple:
+    """128-bit content hash of the given CUDA tensors (pio_hash_words; None entries and shapes are part of the key).
+    One pass over the data and one 16-byte read-back (a host synchronisation)."""
+    dev = next(t.device for t in tensors if t is not None)
+    acc = torch.zeros(2, dtype=torch.int64, device=dev)
+    meta = []
+    with torch.cuda.device(dev):
+        for i, t in enumerate(tensors):
+            if t is None:
+                meta.append(None)
+                continue
+            _need_cuda(t)
+            meta.append((tuple(t.shape), str(t.dtype)))
+            c = t.contiguous()
+            nbytes = c.numel() * c.element_size()
+            if nbytes % 4 != 0 or c.data_ptr() % 16 != 0:      # odd byte counts (bool masks): widen to whole words
+                flat = torch.zeros((nbytes + 3) // 4 * 4, dtype=torch.uint8, device=dev)
+                flat[:nbytes] = c.reshape(-1).view(torch.uint8)
+                c, nbytes = flat, flat.numel()
+            if nbytes:
+                _lib.check(_lib.load().pio_hash_words(_ptr(c), nbytes // 4, (i + 1) << 40, _ptr(acc), _stream()),
+                           "pio_hash_words")
+    h = acc.tolist()
+    return (h[0], h[1], tuple(meta))

@@ -69,11 +69,21 @@ class PerceiverEncoder(nn.Module):
         self.key_shard = None  # set by parallel.shard_encoder_keys(): inputs hold this rank's slice of the key axis
         # Encode-once: the reference's chunked decoders call the whole PerceiverIO — encoder
         # included — once per output chunk on the SAME inputs (multimodal_perceiver.py:146-161: 128 calls).  With
-        # cache_latents = True the encoder returns the latents of the previous call when it is handed inputs / latents /
-        # mask that are exactly equal to the previous call's and its parameters are unchanged (opt-in: it keeps the
-        # previous input array alive and spends one comparison pass + host sync per call).
+        # cache_latents = True the encoder returns the latents of the previous call when the 128-bit content hash of
+        # (inputs, latents, mask) equals the previous call's and its parameters are unchanged (opt-in: one read of the
+        # input array by pio_hash_words + a 16-byte read-back per call; nothing of the input is kept alive).
         self.cache_latents = False
         self._latent_cache = None
+        # Tower LayerNorms folded into the projections: None = automatic (latent arrays of at least
+        # engine.FUSE_LN_MIN_ROWS rows, and only while the residual stream passes the numerics check below), True / False
+        # force it.  The fused form rounds x to bf16 BEFORE the mean is subtracted, which scales that product's rounding
+        # error by sqrt(1 + mean^2 / var) per row: harmless for residual streams centred near zero, not for rows with a
+        # large common offset.  So the first fused forward after a parameter change measures max |mean| / std over every
+        # row of every residual-stream state (from the statistics the GEMMs produced anyway; one host sync, skipped
+        # during CUDA-graph capture) and falls back to the LayerNorm kernels when it exceeds engine.FUSE_LN_MAX_OFFSET.
+        self.fuse_layernorm = None
+        self.fused_layernorm_offset = None      # the measured max |mean| / std (None: not measured yet)
+        self._fuse_ln_checked = None
 
     def latents(self, inputs):
         return self.latent_pos_enc(batch_size=inputs.shape[0])
@@ -83,8 +93,8 @@ class PerceiverEncoder(nn.Module):
         ops._need_cuda(inputs, latents)
         if latents.shape[0] == 0 or latents.shape[1] == 0:   # empty batch / no latents: nothing to launch
             return latents.new_empty(latents.shape)
-        if isinstance(inputs, PositionedInput) and (engine.PRECISION != "bf16" or self.cache_latents):
-            inputs = inputs.dense()   # the validation precision and the latent cache work on the dense array
+        if isinstance(inputs, PositionedInput) and engine.PRECISION != "bf16":
+            inputs = inputs.dense()   # the validation precision works on the dense array
         key_mask = None
         row_keep = None
         if input_mask is not None:
@@ -96,35 +106,33 @@ class PerceiverEncoder(nn.Module):
         use_cache = (self.cache_latents and self.key_shard is None and inputs.is_cuda
                      and not torch.cuda.is_current_stream_capturing())
         if use_cache:
-            params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            # the reference's wrappers rebuild the preprocessed input array for every chunk, so identity of the tensor
+            # object cannot be used: key on the content (a PositionedInput is hashed as its two parts)
+            parts = (inputs.features, inputs.pos) if isinstance(inputs, PositionedInput) else (inputs, None)
+            lat = latents[0] if latents.dim() == 3 and latents.stride(0) == 0 else latents   # stride-0 batch broadcast
+            key = (tuple((p.data_ptr(), p._version) for p in self.parameters()), engine.PRECISION, tuple(latents.shape),
+                   ops.content_hash(parts[0], parts[1], lat, input_mask))
             c = self._latent_cache
-            if (c is not None and c["params"] == params and c["precision"] == engine.PRECISION
-                    and self._equal(inputs, c["inputs"]) and self._equal(latents, c["latents"])
-                    and (input_mask is None) == (c["mask"] is None)
-                    and (input_mask is None or self._equal(input_mask, c["mask"]))):
-                return c["z"]
+            if c is not None and c[0] == key:
+                return c[1]
         z = self._encode(inputs, latents, key_mask, row_keep)
         if use_cache:
-            # private copies: the caller may overwrite its tensors in place afterwards
-            self._latent_cache = dict(params=params, precision=engine.PRECISION, z=z, inputs=inputs.clone(),
-                                      latents=latents.clone(),
-                                      mask=None if input_mask is None else input_mask.clone())
+            self._latent_cache = (key, z)
         return z
-
-    @staticmethod
-    def _equal(t, cached) -> bool:
-        """Exact content equality with the private copy kept from the previous call (one device-side comparison and a
-        host sync; the reference's wrappers rebuild the preprocessed input array for every chunk, so identity of the
-        tensor object cannot be used)."""
-        if t.shape != cached.shape or t.dtype != cached.dtype or t.device != cached.device:
-            return False
-        return bool(torch.equal(t, cached))
 
     def _encode(self, inputs, latents, key_mask, row_keep):
         B, N, C = latents.shape
         layers = [sa for _ in range(self._num_blocks) for sa in self.self_attends]
         fused = None
-        if (engine.FUSE_LN and engine.PRECISION == "bf16" and layers and B * N >= engine.FUSE_LN_MIN_ROWS
+        want = self.fuse_layernorm
+        if want is None:
+            want = engine.FUSE_LN and B * N >= engine.FUSE_LN_MIN_ROWS
+        pver = None
+        if want and self.fuse_layernorm is None:
+            pver = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            if self._fuse_ln_checked is not None and self._fuse_ln_checked[0] == pver and not self._fuse_ln_checked[1]:
+                want = False        # these parameters failed the offset check before
+        if (want and engine.PRECISION == "bf16" and layers
                 and latents.is_cuda and not any(sa.training and any(p > 0 for p in sa._dropout_probs) for sa in layers)):
             fused = [engine.prepared(sa, "fused", lambda sa=sa: engine.PreparedFusedLayer(sa)) for sa in self.self_attends]
             if not all(pf.usable() for pf in fused):
@@ -138,7 +146,7 @@ class PerceiverEncoder(nn.Module):
         # Latent tower with the LayerNorms folded into the projections: every residual-stream
         # state travels as (fp32 rows, their raw bf16 copy, per-row sum / sum of squares); no LayerNorm kernel runs.
         M = B * N
-        stats = torch.zeros((2 * len(layers) + 1, M, 2), dtype=torch.float32, device=latents.device)
+        stats = torch.empty((2 * len(layers) + 1, M, ops.stats_parts(C), 2), dtype=torch.float32, device=latents.device)
         z, zb = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
                                                     shard=self.key_shard, want_bf16_out=True, stats_out=stats[0])
         x = z.view(M, C)
@@ -147,6 +155,20 @@ class PerceiverEncoder(nn.Module):
             last = i == len(layers) - 1
             x, zb = engine.self_attention_block_fused(pf, x, zb, stats[2 * i], B=B, N=N, st_mid=stats[2 * i + 1],
                                                       st_out=None if last else stats[2 * i + 2])
+        if (pver is not None and (self._fuse_ln_checked is None or self._fuse_ln_checked[0] != pver)
+                and not torch.cuda.is_current_stream_capturing()):
+            s = stats[:2 * len(layers)].sum(2)                       # [states, M, 2]: (sum, sum of squares) per row
+            mean = s[..., 0] / C
+            var = (s[..., 1] / C - mean * mean).clamp_min(0.0)
+            offset = float((mean.abs() / (var + 1e-5).sqrt()).max())
+            self.fused_layernorm_offset = offset
+            ok = offset <= engine.FUSE_LN_MAX_OFFSET
+            self._fuse_ln_checked = (pver, ok)
+            if not ok:
+                import warnings
+                warnings.warn(f"perceiverio_pytorch_b200: residual-stream rows reach |mean| / std = {offset:.2f} > "
+                              f"{engine.FUSE_LN_MAX_OFFSET}; the latent tower keeps its LayerNorm kernels for this model")
+                return self._encode(inputs, latents, key_mask, row_keep)
         return x.view(B, N, C)
 
 

@@ -49,8 +49,16 @@ def make_cross_attention_mask(query_mask: torch.Tensor, kv_mask: torch.Tensor) -
     _, key_len = kv_mask.shape
     mask = torch.einsum("bi,bj->bij", (query_mask, kv_mask))
     assert mask.shape == (batch_size, query_len, key_len)
-    mask._pio_factors = (query_mask, kv_mask)
+    mask._pio_factors = (query_mask, kv_mask, _version_of(mask), _version_of(query_mask), _version_of(kv_mask))
     return mask
+
+
+def _version_of(t: torch.Tensor):
+    """In-place modification counter of a tensor (None for inference tensors, which do not track one)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
 
 def _factor_mask(attention_mask: Optional[torch.Tensor]):
@@ -62,6 +70,9 @@ def _factor_mask(attention_mask: Optional[torch.Tensor]):
     if attention_mask is None:
         return None, None
     fac = getattr(attention_mask, "_pio_factors", None)
+    if fac is not None and (fac[2], fac[3], fac[4]) != (_version_of(attention_mask), _version_of(fac[0]),
+                                                        _version_of(fac[1])):
+        fac = None      # the mask (or a factor) was edited in place after make_cross_attention_mask: factor it again
     if fac is None:
         m = attention_mask != 0
         qm, km = m.any(dim=2), m.any(dim=1)

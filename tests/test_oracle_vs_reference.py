@@ -83,6 +83,28 @@ def test_flow_wrapper_hot_path_small_image():
                             dict(num_heads=1, use_query_residual=False, final_project=True))
 
 
+def test_multimodal_wrapper_hot_path_small_video():
+    """The fourth wrapper (multimodal_perceiver.py:146-161): three modalities padded to a common width, the label token
+    replaced by the mask embedding (input_mask_probs label = 1.0, perceiver.py:481-493), subsampled output queries; the
+    hooks keep the last of the chunk calls."""
+    ns = ref_shim.load_wrappers()
+    torch.manual_seed(0)
+    model = ref_shim.perturb_parameters(
+        ns.multimodal.MultiModalPerceiver(img_size=(16, 16), num_frames=2, num_classes=20, audio_samples_per_frame=64,
+                                          num_self_attends_per_block=2, num_latents=48, num_latent_channels=512).eval())
+    images, audio = torch.rand(1, 2, 3, 16, 16), 0.1 * torch.randn(1, 128, 1)
+    rec, hooks = _hot_path_io(model.perceiver)
+    with torch.inference_mode():
+        out = model(images, audio, n_chunks=2)
+    assert out["image"].shape == images.shape and out["label"].shape == (1, 20)
+    (inputs, _), _, _ = rec["enc"]
+    assert inputs.shape[1] == 2 * 4 * 4 + 128 // 16 + 1          # image patches + audio patches + the label token
+    _check_wrapper_hot_path(model.perceiver, rec,
+                            dict(num_blocks=1, num_self_attends_per_block=2, num_cross_attend_heads=1,
+                                 num_self_attend_heads=8, use_query_residual=True),
+                            dict(num_heads=1, use_query_residual=False, final_project=True))
+
+
 @pytest.mark.parametrize("heads,qk,v", [(1, None, None), (4, 32, 80)])
 def test_cross_attention_random(heads, qk, v):
     ns = ref_shim.load_reference()

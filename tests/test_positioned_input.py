@@ -99,6 +99,77 @@ def test_whole_wrapper_glue_on_live_reference():
         assert float((pruned - want).abs().max()) <= 2e-5 * float(want.abs().max()), float((pruned - want).abs().max())
 
 
+def _densifying_encoder(enc, seen):
+    class _Densify(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def latents(self, inputs):
+            return self.inner.latents(inputs)
+
+        def forward(self, inputs, latents, *, input_mask=None):
+            seen.append(type(inputs).__name__)
+            if isinstance(inputs, pio.PositionedInput):
+                inputs = inputs.dense()
+            return self.inner(inputs, latents, input_mask=input_mask)
+    return _Densify(enc)
+
+
+def test_fused_input_glue_on_the_other_wrappers():
+    """swap_hot_path(..., fuse_input=True) routes every PerceiverIO.forward through `perceiver_io_forward`; `model(...)`
+    must keep working for all four wrappers.  Optical flow: its FlowQuery hands the preprocessed inputs back as the
+    decoder query (output_queries.py:73-76, :129-139), so the glue gives it the dense array while the encoder still gets
+    the two parts.  Language / multimodal (embedding preprocessor, several modalities) fall back to the reference's own
+    forward.  On CPU the reference's encoder / decoder stand in for ours: the test pins the glue."""
+    from oracle import ref_shim
+    ns = ref_shim.load_wrappers()
+    if ns is None:
+        pytest.skip("reference tree not mounted")
+    import functools
+    from perceiverio_pytorch_b200 import inputs as pin_mod
+    torch.manual_seed(0)
+    # ---- optical flow
+    flow = ref_shim.perturb_parameters(
+        ns.flow.FlowPerceiver(img_size=(16, 24), num_latents=32, num_self_attends_per_block=1).eval(), 3)
+    a, b = torch.randn(1, 3, 16, 24), torch.randn(1, 3, 16, 24)
+    with torch.inference_mode():
+        want = flow(a, b, test_mode=False)
+    seen = []
+    flow.perceiver._encoder = _densifying_encoder(flow.perceiver._encoder, seen)
+    flow.perceiver.forward = functools.partial(pin_mod.perceiver_io_forward, flow.perceiver)
+    with torch.inference_mode():
+        got = flow(a, b, test_mode=False)
+    assert seen == ["PositionedInput"], seen
+    assert got.shape == want.shape and torch.allclose(got, want, atol=1e-6, rtol=1e-5)
+    # the reference's `pos=` keyword is accepted and forwarded (own forward)
+    with torch.inference_mode():
+        assert flow.perceiver(torch.randn(1, 2, 27, 16, 24), pos=None).shape[0] == 1
+    # ---- language: an embedding preprocessor is not an image modality -> the module's own forward
+    lang = ref_shim.perturb_parameters(ns.language.LanguagePerceiver(num_self_attends_per_block=1, num_latents=16,
+                                                                     num_latent_channels=64, max_seq_len=64).eval(), 4)
+    tok = torch.randint(6, 262, (1, 64))
+    msk = torch.ones(1, 64, dtype=torch.bool)
+    msk[:, 40:] = False
+    with torch.inference_mode():
+        want = lang(tok, msk)
+    lang.perceiver.forward = functools.partial(pin_mod.perceiver_io_forward, lang.perceiver)
+    with torch.inference_mode():
+        got = lang(tok, msk)
+    assert torch.equal(got, want)
+    # ---- multimodal: several modalities with channel padding and modality masking -> the module's own forward
+    mm = ref_shim.perturb_parameters(
+        ns.multimodal.MultiModalPerceiver(img_size=(16, 16), num_frames=2, num_classes=20, audio_samples_per_frame=64,
+                                          num_self_attends_per_block=1, num_latents=16, num_latent_channels=512).eval(), 5)
+    images, audio = torch.rand(1, 2, 3, 16, 16), 0.1 * torch.randn(1, 128, 1)
+    with torch.inference_mode():
+        want = mm(images, audio, n_chunks=2)
+    mm.perceiver.forward = functools.partial(pin_mod.perceiver_io_forward, mm.perceiver)
+    with torch.inference_mode():
+        got = mm(images, audio, n_chunks=2)
+    assert all(torch.equal(got[k], want[k]) for k in want)
+
+
 def test_positioned_image_input_matches_reference_preprocessors():
     """Every single-modality image preprocessor configuration with a concatenated position encoding: the two parts of
     the PositionedInput, densified, are exactly what the reference's ImagePreprocessor returns."""

@@ -82,17 +82,135 @@ def perturb(module, seed):
                 prm.copy_(1.0 + 0.1 * torch.randn(prm.shape, generator=g))
 
 
-def timeit(fn, iters):
+_L2_FLUSH = None
+
+
+def timeit(fn, iters, flush=True):
+    """Mean device time of fn() over `iters` calls (CUDA events).  With `flush`, a 256 MiB buffer (> the 126 MB L2) is
+    overwritten before every call, so no call finds its operands or weights cached by the previous one; the flush's
+    own time (measured the same way) is subtracted."""
+    global _L2_FLUSH
+    if flush and _L2_FLUSH is None:
+        _L2_FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
+        if flush:
+            _L2_FLUSH.zero_()
         fn()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    t = a.elapsed_time(b) / iters
+    if flush:
+        a.record()
+        for _ in range(iters):
+            _L2_FLUSH.zero_()
+        b.record()
+        torch.cuda.synchronize()
+        t -= a.elapsed_time(b) / iters
+    return t
+
+
+def sustained_peak():
+    peak = 1397.9
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p)).get("bf16_tflops_sustained", peak))
+    return peak
+
+
+def measure_config(name, iters=10, eager=True):
+    """One config at full size -> dict (see module docstring).  `eager=False` skips the eagerly launched timings and the
+    per-family profile (bench.py's `other_configs` only wants the replayed-graph numbers)."""
+    peak = sustained_peak()
+    cfg = CONFIGS[name]
+    torch.manual_seed(0)
+    enc = pio.PerceiverEncoder(**cfg["enc"]).eval()
+    dec = pio.PerceiverDecoder(**cfg["dec"]).eval()
+    perturb(enc, 1)
+    perturb(dec, 2)
+    enc, dec = enc.cuda(), dec.cuda()
+    B, Nk, Nq = cfg["B"], cfg["Nk"], cfg["Nq"]
+    x = torch.randn(B, Nk, cfg["enc"]["num_input_channels"], device="cuda")
+    query = x if name == "flow" else torch.randn(B, Nq, cfg["dec"]["query_channels"], device="cuda")
+    imask = qmask = None
+    if cfg["masks"]:
+        imask = torch.zeros(B, Nk, dtype=torch.bool, device="cuda")
+        imask[:, :1500] = True
+        qmask = imask[:, :Nq].clone()
+    res = {"config": name, "B": B, "inputs": Nk, "latents": cfg["enc"]["num_latents"], "queries": Nq}
+    with torch.inference_mode():
+        lat = enc.latents(x)
+        rk = imask.any(dim=1, keepdim=True).expand(B, lat.shape[1]) if imask is not None else None
+
+        def f_enc():
+            return enc.cross_attend._forward_factored(lat, x, key_mask=imask, row_keep=rk)[0]
+
+        z0 = f_enc()
+
+        def f_tower(z=z0):
+            for _ in range(enc._num_blocks):
+                for sa in enc.self_attends:
+                    z = sa(z)
+            return z
+
+        z1 = f_tower()
+
+        def f_dec():
+            return dec(query, z1, query_mask=qmask)
+
+        def f_all():
+            return dec(query, enc(x, lat, input_mask=imask), query_mask=qmask)
+
+        if eager:
+            t_enc, t_tower, t_dec = timeit(f_enc, iters), timeit(f_tower, iters), timeit(f_dec, iters)
+            t_all = timeit(f_all, iters)
+            # per-kernel-family device time of one eager forward (library-side CUDA events around every launch)
+            _lib.profile_read()
+            _lib.profile_enable(True)
+            f_all()
+            torch.cuda.synchronize()
+            _lib.profile_enable(False)
+            res["kernel_families_one_forward"] = {k: {"ms": round(v["ms"], 4), "launches": v["launches"]}
+                                                  for k, v in _lib.profile_read().items() if v["launches"] > 0}
+            res["ms"] = {"encoder_xattn": round(t_enc, 4), "tower": round(t_tower, 4), "decoder": round(t_dec, 4),
+                         "forward_eager": round(t_all, 4)}
+    n0 = _lib.launch_count()
+    g = GraphedForward(lambda xx: dec(xx if name == "flow" else query, enc(xx, enc.latents(xx), input_mask=imask),
+                                      query_mask=qmask), [x], warmup=1)
+    res["launches_per_forward"] = (_lib.launch_count() - n0) // 2      # one warm-up + the capture
+    t_graph = timeit(lambda: g(g.inputs[0]), iters)
+    # the same three subsystems replayed from CUDA graphs: at batch 1 the eager numbers above are bound by the
+    # host's launch rate (7 launches per tower layer from Python), these are the device's
+    g_enc = GraphedForward(lambda xx: enc.cross_attend._forward_factored(enc.latents(xx), xx, key_mask=imask,
+                                                                         row_keep=rk)[0], [x], warmup=1)
+    t_enc_g = timeit(lambda: g_enc(g_enc.inputs[0]), iters)
+    g_tower = GraphedForward(lambda zz: f_tower(zz), [z0], warmup=1)
+    t_tower_g = timeit(lambda: g_tower(g_tower.inputs[0]), iters)
+    g_dec = GraphedForward(lambda zz: dec(query, zz, query_mask=qmask), [z1], warmup=1)
+    t_dec_g = timeit(lambda: g_dec(g_dec.inputs[0]), iters)
+    del g_enc, g_tower, g_dec
+    fe, ft, fd = flops(cfg)
+    tf = lambda fl, ms: round(fl / (ms * 1e-3) / 1e12, 1)   # noqa: E731
+    res.update({
+        "gflop_reference_algorithm": {"encoder": round(fe / 1e9, 1), "tower": round(ft / 1e9, 1),
+                                      "decoder": round(fd / 1e9, 1)},
+        "ms_graph": {"encoder_xattn": round(t_enc_g, 4), "tower": round(t_tower_g, 4), "decoder": round(t_dec_g, 4),
+                     "forward": round(t_graph, 4)},
+        "tflops": {"encoder_xattn": tf(fe, t_enc_g), "tower": tf(ft, t_tower_g), "decoder": tf(fd, t_dec_g),
+                   "forward_graph": tf(fe + ft + fd, t_graph)},
+        "frac_of_sustained_bf16_peak": {"encoder_xattn": round(tf(fe, t_enc_g) / peak, 3),
+                                        "tower": round(tf(ft, t_tower_g) / peak, 3),
+                                        "decoder": round(tf(fd, t_dec_g) / peak, 3),
+                                        "forward_graph": round(tf(fe + ft + fd, t_graph) / peak, 3)},
+        "samples_per_s_graph": round(B / (t_graph * 1e-3), 2),
+        "l2": "256 MiB buffer overwritten before every timed call (its own time subtracted)"})
+    del enc, dec, x, query, g
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -100,91 +218,8 @@ def main():
     ap.add_argument("--configs", nargs="*", default=list(CONFIGS))
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
-    peak = 1397.9
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        peak = float(json.load(open(p)).get("bf16_tflops_sustained", peak))
     for name in args.configs:
-        cfg = CONFIGS[name]
-        torch.manual_seed(0)
-        enc = pio.PerceiverEncoder(**cfg["enc"]).eval()
-        dec = pio.PerceiverDecoder(**cfg["dec"]).eval()
-        perturb(enc, 1)
-        perturb(dec, 2)
-        enc, dec = enc.cuda(), dec.cuda()
-        B, Nk, Nq = cfg["B"], cfg["Nk"], cfg["Nq"]
-        x = torch.randn(B, Nk, cfg["enc"]["num_input_channels"], device="cuda")
-        query = torch.randn(B, Nq, cfg["dec"]["query_channels"], device="cuda")
-        imask = qmask = None
-        if cfg["masks"]:
-            imask = torch.zeros(B, Nk, dtype=torch.bool, device="cuda")
-            imask[:, :1500] = True
-            qmask = imask[:, :Nq].clone()
-
-        with torch.inference_mode():
-            lat = enc.latents(x)
-            rk = imask.any(dim=1, keepdim=True).expand(B, lat.shape[1]) if imask is not None else None
-
-            def f_enc():
-                return enc.cross_attend._forward_factored(lat, x, key_mask=imask, row_keep=rk)[0]
-
-            z0 = f_enc()
-
-            def f_tower(z=z0):
-                for _ in range(enc._num_blocks):
-                    for sa in enc.self_attends:
-                        z = sa(z)
-                return z
-
-            z1 = f_tower()
-
-            def f_dec():
-                return dec(query, z1, query_mask=qmask)
-
-            def f_all():
-                return dec(query, enc(x, lat, input_mask=imask), query_mask=qmask)
-
-            t_enc, t_tower, t_dec = timeit(f_enc, args.iters), timeit(f_tower, args.iters), timeit(f_dec, args.iters)
-            t_all = timeit(f_all, args.iters)
-            # per-kernel-family device time of one eager forward (library-side CUDA events around every launch)
-            _lib.profile_read()
-            _lib.profile_enable(True)
-            f_all()
-            torch.cuda.synchronize()
-            _lib.profile_enable(False)
-            fam = {k: {"ms": round(v["ms"], 4), "launches": v["launches"]} for k, v in _lib.profile_read().items()
-                   if v["launches"] > 0}
-        g = GraphedForward(lambda xx: dec(query, enc(xx, enc.latents(xx), input_mask=imask), query_mask=qmask), [x])
-        t_graph = timeit(lambda: g(g.inputs[0]), args.iters)
-        # the same three subsystems replayed from CUDA graphs: at batch 1 the eager numbers above are bound by the
-        # host's launch rate (7 launches per tower layer from Python), these are the device's
-        g_enc = GraphedForward(lambda xx: enc.cross_attend._forward_factored(enc.latents(xx), xx, key_mask=imask,
-                                                                             row_keep=rk)[0], [x])
-        t_enc_g = timeit(lambda: g_enc(g_enc.inputs[0]), args.iters)
-        g_tower = GraphedForward(lambda zz: f_tower(zz), [z0])
-        t_tower_g = timeit(lambda: g_tower(g_tower.inputs[0]), args.iters)
-        g_dec = GraphedForward(lambda zz: dec(query, zz, query_mask=qmask), [z1])
-        t_dec_g = timeit(lambda: g_dec(g_dec.inputs[0]), args.iters)
-        del g_enc, g_tower, g_dec
-        fe, ft, fd = flops(cfg)
-        tf = lambda fl, ms: round(fl / (ms * 1e-3) / 1e12, 1)   # noqa: E731
-        print(json.dumps({
-            "config": name, "B": B, "inputs": Nk, "latents": cfg["enc"]["num_latents"], "queries": Nq,
-            "gflop_reference_algorithm": {"encoder": round(fe / 1e9, 1), "tower": round(ft / 1e9, 1),
-                                          "decoder": round(fd / 1e9, 1)},
-            "ms": {"encoder_xattn": round(t_enc, 4), "tower": round(t_tower, 4), "decoder": round(t_dec, 4),
-                   "forward_eager": round(t_all, 4), "forward_graph": round(t_graph, 4)},
-            "ms_graph": {"encoder_xattn": round(t_enc_g, 4), "tower": round(t_tower_g, 4), "decoder": round(t_dec_g, 4)},
-            "tflops": {"encoder_xattn": tf(fe, t_enc_g), "tower": tf(ft, t_tower_g), "decoder": tf(fd, t_dec_g),
-                       "forward_graph": tf(fe + ft + fd, t_graph)},
-            "frac_of_sustained_bf16_peak": {"encoder_xattn": round(tf(fe, t_enc_g) / peak, 3),
-                                            "tower": round(tf(ft, t_tower_g) / peak, 3),
-                                            "decoder": round(tf(fd, t_dec_g) / peak, 3),
-                                            "forward_graph": round(tf(fe + ft + fd, t_graph) / peak, 3)},
-            "kernel_families_one_forward": fam,
-            "samples_per_s_graph": round(B / (t_graph * 1e-3), 2)}), flush=True)
-        del enc, dec, x, query, g
-        torch.cuda.empty_cache()
+        print(json.dumps(measure_config(name, args.iters)), flush=True)
 
 
 if __name__ == "__main__":

@@ -245,7 +245,7 @@ def group_perf():
     W1 = torch.randn(1024, 1024, device=dev).to(torch.bfloat16)
     o16 = torch.empty(M, 1024, dtype=torch.bfloat16, device=dev)
     o32 = torch.empty(M, 1024, device=dev)
-    st = torch.zeros(M, 2, device=dev)
+    st = ops.empty_row_stats(M, 1024, dev).zero_()
     cs = torch.randn(1024, device=dev)
     fl = 2 * M * 1024 * 1024
     t = _time(lambda: ops.gemm(A, W1, M=M, N=1024, K=1024, bias=bias, residual=res, ldr=1024, out_f32=o32, ldo32=1024, kernel=2))
