@@ -15,6 +15,12 @@
  *  - bf16 matrices are row-major with a leading dimension (in elements) that is a multiple of 8 (16 bytes, the
  *    TMA global-stride rule) and a 16-byte aligned base.  Logical widths may be odd (261, 322, 1026): TMA
  *    zero-fills out-of-bounds columns, so no padding content is ever read.
+ *  - 16-bit format: every args struct with 16-bit operands or outputs carries an `fp16` field.  0 (default): bfloat16.
+ *    1: IEEE half — same tensor-core rate (tcgen05.mma kind::f16 takes both), 11 instead of 8 mantissa bits, i.e. 8x less
+ *    operand rounding, at the price of fp16's range (conversions saturate at 65504).  All 16-bit buffers of one call use
+ *    the same format.  The optical-flow recipe needs it: with bf16 operands the reference ALGORITHM itself misses the
+ *    1e-2 bound there, and the reference's own mixed-precision mode is fp16 autocast
+ *    (flow_perceiver.py:14,129).
  *  - Return value: 0 on success, negative pio_status otherwise; pio_last_error() gives a thread-local message.
  *    Nothing throws, aborts or falls back to a CPU path.
  */
@@ -27,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 9
+#define PIO_ABI_VERSION 10
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -64,6 +70,7 @@ typedef struct pio_layernorm_args {
                        [hi | lo | hi] (split = 1, the A side of a product) or [hi | hi | lo] (split = 2, the B side) with
                        hi = bf16(v), lo = bf16(v - hi); one K = 3 * pad8(C) GEMM of an A-side by a B-side operand
                        evaluates hi*hi + lo*hi + hi*lo in fp32 */
+  int32_t fp16;     /* 16-bit format of y: 0 = bf16, 1 = fp16 (not with split) */
 } pio_layernorm_args;
 int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream);
 
@@ -120,6 +127,7 @@ typedef struct pio_gemm_args {
    * consumer that starts where its producer finished finds that producer's last-written rows still in L2. */
   int32_t reverse_tiles;
   int32_t row_stats_parts;    /* partial statistics per row in row_stats_out / row_stats_in (see above) */
+  int32_t fp16;               /* 16-bit format of A, B and out_bf16: 0 = bf16, 1 = fp16 */
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 
@@ -145,6 +153,7 @@ typedef struct pio_softmax_args {
   const uint8_t* dense_mask; int64_t dm_stride_b; int64_t dm_stride_r;                  /* [batch, rows, cols] */
   const float* bias; int64_t bias_stride_b; int64_t bias_stride_r; int64_t bias_stride_c; /* broadcast strides (elements) */
   float* P_f32; int64_t ldpf; int64_t stridePf;                                          /* [batch, rows, cols] */
+  int32_t fp16;     /* 16-bit format of P: 0 = bf16, 1 = fp16 (not with split) */
 } pio_softmax_args;
 int pio_softmax_bf16(const pio_softmax_args* a, void* stream);
 
@@ -171,6 +180,7 @@ typedef struct pio_attention_args {
   int32_t num_splits;                            /* key-axis splits inside this GPU (>= 1) */
   int32_t partial;                               /* 1: always emit (O, m, l) partials */
   float* O_part; float* m_part; float* l_part;
+  int32_t fp16;                                  /* 16-bit format of Q, K, V, P and O: 0 = bf16, 1 = fp16 */
 } pio_attention_args;
 int pio_attention_fwd(const pio_attention_args* a, void* stream);
 /* 0 if pio_attention_fwd supports these head sizes, PIO_ERR_UNSUPPORTED otherwise (host picks the GEMM path). */
@@ -197,6 +207,7 @@ typedef struct pio_combine_args {
    * straight through NVLink instead of reading a gathered copy, and O_part / m_part / l_part / part_stride_* are
    * ignored.  The caller orders the ranks' writes before this launch (a symmetric-memory barrier on the stream). */
   const float* const* part_ptrs;
+  int32_t fp16;                                                   /* 16-bit format of O: 0 = bf16, 1 = fp16 */
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
 
@@ -235,6 +246,7 @@ typedef struct pio_layernorm_concat_args {
   const float* gamma; const float* beta; /* [Cf + Cp] or NULL */
   int32_t B, N, Cf, Cp;
   float eps;
+  int32_t fp16;                          /* 16-bit format of y: 0 = bf16, 1 = fp16 */
 } pio_layernorm_concat_args;
 int pio_layernorm_concat_bf16(const pio_layernorm_concat_args* a, void* stream);
 

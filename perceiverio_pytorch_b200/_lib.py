@@ -25,13 +25,13 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 class LayerNormArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
-                ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32), ("split", i32)]
+                ("rows", i64), ("C", i32), ("normalize", i32), ("eps", f32), ("split", i32), ("fp16", i32)]
 
 
 class LayerNormConcatArgs(C.Structure):
     _fields_ = [("feat", vp), ("feat_stride_b", i64), ("feat_stride_n", i64), ("feat_stride_c", i64),
                 ("pos", vp), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp),
-                ("B", i32), ("N", i32), ("Cf", i32), ("Cp", i32), ("eps", f32)]
+                ("B", i32), ("N", i32), ("Cf", i32), ("Cp", i32), ("eps", f32), ("fp16", i32)]
 
 
 class GemmArgs(C.Structure):
@@ -47,7 +47,7 @@ class GemmArgs(C.Structure):
                 ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
                 ("tile_n", i32), ("max_ctas", i32), ("cluster_m", i32), ("kernel", i32),
                 ("row_stats_out", vp), ("row_stats_in", vp), ("ln_colsum", vp), ("ln_channels", i32), ("ln_eps", f32),
-                ("reverse_tiles", i32), ("row_stats_parts", i32)]
+                ("reverse_tiles", i32), ("row_stats_parts", i32), ("fp16", i32)]
 
 
 class SoftmaxArgs(C.Structure):
@@ -59,7 +59,7 @@ class SoftmaxArgs(C.Structure):
                 ("scale", f32), ("split", i32),
                 ("dense_mask", vp), ("dm_stride_b", i64), ("dm_stride_r", i64),
                 ("bias", vp), ("bias_stride_b", i64), ("bias_stride_r", i64), ("bias_stride_c", i64),
-                ("P_f32", vp), ("ldpf", i64), ("stridePf", i64)]
+                ("P_f32", vp), ("ldpf", i64), ("stridePf", i64), ("fp16", i32)]
 
 
 class AttentionArgs(C.Structure):
@@ -72,7 +72,7 @@ class AttentionArgs(C.Structure):
                 ("row_keep", vp), ("stride_rk", i64),
                 ("O", vp), ("ldo", i64), ("strideO", i64),
                 ("num_splits", i32), ("partial", i32),
-                ("O_part", vp), ("m_part", vp), ("l_part", vp)]
+                ("O_part", vp), ("m_part", vp), ("l_part", vp), ("fp16", i32)]
 
 
 class CombineArgs(C.Structure):
@@ -81,7 +81,7 @@ class CombineArgs(C.Structure):
                 ("parts", i32), ("B", i32), ("H", i32), ("Nq", i32), ("dv", i32),
                 ("row_keep", vp), ("stride_rk", i64),
                 ("O", vp), ("ldo", i64), ("strideO", i64),
-                ("O_out_part", vp), ("m_out", vp), ("l_out", vp), ("part_ptrs", vp)]
+                ("O_out_part", vp), ("m_out", vp), ("l_out", vp), ("part_ptrs", vp), ("fp16", i32)]
 
 
 class LinearF32Args(C.Structure):
@@ -128,7 +128,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 9:
+        if lib.pio_abi_version() != 10:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

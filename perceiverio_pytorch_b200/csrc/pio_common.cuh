@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,6 +29,28 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 16-bit operand / activation format of a launch (pio_*_args.fp16): bf16 (8-bit mantissa, fp32's range) or fp16 (11-bit
+// mantissa: 8x less operand rounding, range 65504 — conversions saturate instead of producing inf).  tcgen05.mma
+// kind::f16 runs both at the same rate; the format only changes the instruction descriptor and these conversions.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+// run-time form for the kernels that are bound by memory, not by instruction issue
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint16_t cvt16(float v, int f16) { return (uint16_t)(pack16x2(v, 0.f, f16) & 0xffffu); }
+__device__ __forceinline__ float cvt16_back(uint16_t h, int f16) {
+  return f16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
 }
 
 // Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue one instruction for two lanes) and 3-input max (FMNMX3).
@@ -392,13 +415,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= 2ull << 61;
   return d;
 }
-// 32-bit instruction descriptor for kind::f16, fp32 accumulate.  ab_fmt: 0 = fp16, 1 = bf16.
+// 32-bit instruction descriptor for kind::f16, fp32 accumulate.  ab_fmt: 0 = fp16, 1 = bf16 (idesc_fmt(fp16 flag)).
 // a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t ab_fmt, uint32_t a_mn,
                                                       uint32_t b_mn) {
   return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) |
          ((M >> 4) << 24);
 }
+
+__host__ __device__ constexpr uint32_t idesc_fmt(int fp16) { return fp16 ? 0u : 1u; }
 
 // Byte offset of element (row r, 16-byte chunk c) inside a [rows x 128 B] SWIZZLE_128B tile whose base is
 // 1024-byte aligned (the layout TMA produces and UMMA expects): chunk index XOR (row % 8).

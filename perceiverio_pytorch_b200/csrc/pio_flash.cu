@@ -16,6 +16,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pio_common.cuh"
 #include "pio_host.h"
 
@@ -23,6 +25,7 @@ namespace pio {
 
 struct FlashParams {
   int B, H, Nq, Nk, dqk, dv;
+  int fp16;               // 16-bit operand / output format: 0 = bf16, 1 = fp16
   int q_bcast;            // Q has a single batch entry shared by every b
   float scale_log2;       // scale * log2(e)
   const uint8_t* key_mask; long long stride_km;
@@ -158,7 +161,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // All 32 lanes run the schedule and wait on the barriers; one elected lane issues each tcgen05 instruction and the
     // descriptors advance as 32-bit low words.  (Inside an `if (lane == 0)` region every MMA cost ~25 dependent vector
     // instructions + R2UR moves — several times the 32..128 cycles the MMA itself takes on the tensor pipe.)
-    constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
+    const uint32_t idesc_s = make_idesc_f16(128, BN, idesc_fmt(p.fp16), 0, 0);
     const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
     const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sKV) + (SAME ? 0 : NQC * Cfg::CHUNK_BYTES), Cfg::CHUNK_BYTES, 1024);
@@ -184,7 +187,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t a0 = tmem_base + (j & 1) * BN;   // P_j overlays the first BN/2 columns of S_j (bf16 pairs)
       for (int nb = 0; nb * 256 < dv_n; ++nb) {
         const int n = min(256, dv_n - nb * 256);
-        const uint32_t idesc_pv = make_idesc_f16(128, n, 1, /*A (TMEM) K-major*/ 0, /*B MN-major*/ 1);
+        const uint32_t idesc_pv = make_idesc_f16(128, n, idesc_fmt(p.fp16), /*A (TMEM) K-major*/ 0, /*B MN-major*/ 1);
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks) {
           if (elect_one())
@@ -309,18 +312,24 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c) {
         uint32_t w[16];
+        // one uniform branch per 32 keys selects the 16-bit format; the loop body itself stays select-free
+        auto exp_block = [&](auto f16tag) {
+          constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
-                                    sc2, nm2);
-          float t0, t1;
-          unpack_f32x2(t2, t0, t1);
-          const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-          w[i] = pack_bf16x2(e0, e1);
-          const uint64_t pr = pack_f32x2(e0, e1);   // un-rounded: RN is unbiased, see pio_flash2.cu
-          if (i & 1) lb = fadd2(lb, pr);
-          else la = fadd2(la, pr);
-        }
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
+                                      sc2, nm2);
+            float t0, t1;
+            unpack_f32x2(t2, t0, t1);
+            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+            w[i] = pack16x2<F16>(e0, e1);
+            const uint64_t pr = pack_f32x2(e0, e1);   // un-rounded: RN is unbiased, see pio_flash2.cu
+            if (i & 1) lb = fadd2(lb, pr);
+            else la = fadd2(la, pr);
+          }
+        };
+        if (p.fp16) exp_block(std::true_type{});
+        else exp_block(std::false_type{});
         // P overwrites S in place (two bf16 values per 32-bit column).  Both warps of the pair have their S values in
         // registers (the pair barrier above), so no unread S column is clobbered.
         tmem_st16(tmem_base + (j & 1) * BN + lane_off + (half * HC + c * 32) / 2, w);
@@ -359,16 +368,16 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
-              w.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
-              w.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
-              w.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+              w.x = pack16x2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv, p.fp16);
+              w.y = pack16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv, p.fp16);
+              w.z = pack16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv, p.fp16);
+              w.w = pack16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv, p.fp16);
               reinterpret_cast<uint4*>(op)[g] = w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c + i < p.dv) op[i] = __float2bfloat16_rn(__uint_as_float(r[i]) * inv);
+              if (c + i < p.dv) reinterpret_cast<uint16_t*>(op)[i] = cvt16(__uint_as_float(r[i]) * inv, p.fp16);
           }
         }
       }
@@ -432,6 +441,7 @@ static int launch_flash(const pio_attention_args* a, const DeviceInfo& dev, cuda
   }
   FlashParams p;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.dqk = a->dqk; p.dv = a->dv;
+  p.fp16 = a->fp16 ? 1 : 0;
   p.q_bcast = q_bcast;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.key_mask = a->key_mask; p.stride_km = a->stride_km;

@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pio_common.cuh"
 #include "pio_host.h"
 
@@ -42,6 +44,7 @@ __device__ unsigned long long g_f2_trace[12 * 2 * 512];
 
 struct Flash2Params {
   int B, H, Nq, Nk, dqk, dv;
+  int fp16;               // 16-bit operand / output format: 0 = bf16, 1 = fp16
   int q_bcast;
   float scale_log2;
   const uint8_t* key_mask; long long stride_km;
@@ -230,8 +233,8 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // vector arithmetic plus R2UR moves (~20 dependent instructions per 64-cycle MMA: the issuer, not the tensor
       // pipe, paced the first version of this kernel).
       const bool leader = (lane == 0);
-      constexpr uint32_t idesc_s = make_idesc_f16(128, BN, 1, 0, 0);
-      const uint32_t idesc_pv = make_idesc_f16(128, dv_n, 1, /*A (TMEM) K-major*/ 0, /*B MN-major*/ 1);
+      const uint32_t idesc_s = make_idesc_f16(128, BN, idesc_fmt(p.fp16), 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(128, dv_n, idesc_fmt(p.fp16), /*A (TMEM) K-major*/ 0, /*B MN-major*/ 1);
       const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), Cfg::CHUNK_BYTES, 1024);
@@ -447,21 +450,27 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t w[16];
+          // one uniform branch per 32 keys selects the 16-bit format; the loop body itself stays select-free
+          auto exp_block = [&](auto f16tag) {
+            constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
-                                      sc2, nm2);
-            float t0, t1;
-            unpack_f32x2(t2, t0, t1);
-            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-            w[i] = pack_bf16x2(e0, e1);
-            // the row sum takes the un-rounded exponentials: round-to-nearest is unbiased, so l differs from the sum of
-            // the bf16 values the tensor core multiplies by ~2^-9 / sqrt(Nk) relative, and rebuilding the rounded values
-            // cost two integer instructions per pair in a loop that is issue-bound (one warp per scheduler)
-            const uint64_t pr = pack_f32x2(e0, e1);
-            if (i & 1) lb = fadd2(lb, pr);
-            else la = fadd2(la, pr);
-          }
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
+                                        sc2, nm2);
+              float t0, t1;
+              unpack_f32x2(t2, t0, t1);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+              w[i] = pack16x2<F16>(e0, e1);
+              // the row sum takes the un-rounded exponentials: round-to-nearest is unbiased, so l differs from the sum of
+              // the 16-bit values the tensor core multiplies by ~2^-9 / sqrt(Nk) relative, and rebuilding the rounded
+              // values cost two integer instructions per pair in a loop that is issue-bound (one warp per scheduler)
+              const uint64_t pr = pack_f32x2(e0, e1);
+              if (i & 1) lb = fadd2(lb, pr);
+              else la = fadd2(la, pr);
+            }
+          };
+          if (p.fp16) exp_block(std::true_type{});
+          else exp_block(std::false_type{});
           tmem_st16(t_s + c * 16, w);
           if (c == BN / 64 - 1) {   // first half of the key tile is in TMEM
             tmem_wait_st();
@@ -506,10 +515,10 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(r[8 * gq]) * inv, __uint_as_float(r[8 * gq + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv);
+            w.x = pack16x2(__uint_as_float(r[8 * gq]) * inv, __uint_as_float(r[8 * gq + 1]) * inv, p.fp16);
+            w.y = pack16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv, p.fp16);
+            w.z = pack16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv, p.fp16);
+            w.w = pack16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv, p.fp16);
             *reinterpret_cast<uint4*>(chunk + sw128_offset((uint32_t)row, (uint32_t)(((c & 63) >> 3) + gq))) = w;
           }
         }
@@ -532,7 +541,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               uint32_t w[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                w[i] = pack_bf16x2(__uint_as_float(r[16 * gq + 2 * i]) * inv, __uint_as_float(r[16 * gq + 2 * i + 1]) * inv);
+                w[i] = pack16x2(__uint_as_float(r[16 * gq + 2 * i]) * inv, __uint_as_float(r[16 * gq + 2 * i + 1]) * inv, p.fp16);
               asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + 16 * gq), "r"(w[0]),
                            "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                            : "memory");
@@ -541,16 +550,16 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
               uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(r[8 * gq]) * inv, __uint_as_float(r[8 * gq + 1]) * inv);
-              w.y = pack_bf16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv);
-              w.z = pack_bf16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv);
-              w.w = pack_bf16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv);
+              w.x = pack16x2(__uint_as_float(r[8 * gq]) * inv, __uint_as_float(r[8 * gq + 1]) * inv, p.fp16);
+              w.y = pack16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv, p.fp16);
+              w.z = pack16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv, p.fp16);
+              w.w = pack16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv, p.fp16);
               reinterpret_cast<uint4*>(op)[gq] = w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c + i < p.dv) op[i] = __float2bfloat16_rn(__uint_as_float(r[i]) * inv);
+              if (c + i < p.dv) reinterpret_cast<uint16_t*>(op)[i] = cvt16(__uint_as_float(r[i]) * inv, p.fp16);
           }
         }
       }
@@ -613,6 +622,7 @@ static int launch_flash2_cfg(const pio_attention_args* a, const DeviceInfo& dev,
   Flash2Params p;
   p.staged = staged ? 1 : 0;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.dqk = a->dqk; p.dv = a->dv;
+  p.fp16 = a->fp16 ? 1 : 0;
   p.q_bcast = q_bcast;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.key_mask = a->key_mask; p.stride_km = a->stride_km;

@@ -18,6 +18,7 @@ namespace pio {
 
 struct GemmEpilogue {
   int M, N, K, batch;
+  int fp16;              // 16-bit operand / output format: 0 = bf16, 1 = fp16
   int tiles_m, tiles_n;
   int m_groups;          // ceil(tiles_m / CL): M tiles are handed out to a cluster CL at a time
   int a_bcast, b_bcast;  // operand shared by every batch entry (batch stride 0)
@@ -151,7 +152,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer =================
-      constexpr uint32_t idesc = make_idesc_f16(128, BN, /*bf16*/ 1, /*a K-major*/ 0, B_MN ? 1 : 0);
+      const uint32_t idesc = make_idesc_f16(128, BN, idesc_fmt(ep.fp16), /*a K-major*/ 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -270,16 +271,16 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 q;
-                q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-                q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                q.x = pack16x2(v[8 * j], v[8 * j + 1], ep.fp16);
+                q.y = pack16x2(v[8 * j + 2], v[8 * j + 3], ep.fp16);
+                q.z = pack16x2(v[8 * j + 4], v[8 * j + 5], ep.fp16);
+                q.w = pack16x2(v[8 * j + 6], v[8 * j + 7], ep.fp16);
                 reinterpret_cast<uint4*>(op)[j] = q;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < ep.N) op[j] = __float2bfloat16_rn(v[j]);
+                if (col0 + j < ep.N) reinterpret_cast<uint16_t*>(op)[j] = cvt16(v[j], ep.fp16);
             }
           }
         } else {
@@ -326,12 +327,13 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (o16_z) {
                 __nv_bfloat16* op = o16_z + static_cast<long long>(grow) * ep.ldo16 + gcol;
                 if (quad && vec16) {
-                  *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+                  *reinterpret_cast<uint2*>(op) = make_uint2(pack16x2(w.x, w.y, ep.fp16), pack16x2(w.z, w.w, ep.fp16));
                 } else {
-                  op[0] = __float2bfloat16_rn(w.x);
-                  if (gcol + 1 < ep.N) op[1] = __float2bfloat16_rn(w.y);
-                  if (gcol + 2 < ep.N) op[2] = __float2bfloat16_rn(w.z);
-                  if (gcol + 3 < ep.N) op[3] = __float2bfloat16_rn(w.w);
+                  uint16_t* oh = reinterpret_cast<uint16_t*>(op);
+                  oh[0] = cvt16(w.x, ep.fp16);
+                  if (gcol + 1 < ep.N) oh[1] = cvt16(w.y, ep.fp16);
+                  if (gcol + 2 < ep.N) oh[2] = cvt16(w.z, ep.fp16);
+                  if (gcol + 3 < ep.N) oh[3] = cvt16(w.w, ep.fp16);
                 }
               }
             }
@@ -383,6 +385,7 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   }
   GemmEpilogue ep;
   ep.M = a->M; ep.N = a->N; ep.K = a->K; ep.batch = a->batch;
+  ep.fp16 = a->fp16 ? 1 : 0;
   ep.a_bcast = a_bcast ? 1 : 0; ep.b_bcast = b_bcast ? 1 : 0;
   ep.tiles_m = (a->M + 127) / 128;
   ep.tiles_n = (a->N + BN - 1) / BN;

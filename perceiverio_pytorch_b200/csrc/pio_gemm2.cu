@@ -16,6 +16,8 @@
 // 128-column half (w-4)/4 of the tile.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pio_common.cuh"
 #include "pio_host.h"
 
@@ -23,6 +25,7 @@ namespace pio {
 
 struct Gemm2Params {
   int M, N, K, batch;
+  int fp16;                      // 16-bit operand / output format: 0 = bf16, 1 = fp16
   int tiles_n, m_pairs;          // 256-column tiles, 256-row CTA-pair tiles
   int a_bcast, b_bcast, r_bcast; // operand shared by every batch entry
   const float* bias;
@@ -174,7 +177,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // All 32 lanes run the schedule and the barrier waits; one elected lane issues each tcgen05 instruction, and the
       // descriptors advance as 32-bit low words (inside an `if (lane == 0)` region every MMA costs ~25 dependent
       // vector instructions + R2UR moves, about as long as the 128-cycle MMA itself).
-      constexpr uint32_t idesc = make_idesc_f16(256, Cfg::BN, /*bf16*/ 1, 0, 0);
+      const uint32_t idesc = make_idesc_f16(256, Cfg::BN, idesc_fmt(p.fp16), 0, 0);
       const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint32_t d_lo = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
       int stage = 0;
@@ -381,10 +384,17 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (p.raw_bf16 != nullptr) {
             // bf16 copy of the un-normalised row segment (32 bytes per row) for the fused LayerNorm of the consumer
             uint4* rp = reinterpret_cast<uint4*>(slot_raw + lane * 32);
-            rp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                               pack_bf16x2(v[6], v[7]));
-            rp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                               pack_bf16x2(v[14], v[15]));
+            if (p.fp16) {
+              rp[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                 pack_f16x2(v[6], v[7]));
+              rp[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]),
+                                 pack_f16x2(v[14], v[15]));
+            } else {
+              rp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+              rp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                 pack_bf16x2(v[14], v[15]));
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -403,15 +413,21 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
           if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
           __syncwarp();
+          // one uniform branch per 64-value chunk picks the conversion (no per-element select in the issue stream)
+          auto stage_out = [&](auto f16tag) {
+            constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(slot_out + sw128_offset(lane, j)) = q;
-          }
+            for (int j = 0; j < 8; ++j) {
+              uint4 q;
+              q.x = pack16x2<F16>(v[8 * j], v[8 * j + 1]);
+              q.y = pack16x2<F16>(v[8 * j + 2], v[8 * j + 3]);
+              q.z = pack16x2<F16>(v[8 * j + 4], v[8 * j + 5]);
+              q.w = pack16x2<F16>(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(slot_out + sw128_offset(lane, j)) = q;
+            }
+          };
+          if (p.fp16) stage_out(std::true_type{});
+          else stage_out(std::false_type{});
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -495,6 +511,7 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   }
   Gemm2Params p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+  p.fp16 = a->fp16 ? 1 : 0;
   p.tiles_n = (a->N + Cfg::BN - 1) / Cfg::BN;
   p.m_pairs = (a->M + 255) / 256;
   p.a_bcast = a_bcast; p.b_bcast = b_bcast; p.r_bcast = r_bcast;

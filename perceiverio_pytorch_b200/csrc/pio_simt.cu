@@ -1,5 +1,7 @@
 // HBM-bound SIMT kernels: LayerNorm + bf16 cast, row softmax (materialised attention path) and the
 // log-sum-exp merge of partial attention results (key splits / key-axis shards across GPUs).
+#include <type_traits>
+
 #include "pio_common.cuh"
 #include "pio_host.h"
 
@@ -33,6 +35,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
                                                                 int mode, float eps) {
   pdl_sync();
   const int normalize = mode & 1;
+  const int f16 = (mode >> 3) & 1;   // 16-bit output format: 0 = bf16, 1 = fp16 (never with the split layouts)
   const int lane = threadIdx.x & 31;
   // Rows are walked from the END of the array: x was just written front-to-back by the producing GEMM (or H2D copy),
   // so its tail is what is still resident in the 126 MB L2; and the bf16 rows written last (the front) are the first
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
           o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
         }
       }
-      const uint2 hi = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      const uint2 hi = make_uint2(pack16x2(o.x, o.y, f16), pack16x2(o.z, o.w, f16));
       yr[c] = hi;
       if (split) {
         const uint2 lo = make_uint2(pack_bf16x2(o.x - __uint_as_float(hi.x << 16), o.y - __uint_as_float(hi.x & 0xffff0000u)),
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
   // each warp walks many row groups with the affine parameters held in registers and as little per-element control
   // flow as possible.
   const int normalize = mode & 1;
+  const int f16 = SPLIT ? 0 : (mode >> 3) & 1;   // 16-bit output format: 0 = bf16, 1 = fp16
   // validation mode: three segments of ldy / 3 columns, [hi | lo | hi] (A side, bit 1) or [hi | hi | lo] (B side, bit 2)
   const bool b_side = (mode & 4) != 0;
   const int seg = SPLIT ? (int)(ldy / 3) : (int)ldy;
@@ -162,6 +166,10 @@ __global__ void __launch_bounds__(128) pio_layernorm_kernel(const float* __restr
           // (v - mean) * rstd * gamma + beta; pad columns (C <= c < seg) have v = 0, gamma = 1, beta = 0 -> forced to 0
           float o = fmaf(fmaf(v[r][i], rstd, nmr), g[i], bt[i]);
           if (c >= C) o = 0.f;
+          if (!SPLIT) {
+            reinterpret_cast<uint16_t*>(yr)[c] = cvt16(o, f16);
+            continue;
+          }
           const __nv_bfloat16 hi = __float2bfloat16_rn(o);
           yr[c] = hi;
           if (SPLIT) {
@@ -194,9 +202,11 @@ __global__ void __launch_bounds__(LNB_THREADS) pio_layernorm_bulk_kernel(const f
                                                                          __nv_bfloat16* __restrict__ y, int ldy,
                                                                          const float* __restrict__ gamma,
                                                                          const float* __restrict__ beta,
-                                                                         long long ngroups, int R, int C, int normalize,
+                                                                         long long ngroups, int R, int C, int mode,
                                                                          float eps) {
   pdl_sync();
+  const int normalize = mode & 1;
+  const int f16 = (mode >> 3) & 1;   // 16-bit output format: 0 = bf16, 1 = fp16
   extern __shared__ __align__(128) uint8_t lnb_smem[];
   const uint32_t in_bytes = (uint32_t)R * (uint32_t)C * 4u;          // multiple of 16 (R % 4 == 0)
   const uint32_t in_pitch = (in_bytes + 127u) & ~127u;
@@ -289,17 +299,23 @@ __global__ void __launch_bounds__(LNB_THREADS) pio_layernorm_bulk_kernel(const f
         rstd1 = rsqrtf(q1 * inv_c + eps);
       }
       const float n0 = -mean0 * rstd0, n1 = -mean1 * rstd1;
-      __nv_bfloat16* y0 = out + r * ldy + lane;
-      __nv_bfloat16* y1 = y0 + ldy;
+      uint16_t* y0 = reinterpret_cast<uint16_t*>(out + r * ldy + lane);
+      uint16_t* y1 = y0 + ldy;
+      // one uniform branch per row pair selects the 16-bit format (the loop is issue-bound: no per-element select)
+      auto store_rows = [&](auto f16tag) {
+        constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-      for (int i = 0; i < NFULL; ++i) {
-        y0[32 * i] = __float2bfloat16_rn(fmaf(fmaf(v0[i], rstd0, n0), g[i], bt[i]));
-        y1[32 * i] = __float2bfloat16_rn(fmaf(fmaf(v1[i], rstd1, n1), g[i], bt[i]));
-      }
-      if (t_out) {   // tail of the row and the zero pad (g = bt = 0 there)
-        y0[32 * NFULL] = __float2bfloat16_rn(fmaf(fmaf(v0[NFULL], rstd0, n0), g[NFULL], bt[NFULL]));
-        y1[32 * NFULL] = __float2bfloat16_rn(fmaf(fmaf(v1[NFULL], rstd1, n1), g[NFULL], bt[NFULL]));
-      }
+        for (int i = 0; i < NFULL; ++i) {
+          y0[32 * i] = (uint16_t)pack16x2<F16>(fmaf(fmaf(v0[i], rstd0, n0), g[i], bt[i]), 0.f);
+          y1[32 * i] = (uint16_t)pack16x2<F16>(fmaf(fmaf(v1[i], rstd1, n1), g[i], bt[i]), 0.f);
+        }
+        if (t_out) {   // tail of the row and the zero pad (g = bt = 0 there)
+          y0[32 * NFULL] = (uint16_t)pack16x2<F16>(fmaf(fmaf(v0[NFULL], rstd0, n0), g[NFULL], bt[NFULL]), 0.f);
+          y1[32 * NFULL] = (uint16_t)pack16x2<F16>(fmaf(fmaf(v1[NFULL], rstd1, n1), g[NFULL], bt[NFULL]), 0.f);
+        }
+      };
+      if (f16) store_rows(std::true_type{});
+      else store_rows(std::false_type{});
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -481,26 +497,32 @@ __global__ void __launch_bounds__(LNC_THREADS, 3) pio_layernorm_concat_kernel(pi
           const float nmr = -mean * rstd;
           uint32_t* yr = reinterpret_cast<uint32_t*>(y + ((long long)b * a.N + n0 + r) * ldy) + lane;
           const uint64_t nmr2 = pack_f32x2(nmr, nmr), rstd2 = pack_f32x2(rstd, rstd);
+          // one uniform branch per row selects the 16-bit format (the loop is issue-bound: no per-element select)
+          auto store_row = [&](auto f16tag) {
+            constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-          for (int i = 0; i <= NP; ++i) {
-            if (i < NP || t_out) {
-              uint64_t x2 = pg2[k][i];
-              if (i == 0 || !few_feat) {   // slots that can hold features
-                const int c = 2 * lane + 64 * i;
-                if (c < Cf) {
-                  float x0, x1;
-                  unpack_f32x2(x2, x0, x1);
-                  x0 = fr[c] * g[i][0];
-                  if (c + 1 < Cf) x1 = fr[c + 1] * g[i][1];
-                  x2 = pack_f32x2(x0, x1);
+            for (int i = 0; i <= NP; ++i) {
+              if (i < NP || t_out) {
+                uint64_t x2 = pg2[k][i];
+                if (i == 0 || !few_feat) {   // slots that can hold features
+                  const int c = 2 * lane + 64 * i;
+                  if (c < Cf) {
+                    float x0, x1;
+                    unpack_f32x2(x2, x0, x1);
+                    x0 = fr[c] * g[i][0];
+                    if (c + 1 < Cf) x1 = fr[c + 1] * g[i][1];
+                    x2 = pack_f32x2(x0, x1);
+                  }
                 }
+                // two packed fp32x2 FMAs per column pair: x * rstd + (-mean * rstd * gamma + beta)
+                float y0, y1;
+                unpack_f32x2(ffma2(x2, rstd2, ffma2(nmr2, g2[i], bt2[i])), y0, y1);
+                yr[32 * i] = pack16x2<F16>(y0, y1);
               }
-              // two packed fp32x2 FMAs per column pair: x * rstd + (-mean * rstd * gamma + beta)
-              float y0, y1;
-              unpack_f32x2(ffma2(x2, rstd2, ffma2(nmr2, g2[i], bt2[i])), y0, y1);
-              yr[32 * i] = pack_bf16x2(y0, y1);
             }
-          }
+          };
+          if (a.fp16) store_row(std::true_type{});
+          else store_row(std::false_type{});
         }
       }
     }
@@ -566,7 +588,7 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   __syncthreads();
   if (m == -INFINITY) {  // wiped row or every key masked: zeros for P.V (:168-175); the returned matrix is uniform,
                          // which is what softmax makes of a row of -1e30 in the reference
-    for (int c = tid; c < a.ldp; c += 256) p[c] = __float2bfloat16_rn(0.f);
+    for (int c = tid; c < a.ldp; c += 256) p[c] = __float2bfloat16_rn(0.f);   // 0 has the same bits in fp16
     if (pf) {
       const float u = 1.0f / (float)a.cols;
       for (int c = tid; c < a.cols; c += 256) pf[c] = u;
@@ -589,9 +611,11 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
   for (int c = tid; c < seg; c += 256) {
     float o = 0.f;
     if (c < a.cols && valid(c)) o = __expf(logit(c) - m) * inv;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-    p[c] = hi;
-    if (a.split) {
+    if (!a.split) {
+      reinterpret_cast<uint16_t*>(p)[c] = cvt16(o, a.fp16);
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+      p[c] = hi;
       p[seg + c] = __float2bfloat16_rn(o - __bfloat162float(hi));
       p[2 * seg + c] = hi;
     }
@@ -654,7 +678,7 @@ __global__ void __launch_bounds__(256) pio_softmax_warp_kernel(pio_softmax_args 
     if (c4 < nvec_out) {
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (inv != 0.f && c4 < nvec) o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
-      p2[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      p2[c4] = make_uint2(pack16x2(o.x, o.y, a.fp16), pack16x2(o.z, o.w, a.fp16));
     }
   }
 }
@@ -737,7 +761,7 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
 #pragma unroll
       for (int p = 0; p < MAXP; ++p)
         if (p < parts && w[p] != 0.f) acc += Op[p][c] * w[p];
-      o[c] = __float2bfloat16_rn(acc * inv);
+      reinterpret_cast<uint16_t*>(o)[c] = cvt16(acc * inv, a.fp16);
     }
   }
 }
@@ -794,7 +818,7 @@ __global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args 
         const float mp = __ldg(a.m_part + p * sm + row);
         if (mp != -INFINITY) acc += __ldg(a.O_part + p * so + row * a.dv + c) * __expf(mp - M);
       }
-      o[c] = __float2bfloat16_rn(acc * inv);
+      reinterpret_cast<uint16_t*>(o)[c] = cvt16(acc * inv, a.fp16);
     }
   }
 }
@@ -954,7 +978,8 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
   const long long seg = split ? a->ldy / 3 : a->ldy;
   PIO_REQUIRE(!split || (a->ldy % 24 == 0 && seg >= a->C), "pio_layernorm_bf16: split output needs ldy = 3 * pad8(C)");
   PIO_REQUIRE(seg <= 2048, "pio_layernorm_bf16: C up to 2048 supported (got %lld columns)", (long long)seg);
-  const int mode = (a->normalize ? 1 : 0) | (split == 1 ? 2 : 0) | (split == 2 ? 4 : 0);
+  PIO_REQUIRE(!(a->fp16 && split), "pio_layernorm_bf16: the split (validation) layouts are bf16 only");
+  const int mode = (a->normalize ? 1 : 0) | (split == 1 ? 2 : 0) | (split == 2 ? 4 : 0) | (a->fp16 ? 8 : 0);
   DeviceInfo dev;
   int rc = get_device_info(&dev);
   if (rc != PIO_OK) return rc;
@@ -1012,7 +1037,7 @@ extern "C" int pio_layernorm_bf16(const pio_layernorm_args* a, void* stream_) {
     long long blocks = (long long)dev.sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     if (blocks > ngroups) blocks = ngroups;
     PIO_CUDA_OK(launch_kernel(kern, dim3((unsigned)blocks), dim3(LNB_THREADS), smem, stream, 1, a->x, y, (int)a->ldy,
-                              a->gamma, a->beta, ngroups, R, (int)a->C, (int)(a->normalize ? 1 : 0), a->eps));
+                              a->gamma, a->beta, ngroups, R, (int)a->C, mode, a->eps));
   } else {
     const int need = (int)((seg + 31) / 32);
     const int rows_per_warp = need <= 12 ? 2 : 1;

@@ -17,18 +17,51 @@ import torch
 
 from . import ops
 from .inputs import PositionedInput
-from .ops import BF16, pad8
+from .ops import pad8
 
-# Arithmetic mode: "bf16" (default: bf16 MMA operands, fp32 everything else) or "bf16x3" (validation precision: bf16 x 2
-# split operands, three MMAs per product — validate.py)
+# Arithmetic mode:
+#   "bf16"   (default) bf16 MMA operands, fp32 residual stream / statistics / accumulators;
+#   "fp16"   the same kernels at the same speed with IEEE-half operands: 11 instead of 8 mantissa bits, i.e. 8x less
+#            operand rounding, fp16's range (conversions saturate).  The optical-flow recipe needs it — with bf16 operands
+#            the reference ALGORITHM itself misses the 1e-2 bound there (1.86e-2 in a CPU emulation;
+#            2.7e-2 measured on tests/golden/full/flow.npz) — and it is what the reference's own `mixed_precision=True`
+#            means (fp16 autocast, flow_perceiver.py:14,129);
+#   "bf16x3" validation precision: bf16 x 2 split operands, three MMAs per product (validate.py).
 PRECISION = "bf16"
+MODES = ("bf16", "fp16", "bf16x3")
 
 
 def set_precision(mode: str) -> None:
     global PRECISION
-    if mode not in ("bf16", "bf16x3"):
-        raise ValueError(f"unknown precision {mode!r}: use 'bf16' or 'bf16x3'")
+    if mode not in MODES:
+        raise ValueError(f"unknown precision {mode!r}: use one of {MODES}")
     PRECISION = mode
+    ops.FP16 = (mode == "fp16")
+
+
+class precision_scope:
+    """`with precision_scope("fp16"): ...` — run a block in another arithmetic mode (None: keep the current one).
+    PerceiverEncoder / PerceiverDecoder use it for their per-module `precision` attribute."""
+
+    def __init__(self, mode: Optional[str]):
+        if mode is not None and mode not in MODES:
+            raise ValueError(f"unknown precision {mode!r}: use one of {MODES}")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = PRECISION
+        if self.mode is not None:
+            set_precision(self.mode)
+
+    def __exit__(self, *exc):
+        if self.mode is not None:
+            set_precision(self.prev)
+        return False
+
+
+def fast() -> bool:
+    """True for the 16-bit-operand modes (everything except the validation precision)."""
+    return PRECISION != "bf16x3"
 
 
 # Tower LayerNorms folded into the projections around them (DESIGN.md section 4.7) when the latent array has at least
@@ -48,10 +81,10 @@ ENCODER_KEY_SPLITS = 0     # 0 = auto
 
 
 def _bf16_weight(w: torch.Tensor) -> torch.Tensor:
-    """fp32 [N, K] -> bf16 [N, pad8(K)] (pad columns zero; never read by TMA anyway)."""
+    """fp32 [N, K] -> 16-bit [N, pad8(K)] in the current operand format (pad columns zero; never read by TMA anyway)."""
     n, k = w.shape
-    out = torch.zeros((n, pad8(k)), dtype=BF16, device=w.device)
-    out[:, :k] = w.detach().to(BF16)
+    out = torch.zeros((n, pad8(k)), dtype=ops.dtype16(), device=w.device)
+    out[:, :k] = w.detach().to(ops.dtype16())
     return out
 
 
@@ -163,21 +196,21 @@ def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torc
     dev = x.device
     nqkv = 2 * pf.QK + pf.V
     ld = pad8(nqkv)
-    qkv = torch.empty((M, ld), dtype=BF16, device=dev)
+    qkv = torch.empty((M, ld), dtype=ops.dtype16(), device=dev)
     ops.gemm(xb, pf.wqkv, M=M, N=nqkv, K=C, lda=xb.stride(0), bias=pf.bqkv, out_bf16=qkv, ldo16=ld,
              row_stats_in=st, ln_colsum=pf.cs_qkv, ln_channels=C, ln_eps=pf.eps1)
     o = attention(qkv, ld, 0, qkv, ld, pf.QK, qkv, ld, 2 * pf.QK, B=B, H=pf.H, Nq=N, Nk=N, dqk=pf.dqk, dv=pf.dv,
                   scale=pf.scale)
     o2 = o.view(M, -1)
     x1 = torch.empty((M, C), dtype=torch.float32, device=dev)
-    x1b = torch.empty((M, C), dtype=BF16, device=dev)
+    x1b = torch.empty((M, C), dtype=ops.dtype16(), device=dev)
     ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, residual=x, ldr=x.stride(0), out_f32=x1, ldo32=C,
              out_bf16=x1b, ldo16=C, row_stats_out=st_mid)
-    h = torch.empty((M, pad8(pf.hidden)), dtype=BF16, device=dev)
+    h = torch.empty((M, pad8(pf.hidden)), dtype=ops.dtype16(), device=dev)
     ops.gemm(x1b, pf.w1, M=M, N=pf.hidden, K=C, bias=pf.b1, act=1, out_bf16=h, ldo16=h.stride(0),
              row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2, reverse_tiles=REVERSE_FC1)
     y = torch.empty((M, C), dtype=torch.float32, device=dev)
-    yb = torch.empty((M, C), dtype=BF16, device=dev) if st_out is not None else None
+    yb = torch.empty((M, C), dtype=ops.dtype16(), device=dev) if st_out is not None else None
     # fc2 walks its tiles back to front: fc1 and the out-projection wrote h and x1 front to back, so their last rows are
     # what L2 still holds; and the rows fc2 writes last (the first ones) are where the next QKV projection starts
     ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, residual=x1, ldr=C, out_f32=y, ldo32=C,
@@ -193,6 +226,7 @@ def prepared(module, key, builder):
     """Per-module cache of derived weights, rebuilt when any parameter changes (in-place update, load_state_dict,
     .to(device))."""
     cache = module.__dict__.setdefault("_pio_cache", {})
+    key = (key, ops.FP16)      # derived weights exist once per 16-bit operand format
     ver = _versions(module)
     hit = cache.get(key)
     if hit is None or hit[0] != ver:
@@ -211,7 +245,7 @@ def _head_slice(t: torch.Tensor, B: int, N: int, ld: int, col0: int, d: int):
     base is 16-byte aligned; copies into a fresh padded buffer only when it is not."""
     if (col0 * 2) % 16 == 0:
         return t, ld, col0
-    out = torch.zeros((B * N, pad8(d)), dtype=BF16, device=t.device)
+    out = torch.zeros((B * N, pad8(d)), dtype=ops.dtype16(), device=t.device)
     out[:, :d] = t.view(B * N, ld)[:, col0:col0 + d]
     return out, pad8(d), 0
 
@@ -241,7 +275,7 @@ def _materialised_attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, N
     general attention arguments (dense mask / bias / return_matrix)."""
     dev = q.device
     ldo = pad8(H * dv)
-    O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+    O = torch.empty((B, Nq, ldo), dtype=ops.dtype16(), device=dev)
     lds = (Nk + 3) // 4 * 4
     for h in range(H):
         qh, ldqh, qo = _head_slice(q, 1 if q_bcast else B, Nq, ldq, qcol + h * dqk, dqk)
@@ -286,7 +320,7 @@ def _materialised_attention_h1(q, k, vT, *, B, Nq, Nk, dqk, dv, scale, key_mask,
     P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)          # [B, Nq, pad8(Nk)]
     del S
     ldo = pad8(dv)
-    O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+    O = torch.empty((B, Nq, ldo), dtype=ops.dtype16(), device=dev)
     ops.gemm(P, vT, M=Nq, N=dv, K=Nk, batch=B, strideA=Nq * P.shape[-1], strideB=dv * nkp, lda=P.shape[-1], ldb=nkp,
              out_bf16=O, ldo16=ldo, strideO16=Nq * ldo)
     return O
@@ -361,7 +395,7 @@ def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out
         return ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, residual=x_f32, want_f32=True, want_bf16=want_bf16_out)
     m = h.shape[0]
     y32 = ops.empty_f32_rows(m, pm.cout, h.device)
-    y16 = torch.empty((m, pad8(pm.cout)), dtype=BF16, device=h.device)
+    y16 = torch.empty((m, pad8(pm.cout)), dtype=ops.dtype16(), device=h.device)
     ops.gemm(h, pm.w2, M=m, N=pm.cout, K=pm.hidden, bias=pm.b2, residual=x_f32, ldr=x_f32.stride(0),
              out_f32=y32, ldo32=y32.stride(0), out_bf16=y16, ldo16=y16.stride(0), row_stats_out=stats_out)
     return y32, y16
@@ -414,7 +448,7 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
         _, k = ops.linear(kvn, pa.Ck, wk, pa.QK, bk)
         nkp = pad8(Nk)
         ldkv = kvn.shape[-1]
-        vT = torch.empty((B, pa.V, nkp), dtype=BF16, device=kvn.device)
+        vT = torch.empty((B, pa.V, nkp), dtype=ops.dtype16(), device=kvn.device)
         if nkp != Nk:
             vT[:, :, Nk:].zero_()       # P's pad columns are zero as well; keep the products finite
         ops.gemm(wv, kvn, M=pa.V, N=Nk, K=pa.Ck, batch=B, strideA=0, strideB=Nk * ldkv, lda=wv.stride(0), ldb=ldkv,

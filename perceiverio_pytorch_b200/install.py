@@ -79,8 +79,25 @@ def _decoder_from_reference(dec: nn.Module) -> _perceiver.PerceiverDecoder:
     return new.to(next(dec.parameters()).device).eval()
 
 
-def swap_hot_path(model: nn.Module, fuse_input: bool = False) -> nn.Module:
+def _auto_precision(model: nn.Module):
+    """Arithmetic mode for a swapped model when the caller does not name one: "fp16" operands for models with a dense
+    regression head of a handful of channels (optical flow: 322 -> 2; with bf16 operands the reference algorithm itself
+    misses the 1e-2 bound there) and for wrappers constructed with the reference's
+    `mixed_precision=True` (fp16 autocast, flow_perceiver.py:14,129); otherwise None (the global default, bf16)."""
+    for m in model.modules():
+        if getattr(m, "mixed_precision", False):
+            return "fp16"
+        if type(m).__name__ == "PerceiverDecoder" and getattr(m, "_final_project", False) \
+                and getattr(m, "_output_num_channels", 1 << 30) <= 16:
+            return "fp16"
+    return None
+
+
+def swap_hot_path(model: nn.Module, fuse_input: bool = False, precision: str = "auto") -> nn.Module:
     """Replace every reference PerceiverEncoder / PerceiverDecoder inside `model` by its B200 drop-in.
+
+    precision: "auto" (see `_auto_precision`), None (follow the global engine.PRECISION) or "bf16" / "fp16" / "bf16x3";
+    stored as the `precision` attribute of every swapped-in encoder / decoder.
 
     fuse_input: additionally route every `PerceiverIO.forward` inside `model` through `inputs.perceiver_io_forward`, which
     keeps the preprocessor's features and position table apart whenever the configuration
@@ -91,6 +108,8 @@ def swap_hot_path(model: nn.Module, fuse_input: bool = False) -> nn.Module:
         for m in model.modules():
             if type(m).__name__ == "PerceiverIO" and "forward" not in m.__dict__:
                 m.forward = functools.partial(_inputs.perceiver_io_forward, m)
+    if precision == "auto":
+        precision = _auto_precision(model)
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             cls = type(child).__name__
@@ -98,6 +117,8 @@ def swap_hot_path(model: nn.Module, fuse_input: bool = False) -> nn.Module:
                 continue
             if cls == "PerceiverEncoder":
                 setattr(parent, name, _encoder_from_reference(child))
+                getattr(parent, name).precision = precision
             elif cls == "PerceiverDecoder":
                 setattr(parent, name, _decoder_from_reference(child))
+                getattr(parent, name).precision = precision
     return model

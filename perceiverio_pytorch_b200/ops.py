@@ -13,6 +13,19 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+# 16-bit operand / activation format of the launches issued from here on: bf16 (default) or fp16 (pio_*_args.fp16 in
+# include/pio_b200.h).  Set through engine.set_precision() / engine.precision_scope(); every 16-bit buffer a block
+# allocates and every launch it issues use the format current at that moment.
+FP16 = False
+
+
+def dtype16() -> torch.dtype:
+    return torch.float16 if FP16 else BF16
+
+
+def _f16() -> int:
+    return 1 if FP16 else 0
+
 GEMM_CLUSTER_M = 0   # 0 = library default; tests / bench can force 1, 2 or 4
 GEMM_KERNEL = 0      # 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair (cta_group::2) kernel
 
@@ -97,10 +110,10 @@ def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optiona
     rows = x2.shape[0]
     ldy = pad8(c) * (3 if split else 1)
     if out is None:
-        out = torch.empty((rows, ldy), dtype=BF16, device=x.device)
-    assert out.dtype == BF16 and out.shape[-1] == ldy and out.is_contiguous()
+        out = torch.empty((rows, ldy), dtype=BF16 if split else dtype16(), device=x.device)
+    assert out.dtype == (BF16 if split else dtype16()) and out.shape[-1] == ldy and out.is_contiguous()
     a = _lib.LayerNormArgs(_ptr(x2), x2.stride(0), _ptr(out), ldy, _ptr(gamma), _ptr(beta), rows, c,
-                           1 if normalize else 0, eps, split)
+                           1 if normalize else 0, eps, split, 0 if split else _f16())
     _lib.check(_lib.load().pio_layernorm_bf16(C.byref(a), _stream()), "pio_layernorm_bf16")
     return out
 
@@ -126,9 +139,9 @@ def layernorm_concat_bf16(feat: torch.Tensor, pos: torch.Tensor, gamma: Optional
     assert pos.shape[0] == N and pos.is_contiguous()
     Cp = pos.shape[1]
     ldy = pad8(Cf + Cp)
-    out = torch.empty((B * N, ldy), dtype=BF16, device=feat.device)
+    out = torch.empty((B * N, ldy), dtype=dtype16(), device=feat.device)
     a = _lib.LayerNormConcatArgs(_ptr(feat), feat.stride(0), feat.stride(1), feat.stride(2), _ptr(pos), _ptr(out), ldy,
-                                 _ptr(gamma), _ptr(beta), B, N, Cf, Cp, eps)
+                                 _ptr(gamma), _ptr(beta), B, N, Cf, Cp, eps, _f16())
     _lib.check(_lib.load().pio_layernorm_concat_bf16(C.byref(a), _stream()), "pio_layernorm_concat_bf16")
     return out
 
@@ -146,7 +159,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          reverse_tiles: bool = False, row_stats_parts: int = 0) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
     _need_cuda(A, B, bias, residual, out_f32, out_bf16)
-    assert A.dtype == BF16 and B.dtype == BF16
+    assert A.dtype == B.dtype and A.dtype in (BF16, torch.float16)
     lda = A.stride(-2) if lda is None else lda
     ldb = B.stride(-2) if ldb is None else ldb
     st = row_stats_out if row_stats_out is not None else row_stats_in
@@ -160,7 +173,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       GEMM_CLUSTER_M if cluster_m is None else cluster_m,
                       GEMM_KERNEL if kernel is None else kernel,
                       _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps,
-                      1 if reverse_tiles else 0, row_stats_parts)
+                      1 if reverse_tiles else 0, row_stats_parts, 1 if A.dtype == torch.float16 else 0)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 
@@ -171,7 +184,7 @@ def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torc
     Returns (y_f32 [M, N] or None, y_bf16 [M, pad8(N)] or None)."""
     m = x.shape[0]
     y32 = empty_f32_rows(m, N, x.device) if want_f32 else None
-    y16 = torch.empty((m, pad8(N)), dtype=BF16, device=x.device) if want_bf16 else None
+    y16 = torch.empty((m, pad8(N)), dtype=dtype16(), device=x.device) if want_bf16 else None
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.stride(-1) == 1
     gemm(x, w, M=m, N=N, K=K, bias=bias, bias_mode=bias_mode, act=act, alpha=alpha,
@@ -205,7 +218,7 @@ def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[to
     _need_cuda(S, key_mask, row_keep, dense_mask, bias, probs_out)
     b, rows, lds = S.shape
     ldp = pad8(cols) * (3 if split else 1)
-    P = torch.empty((b, rows, ldp), dtype=BF16, device=S.device)
+    P = torch.empty((b, rows, ldp), dtype=BF16 if split else dtype16(), device=S.device)
     if dense_mask is not None:
         assert dense_mask.dtype == torch.uint8 and dense_mask.shape == (b, rows, cols) and dense_mask.stride(2) == 1
     if bias is not None:
@@ -220,7 +233,7 @@ def softmax_bf16(S: torch.Tensor, cols: int, scale: float, key_mask: Optional[to
                          dense_mask.stride(1) if dense_mask is not None else 0,
                          _ptr(bias), *(bias.stride() if bias is not None else (0, 0, 0)),
                          _ptr(probs_out), probs_out.stride(1) if probs_out is not None else 0,
-                         probs_out.stride(0) if probs_out is not None else 0)
+                         probs_out.stride(0) if probs_out is not None else 0, 0 if split else _f16())
     _lib.check(_lib.load().pio_softmax_bf16(C.byref(a), _stream()), "pio_softmax_bf16")
     return P
 
@@ -243,7 +256,7 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
     emit_partial = partial or num_splits > 1
     O = out
     if O is None and not partial:
-        O = torch.empty((B, Nq, ldo), dtype=BF16, device=dev)
+        O = torch.empty((B, Nq, ldo), dtype=dtype16(), device=dev)
     Op = mp = lp = None
     if emit_partial:
         Op = torch.empty((num_splits, B, H, Nq, dv), dtype=torch.float32, device=dev)
@@ -254,7 +267,8 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
                            _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
                            _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
                            _ptr(O), ldo, (O.stride(0) if O is not None else 0),
-                           num_splits, 1 if partial else 0, _ptr(Op), _ptr(mp), _ptr(lp))
+                           num_splits, 1 if partial else 0, _ptr(Op), _ptr(mp), _ptr(lp),
+                           1 if Q.dtype == torch.float16 else 0)
     _lib.check(_lib.load().pio_attention_fwd(C.byref(a), _stream()), "pio_attention_fwd")
     if partial:
         return Op, mp, lp
@@ -278,12 +292,13 @@ def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp
     parts, b, h, nq, dv = Op.shape if shape is None else shape
     ldo = pad8(h * dv)
     if out is None and normalised:
-        out = torch.empty((b, nq, ldo), dtype=BF16, device=Op.device if Op is not None else device)
+        out = torch.empty((b, nq, ldo), dtype=dtype16(), device=Op.device if Op is not None else device)
     mo = merged_out if merged_out is not None else (None, None, None)
     a = _lib.CombineArgs(_ptr(Op), _ptr(mp), _ptr(lp), part_stride_O, part_stride_ml, parts, b, h, nq, dv,
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
                          _ptr(out), ldo, out.stride(0) if out is not None else 0,
-                         _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]), C.c_void_p(part_ptrs_dev) if part_ptrs_dev else None)
+                         _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]), C.c_void_p(part_ptrs_dev) if part_ptrs_dev else None,
+                         1 if (out is not None and out.dtype == torch.float16) else 0)
     _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
     return out
 

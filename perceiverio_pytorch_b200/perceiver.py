@@ -82,6 +82,8 @@ class PerceiverEncoder(nn.Module):
         # row of every residual-stream state (from the statistics the GEMMs produced anyway; one host sync, skipped
         # during CUDA-graph capture) and falls back to the LayerNorm kernels when it exceeds engine.FUSE_LN_MAX_OFFSET.
         self.fuse_layernorm = None
+        # arithmetic mode of this module's forward: None = the global engine.PRECISION, or "bf16" / "fp16" / "bf16x3"
+        self.precision = None
         self.fused_layernorm_offset = None      # the measured max |mean| / std (None: not measured yet)
         self._fuse_ln_checked = None
 
@@ -90,10 +92,18 @@ class PerceiverEncoder(nn.Module):
 
     def forward(self, inputs, latents, *, input_mask=None):
         """inputs fp32 [B, Nk, C_in] (this rank's key slice when `key_shard` is set), latents [B, Nlat, C]."""
+        with engine.precision_scope(self.precision):
+            return self._forward(inputs, latents, input_mask=input_mask)
+
+    def _forward(self, inputs, latents, *, input_mask=None):
         ops._need_cuda(inputs, latents)
+        if isinstance(inputs, torch.Tensor) and inputs.dtype != torch.float32:
+            inputs = inputs.float()     # e.g. fp16 activations under the reference's autocast (flow_perceiver.py:129)
+        if latents.dtype != torch.float32:
+            latents = latents.float()
         if latents.shape[0] == 0 or latents.shape[1] == 0:   # empty batch / no latents: nothing to launch
             return latents.new_empty(latents.shape)
-        if isinstance(inputs, PositionedInput) and engine.PRECISION != "bf16":
+        if isinstance(inputs, PositionedInput) and not engine.fast():
             inputs = inputs.dense()   # the validation precision works on the dense array
         key_mask = None
         row_keep = None
@@ -132,7 +142,7 @@ class PerceiverEncoder(nn.Module):
             pver = tuple((p.data_ptr(), p._version) for p in self.parameters())
             if self._fuse_ln_checked is not None and self._fuse_ln_checked[0] == pver and not self._fuse_ln_checked[1]:
                 want = False        # these parameters failed the offset check before
-        if (want and engine.PRECISION == "bf16" and layers
+        if (want and engine.fast() and layers
                 and latents.is_cuda and not any(sa.training and any(p > 0 for p in sa._dropout_probs) for sa in layers)):
             fused = [engine.prepared(sa, "fused", lambda sa=sa: engine.PreparedFusedLayer(sa)) for sa in self.self_attends]
             if not all(pf.usable() for pf in fused):
@@ -201,15 +211,25 @@ class PerceiverDecoder(nn.Module):
             else:
                 raise ValueError(f"{self._output_w_init} not supported as output_w_init")
             nn.init.constant_(self.final_layer.bias, 0)
+        # arithmetic mode of this module's forward: None = the global engine.PRECISION, or "bf16" / "fp16" / "bf16x3"
+        self.precision = None
 
     def forward(self, query, latents, *, query_mask=None):
+        with engine.precision_scope(self.precision):
+            return self._forward(query, latents, query_mask=query_mask)
+
+    def _forward(self, query, latents, *, query_mask=None):
         ops._need_cuda(query, latents)
+        if query.dtype != torch.float32:
+            query = query.float()       # e.g. fp16 activations under the reference's autocast (flow_perceiver.py:129)
+        if latents.dtype != torch.float32:
+            latents = latents.float()
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
         n_out = self._output_num_channels
         if query.shape[0] == 0 or query.shape[1] == 0:   # empty batch / no output queries: nothing to launch
             return query.new_empty(query.shape[0], query.shape[1], n_out if self._final_project else query.shape[2])
         # the wide final projection consumes bf16 rows: let the MLP's last GEMM write them next to the fp32 result
-        want16 = (self._final_project and n_out > 16 and engine.PRECISION == "bf16"
+        want16 = (self._final_project and n_out > 16 and engine.fast()
                   and self.query_channels % 16 == 0)
         y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
                                                               want_bf16_out=want16)

@@ -6,8 +6,13 @@ layers): the CUDA path against
   * the complete output of the fp32 CPU oracle, evaluated on the test machine's host cores (seconds per config).
 
 Parameters and inputs are regenerated from seeds on both sides (oracle/full_configs.py).  Tolerance: BASELINE.json's
-max|d| / max|ref| <= 1e-2 for the bf16 path; optical flow — the config with the thinnest margin —
-is held to 9e-3.  The CPU-only tests pin the oracle itself against the same fixtures.
+max|d| / max|ref| <= 1e-2.  Language, classification and multimodal meet it with bf16 operands.  Optical flow does not,
+and cannot: a CPU emulation of the reference ALGORITHM with bf16-rounded operands already gives 1.86e-2 (SURVEY.md
+section 0.4), the CUDA path measures 2.7e-2 on this fixture — the 322 -> 2 regression head amplifies operand rounding.
+Flow therefore runs with fp16 operands (`precision="fp16"`: same kernels, same tensor-core rate, 11 instead of 8
+mantissa bits — what `swap_hot_path` selects for such heads and what the reference's own mixed-precision mode uses,
+flow_perceiver.py:129) and is held to 5e-3; every config is also checked in that mode.  The CPU-only tests pin the
+oracle itself against the same fixtures.
 """
 import os
 
@@ -19,7 +24,12 @@ from golden_util import rel_err
 from oracle import full_configs as F
 
 FULL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full")
-TOL = {"language": 1e-2, "classification": 1e-2, "multimodal": 1e-2, "flow": 9e-3}
+# (config, arithmetic mode) -> bound on max|d| / max|ref| of the output
+CASES = {("language", "bf16"): 1e-2, ("classification", "bf16"): 1e-2, ("multimodal", "bf16"): 1e-2,
+         ("flow", "fp16"): 5e-3,
+         ("language", "fp16"): 3e-3, ("classification", "fp16"): 3e-3, ("multimodal", "fp16"): 3e-3,
+         # recorded, not a pass criterion of the model: bf16 operands on the flow head (see the module docstring)
+         ("flow", "bf16"): 5e-2}
 
 
 def _fixture(name):
@@ -54,8 +64,10 @@ def test_oracle_matches_live_reference_at_full_size(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(F.FULL_CONFIGS))
-def test_cuda_path_matches_reference_and_oracle_at_full_size(name):
+@pytest.mark.parametrize("name,mode", sorted(CASES))
+def test_cuda_path_matches_reference_and_oracle_at_full_size(name, mode):
+    from perceiverio_pytorch_b200 import engine
+    tol = CASES[(name, mode)]
     fx = _fixture(name)
     enc, dec = _drop_in(name, fx)
     data = F.hot_path_inputs(name, int(fx["input_seed"]))
@@ -63,6 +75,8 @@ def test_cuda_path_matches_reference_and_oracle_at_full_size(name):
     # the oracle itself against the live reference's vectors, on this machine
     assert _sub_err(z_ref, fx, "latents") < 1e-5 and _sub_err(out_ref, fx, "output") < 1e-5
     enc, dec = enc.cuda(), dec.cuda()
+    enc.precision = dec.precision = mode
+    assert engine.PRECISION == "bf16"            # the per-module attribute selects the mode, the global default stays
     cu = {k: (v.cuda() if isinstance(v, torch.Tensor) else None) for k, v in data.items()}
     with torch.inference_mode():
         z = enc(cu["inputs"], enc.latents(cu["inputs"]), input_mask=cu["input_mask"])
@@ -72,10 +86,11 @@ def test_cuda_path_matches_reference_and_oracle_at_full_size(name):
     assert torch.isfinite(out).all()
     ez, eo = rel_err(z.cpu(), z_ref), rel_err(out.cpu(), out_ref)
     gz, go = _sub_err(z, fx, "latents"), _sub_err(out, fx, "output")
-    print(f"\nFULL {name}: vs oracle latents max {ez[0]:.3e} l2 {ez[1]:.3e}, output max {eo[0]:.3e} l2 {eo[1]:.3e}; "
+    print(f"\nFULL {name} [{mode}]: vs oracle latents max {ez[0]:.3e} l2 {ez[1]:.3e}, output max {eo[0]:.3e} l2 {eo[1]:.3e}; "
           f"vs reference subsample latents {gz:.3e}, output {go:.3e}")
-    assert eo[0] <= TOL[name] and ez[0] <= 1e-2, (name, ez, eo)
-    assert go <= TOL[name] and gz <= 1e-2, (name, gz, go)
+    assert eo[0] <= tol and ez[0] <= 1e-2, (name, mode, ez, eo)
+    assert go <= tol and gz <= 1e-2, (name, mode, gz, go)
+    assert engine.PRECISION == "bf16"
     # twice in a row: bit-identical (no atomics anywhere on the path, fixed reduction orders)
     assert torch.equal(z, z2) and torch.equal(out, out2), name
 
@@ -129,6 +144,7 @@ def test_flow_batch_two_takes_the_fused_layernorm_tower_within_tolerance():
     data = F.hot_path_inputs(name, int(fx["input_seed"]))
     z_ref, out_ref = F.oracle_forward(name, dict(enc.state_dict()), dict(dec.state_dict()), data)
     enc, dec = enc.cuda(), dec.cuda()
+    enc.precision = dec.precision = "fp16"
     x = data["inputs"].cuda()
     x2 = torch.cat([x, torch.randn(1, x.shape[1], x.shape[2], device="cuda",
                                    generator=torch.Generator(device="cuda").manual_seed(5))], 0)
@@ -137,4 +153,4 @@ def test_flow_batch_two_takes_the_fused_layernorm_tower_within_tolerance():
         out = dec(x2, z)
     e = rel_err(out[:1].cpu(), out_ref)
     print(f"\nFULL flow B=2: output max {e[0]:.3e} l2 {e[1]:.3e}; latents {rel_err(z[:1].cpu(), z_ref)[0]:.3e}")
-    assert e[0] <= 1e-2, e
+    assert e[0] <= 5e-3, e
