@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 10
+#define PIO_ABI_VERSION 11
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -210,6 +210,35 @@ typedef struct pio_combine_args {
   int32_t fp16;                                                   /* 16-bit format of O: 0 = bf16, 1 = fp16 */
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Query-tiled decoder attention (single head): very many output queries attend over a short latent array — the
+ * decoder's cross-attend (perceiver.py:166-180 -> CrossAttention.forward, transformer_primitives.py:371-399 ->
+ * Attention.attend :117-180); optical flow: 182,528 queries x 2048 latents.
+ *   out[b, i, :] = softmax_j(scale * Q[b, i, :] . K[b, j, :]) . V[b, :, :] + bias (+ residual[b, i, :])      (fp32)
+ * K and V are distinct Nk x {dqk, dv} matrices (dqk, dv <= 384): the host folds the query projection into K and the
+ * output projection into V (K' = k Wq, V' = v Wf^T), so `out` is already the attention block's output
+ * incl. `final`, and no [Nq, Nk] matrix is ever written.  Runs on CTA pairs (cta_group::2): each CTA owns 128 queries
+ * and stages half of every latent tile; K / V stream from L2 (they are a few MB), Q and out touch HBM once.
+ * Rows with row_keep == 0 (or without any valid key) come out as bias (+ residual), as the reference's wiped rows do
+ * (:168-175 then :110).  A per-key logit bias can be carried as an extra contraction column (Q column = 1).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct pio_decoder_attention_args {
+  const void* Q; int64_t ldq; int64_t strideQ;   /* 16-bit [B, Nq, ldq]; batch stride 0 = shared by every b */
+  const void* K; int64_t ldk; int64_t strideK;   /* 16-bit [B, Nk, ldk] */
+  const void* V; int64_t ldv; int64_t strideV;   /* 16-bit [B, Nk, ldv] */
+  int32_t B, Nq, Nk, dqk, dv;
+  float scale;
+  const uint8_t* key_mask; int64_t stride_km;    /* [B, Nk] 1 = attend, or NULL */
+  const uint8_t* row_keep; int64_t stride_rk;    /* [B, Nq] 1 = keep, or NULL */
+  const float* bias;                             /* [dv] or NULL */
+  const float* residual; int64_t ldr; int64_t strideR;   /* fp32 [B, Nq, ldr] or NULL */
+  float* out; int64_t ldo; int64_t strideO;      /* fp32 [B, Nq, ldo] */
+  int32_t fp16;                                  /* 16-bit format of Q, K, V and P: 0 = bf16, 1 = fp16 */
+} pio_decoder_attention_args;
+int pio_decoder_attention_fwd(const pio_decoder_attention_args* a, void* stream);
+/* 0 if pio_decoder_attention_fwd covers these head sizes, PIO_ERR_UNSUPPORTED otherwise. */
+int pio_decoder_attention_supported(int32_t dqk, int32_t dv);
 
 /* ---------------------------------------------------------------------------------------------------------
  * fp32 SIMT linear for very narrow outputs (N <= 16): y[m, :] = x[m, :] . W^T + bias, everything fp32.

@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
     "pio_linear_f32", "pio_layernorm_concat_bf16", "pio_hash_words",
+    "pio_decoder_attention_fwd", "pio_decoder_attention_supported",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -75,6 +76,20 @@ class AttentionArgs(C.Structure):
                 ("O_part", vp), ("m_part", vp), ("l_part", vp), ("fp16", i32)]
 
 
+class DecoderAttentionArgs(C.Structure):
+    _fields_ = [("Q", vp), ("ldq", i64), ("strideQ", i64),
+                ("K", vp), ("ldk", i64), ("strideK", i64),
+                ("V", vp), ("ldv", i64), ("strideV", i64),
+                ("B", i32), ("Nq", i32), ("Nk", i32), ("dqk", i32), ("dv", i32),
+                ("scale", f32),
+                ("key_mask", vp), ("stride_km", i64),
+                ("row_keep", vp), ("stride_rk", i64),
+                ("bias", vp),
+                ("residual", vp), ("ldr", i64), ("strideR", i64),
+                ("out", vp), ("ldo", i64), ("strideO", i64),
+                ("fp16", i32)]
+
+
 class CombineArgs(C.Structure):
     _fields_ = [("O_part", vp), ("m_part", vp), ("l_part", vp),
                 ("part_stride_O", i64), ("part_stride_ml", i64),
@@ -114,12 +129,15 @@ def load(build_if_missing: bool = True):
         for name, argt in (("pio_layernorm_bf16", LayerNormArgs), ("pio_gemm_bf16", GemmArgs),
                            ("pio_softmax_bf16", SoftmaxArgs), ("pio_attention_fwd", AttentionArgs),
                            ("pio_attention_combine", CombineArgs), ("pio_linear_f32", LinearF32Args),
-                           ("pio_layernorm_concat_bf16", LayerNormConcatArgs)):
+                           ("pio_layernorm_concat_bf16", LayerNormConcatArgs),
+                           ("pio_decoder_attention_fwd", DecoderAttentionArgs)):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
         lib.pio_hash_words.restype = C.c_int
         lib.pio_hash_words.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
+        lib.pio_decoder_attention_supported.restype = C.c_int
+        lib.pio_decoder_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_supported.restype = C.c_int
         lib.pio_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_key_tile.restype = C.c_int
@@ -128,7 +146,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 10:
+        if lib.pio_abi_version() != 11:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

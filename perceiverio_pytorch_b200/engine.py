@@ -108,6 +108,29 @@ class PreparedAttention:
         self.folded = bool(allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck
                            and ops.attention_supported(self.Ck, self.Ck) and self.Ck <= 384)
         self.wf, self.bf = _bf16_weight(wf), (bf.float().contiguous() if bf is not None else None)
+        # Query-side fold for single-head cross-attends with MANY queries and few keys (the decoders):
+        #   S_ij = (LN(q_i) Wq^T + bq) . k_j = LN(q_i) . K'_j + b'_j,    K' = k Wq = LN(z) (Wq^T Wk)^T + Wq^T bk,
+        #                                                             b'_j = bq . k_j = LN(z_j) . (Wk^T bq) + bq . bk
+        #   out_i = sum_j P_ij (v_j Wf^T) + bf = (P V')_i + bf,         V' = v Wf^T = LN(z) (Wf Wv)^T + Wf bv
+        # so ONE projection of the (short) latent array yields both operands [K' | b' | 0.. | V'] with a single rounding,
+        # the per-query projections proj_q / final disappear, the contraction shrinks from QK to Cq + 1 (b' rides on a
+        # constant-one column of the query rows, which needs a free pad column: Cq % 8 != 0) and the kernel's output is
+        # the block's output.  Wiped rows come out as bf, exactly as in the reference (P row = 0).
+        self.qfold = None
+        if (allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck and self.Cq % 8 != 0
+                and ops.decoder_attention_supported(self.Cq + 1, self.O)):
+            wq64, wk64, wv64, wf64 = (t.double() for t in (wq, wk, wv, wf))
+            koff = pad8(self.Cq + 1)
+            n_ext = koff + self.O
+            w_ext = torch.zeros((n_ext, self.Ck), dtype=torch.float64, device=wq.device)
+            b_ext = torch.zeros((n_ext,), dtype=torch.float64, device=wq.device)
+            w_ext[:self.Cq] = wq64.t() @ wk64
+            b_ext[:self.Cq] = wq64.t() @ bk.double()
+            w_ext[self.Cq] = wk64.t() @ bq.double()
+            b_ext[self.Cq] = bq.double() @ bk.double()
+            w_ext[koff:] = wf64 @ wv64
+            b_ext[koff:] = wf64 @ bv.double()
+            self.qfold = dict(w=_bf16_weight(w_ext.float()), b=b_ext.float().contiguous(), koff=koff, n=n_ext)
         if self.folded:
             # S = (LN(q) Wq^T + bq) Wk . LN(x)^T  (the q.bk term is constant per row and cancels in the softmax)
             # out = (P . LN(x)) (Wf Wv)^T + (Wf bv + bf)          (rows of P sum to one)
@@ -471,6 +494,33 @@ def cross_attention_core(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, 
     return o, pa.V
 
 
+# the query-side fold pays once the per-forward projection of the latent array is small next to the per-query work
+QFOLD_MIN_QUERIES = 1024
+
+
+def use_query_fold(pa: PreparedAttention, Nq: int, Nk: int) -> bool:
+    return pa.qfold is not None and Nq >= QFOLD_MIN_QUERIES and Nq >= 2 * Nk
+
+
+def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep, residual):
+    """Attention + output projection (+ query residual) of a single-head cross-attend through the query-side fold and
+    the query-tiled decoder kernel (pio_decoder_attention_fwd).  qn: 16-bit [(1|B)*Nq, pad8(Cq)] (its first pad column
+    becomes the constant one that carries the per-key logit bias), kvn: 16-bit [B*Nk, pad8(Ck)].
+    Returns the fp32 block output [B*Nq, O] before the MLP."""
+    f = pa.qfold
+    qn[:, pa.Cq] = 1.0
+    _, kvp = ops.linear(kvn, pa.Ck, f["w"], f["n"], f["b"])      # [B*Nk, pad8(n)]: K' | b' | 0.. | V'
+    ld = kvp.shape[-1]
+    ldq = qn.shape[-1]
+    if residual is not None:
+        assert residual.stride(2) == 1
+    return ops.decoder_attention(qn, kvp, kvp.view(-1)[f["koff"]:], B=B, Nq=Nq, Nk=Nk, dqk=pa.Cq + 1, dv=pa.O,
+                                 ldq=ldq, ldk=ld, ldv=ld, strideQ=0 if q_bcast else Nq * ldq, strideK=Nk * ld,
+                                 strideV=Nk * ld, scale=pa.scale, key_mask=key_mask, row_keep=row_keep, bias=pa.bf,
+                                 residual=residual, ldr=residual.stride(1) if residual is not None else 0,
+                                 strideR=(residual.stride(0) if B > 1 else 0) if residual is not None else 0)
+
+
 def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual, row_keep=None):
     """Output projection (+ query residual) of a cross-attend: returns fp32 [B*Nq, O].  `row_keep` (u8 [B, Nq]) marks the
     rows the attention kernel did not wipe; it only matters on the folded path (see PreparedAttention.wf_bv)."""
@@ -530,6 +580,15 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
         q_src = q_src.contiguous()
     qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias)
     km, rk = _as_u8(key_mask), _as_u8(row_keep)
+    if use_query_residual:
+        res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
+    else:
+        res = None
+    if general is None and shard is None and use_query_fold(pa, Nq, Nk):
+        x = cross_attention_query_fold(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
+                                       residual=res)
+        y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
+        return y32.view(B, Nq, -1), y16
     if general is not None:
         assert shard is None and not pa.folded
         o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
@@ -541,10 +600,6 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
                                             row_keep=None, partial=True,
                                             num_splits=shard.local_splits if shard.local_splits > 0 else None)
         o = shard.combine(parts, row_keep=rk)
-    if use_query_residual:
-        res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
-    else:
-        res = None
     x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk)
     y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
     return y32.view(B, Nq, -1), y16

@@ -277,6 +277,32 @@ def attention_fwd(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, 
     return O
 
 
+def decoder_attention_supported(dqk: int, dv: int) -> bool:
+    return _lib.load().pio_decoder_attention_supported(dqk, dv) == 0
+
+
+@_device_guard
+def decoder_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: int, Nq: int, Nk: int, dqk: int, dv: int,
+                      ldq: int, ldk: int, ldv: int, strideQ: int, strideK: int, strideV: int, scale: float,
+                      key_mask: Optional[torch.Tensor] = None, row_keep: Optional[torch.Tensor] = None,
+                      bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                      ldr: int = 0, strideR: int = 0) -> torch.Tensor:
+    """Query-tiled single-head decoder attention (pio_decoder_attention_fwd): returns fp32 [B * Nq, dv] (row pitch a
+    multiple of 4 floats) = softmax(scale Q K^T) V + bias (+ residual)."""
+    _need_cuda(Q, K, V, key_mask, row_keep, bias, residual)
+    assert Q.dtype == K.dtype == V.dtype and Q.dtype in (BF16, torch.float16)
+    out = empty_f32_rows(B * Nq, dv, Q.device)
+    ldo = out.stride(0)
+    a = _lib.DecoderAttentionArgs(_ptr(Q), ldq, strideQ, _ptr(K), ldk, strideK, _ptr(V), ldv, strideV,
+                                  B, Nq, Nk, dqk, dv, scale,
+                                  _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
+                                  _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
+                                  _ptr(bias), _ptr(residual), ldr, strideR, _ptr(out), ldo, Nq * ldo,
+                                  1 if Q.dtype == torch.float16 else 0)
+    _lib.check(_lib.load().pio_decoder_attention_fwd(C.byref(a), _stream()), "pio_decoder_attention_fwd")
+    return out
+
+
 @_device_guard
 def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp: Optional[torch.Tensor], *,
                       row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,

@@ -275,3 +275,59 @@ def test_gemm_pair_kernel_reverse_tile_order_gives_identical_results(M, N, K, ba
     ref = A[:, :, :K].float() @ W[:, :, :K].float().transpose(1, 2) + bias + res
     assert _rel(outs[0], ref) < 2e-3
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("B,Nq,Nk,dqk,dv,masks,fp16", [
+    (1, 256, 64, 64, 64, False, False),          # one pair, one key tile
+    (1, 300, 200, 51, 37, False, False),         # ragged everything, odd head sizes
+    (2, 1000, 2048, 323, 322, False, False),     # the optical-flow decoder's folded head sizes
+    (2, 700, 777, 100, 200, True, False),        # key mask + wiped rows + residual + bias
+    (1, 5000, 2048, 323, 322, False, True),      # fp16 operands
+    (3, 129, 65, 384, 384, True, True),          # largest head sizes
+])
+def test_decoder_attention_pair_kernel(B, Nq, Nk, dqk, dv, masks, fp16):
+    """pio_decoder_attention_fwd (CTA-pair query-tiled kernel, distinct K / V) vs a plain fp32 evaluation."""
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(B * 1000 + Nq)
+    dt = torch.float16 if fp16 else torch.bfloat16
+    pad8 = ops.pad8
+    q = torch.randn(B, Nq, dqk, device="cuda")
+    k = torch.randn(B, Nk, dqk, device="cuda")
+    v = torch.randn(B, Nk, dv, device="cuda")
+    scale = 1.0 / dqk ** 0.5 * 2.0          # logits of a few units: the running max moves
+    Q = torch.zeros(B, Nq, pad8(dqk), dtype=dt, device="cuda")
+    K = torch.full((B, Nk, pad8(dqk) + 8), 7.0, dtype=dt, device="cuda")      # junk beyond dqk must never be read as data
+    V = torch.full((B, Nk, pad8(dv) + 16), -3.0, dtype=dt, device="cuda")
+    Q[:, :, :dqk], K[:, :, :dqk], V[:, :, :dv] = q.to(dt), k.to(dt), v.to(dt)
+    km = rk = res = bias = None
+    if masks:
+        km = (torch.rand(B, Nk, device="cuda") > 0.3)
+        km[0, : Nk // 2] = False
+        if B > 1:
+            km[1, :] = False                  # a sample without any valid key: every row is wiped
+        rk = (torch.rand(B, Nq, device="cuda") > 0.2)
+        res = torch.randn(B, Nq, dv + 3, device="cuda")
+        bias = torch.randn(dv, device="cuda")
+    out = ops.decoder_attention(Q, K, V, B=B, Nq=Nq, Nk=Nk, dqk=dqk, dv=dv, ldq=Q.stride(1), ldk=K.stride(1),
+                                ldv=V.stride(1), strideQ=Q.stride(0), strideK=K.stride(0), strideV=V.stride(0), scale=scale,
+                                key_mask=km.to(torch.uint8) if km is not None else None,
+                                row_keep=rk.to(torch.uint8) if rk is not None else None, bias=bias,
+                                residual=res, ldr=res.stride(1) if res is not None else 0,
+                                strideR=res.stride(0) if res is not None else 0)
+    out = out.reshape(B, Nq, dv)
+    qf, kf, vf = Q[:, :, :dqk].float(), K[:, :, :dqk].float(), V[:, :, :dv].float()
+    s = torch.einsum("bqd,bkd->bqk", qf, kf) * scale
+    if km is not None:
+        s = s.masked_fill(~km[:, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)          # rows without a valid key
+    ref = torch.einsum("bqk,bkd->bqd", p, vf)
+    if rk is not None:
+        ref = ref * rk[:, :, None]
+    if bias is not None:
+        ref = ref + bias
+    if res is not None:
+        ref = ref + res[:, :, :dv]
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert torch.isfinite(out).all()
+    assert err < (2e-3 if fp16 else 1e-2), err

@@ -536,3 +536,25 @@ def test_module_on_second_device_while_first_is_current():
         assert rel_err(z.cpu(), ref)[0] <= BF16_TOL
         with pytest.raises(RuntimeError, match="different devices"):
             enc.cross_attend(enc.latents(x.to("cuda:1")), x.to("cuda:0"))
+
+
+@pytest.mark.parametrize("name", ["decoder_small", "decoder_h1_querymask"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_query_fold_decoder_kernel_on_reference_goldens(name, mode, monkeypatch):
+    """The query-side fold + CTA-pair decoder kernel (engine.cross_attention_query_fold -> pio_decoder_attention_fwd),
+    forced onto the small single-head decoder fixtures (normally it takes over at >= 1024 queries): query residual,
+    query mask with wiped rows, final projection."""
+    from perceiverio_pytorch_b200 import engine, ops
+    params, inputs, meta, expected = load_golden(name)
+    m = _build_ours(meta)
+    m.load_state_dict(params, strict=True)
+    m = m.cuda()
+    calls = []
+    real = ops.decoder_attention
+    monkeypatch.setattr(ops, "decoder_attention", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    monkeypatch.setattr(engine, "use_query_fold", lambda pa, nq, nk: pa.qfold is not None)
+    with engine.precision_scope(mode):
+        got = _run_ours(m, inputs, meta)
+    assert calls, "the decoder kernel was not used"
+    emax, el2 = rel_err(got.float().cpu(), expected)
+    assert emax <= (BF16_TOL if mode == "bf16" else 2e-3), (name, mode, emax, el2)

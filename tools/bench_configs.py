@@ -91,7 +91,8 @@ def timeit(fn, iters, flush=True):
     own time (measured the same way) is subtracted."""
     global _L2_FLUSH
     if flush and _L2_FLUSH is None:
-        _L2_FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        with torch.inference_mode(False):     # a normal tensor: it is overwritten in place inside and outside inference mode
+            _L2_FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
