@@ -271,7 +271,7 @@ def graph_gap_profile(runner, inputs, replays=3, between=None):
         for s, e, n in evs:
             k = n.split("(")[0].replace("void ", "").replace("pio::", "")
             by[k] = by.get(k, 0.0) + (e - s)
-        top = sorted(by.items(), key=lambda kv: -kv[1])[:8]
+        top = sorted(by.items(), key=lambda kv: -kv[1])[:12]
         return {"replays": replays, "kernels_per_step": len(evs) / replays,
                 "span_ms_per_step": (evs[-1][1] - evs[0][0]) / replays / 1e3,
                 "kernel_ms_per_step": busy / replays / 1e3, "gap_ms_per_step": sum(inner) / replays / 1e3,

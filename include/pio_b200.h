@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 11
+#define PIO_ABI_VERSION 12
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -234,7 +234,12 @@ typedef struct pio_decoder_attention_args {
   const float* bias;                             /* [dv] or NULL */
   const float* residual; int64_t ldr; int64_t strideR;   /* fp32 [B, Nq, ldr] or NULL */
   float* out; int64_t ldo; int64_t strideO;      /* fp32 [B, Nq, ldo] */
-  int32_t fp16;                                  /* 16-bit format of Q, K, V and P: 0 = bf16, 1 = fp16 */
+  int32_t fp16;                                  /* 16-bit format of Q, K, V, P and out_ln: 0 = bf16, 1 = fp16 */
+  /* optional fused LayerNorm of the output rows (CrossAttention.layer_norm2, transformer_primitives.py:401): if out_ln
+   * != NULL the epilogue also writes out_ln[b, i, :] = LayerNorm(out[b, i, :dv]) * ln_gamma + ln_beta as 16-bit rows
+   * (columns dv..ld_ln-1 := 0) — the operand of the block's MLP, so no LayerNorm kernel re-reads `out`. */
+  void* out_ln; int64_t ld_ln; int64_t stride_ln;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 } pio_decoder_attention_args;
 int pio_decoder_attention_fwd(const pio_decoder_attention_args* a, void* stream);
 /* 0 if pio_decoder_attention_fwd covers these head sizes, PIO_ERR_UNSUPPORTED otherwise. */
@@ -253,6 +258,13 @@ typedef struct pio_linear_f32_args {
   float* y; int64_t ldy;            /* [M, N] */
   int64_t M;
   int32_t N, K;
+  /* optional second operand, y += x2 . w2^T: x2 is a 16-bit [M, K2] matrix (bf16, or fp16 if x2_fp16), w2 fp32 [N, K2].
+   * The decoder tail uses it: final_layer(x + fc2(h)) = x . Wfinal^T + h . (Wfinal W2)^T + const, so for a narrow head
+   * fc2, its fp32 output array and the separate head all collapse into this one pass (perceiver.py:177-179). */
+  const void* x2; int64_t ldx2;
+  const float* w2; int64_t ldw2;
+  int32_t K2;
+  int32_t x2_fp16;
 } pio_linear_f32_args;
 int pio_linear_f32(const pio_linear_f32_args* a, void* stream);
 

@@ -87,7 +87,8 @@ class DecoderAttentionArgs(C.Structure):
                 ("bias", vp),
                 ("residual", vp), ("ldr", i64), ("strideR", i64),
                 ("out", vp), ("ldo", i64), ("strideO", i64),
-                ("fp16", i32)]
+                ("fp16", i32),
+                ("out_ln", vp), ("ld_ln", i64), ("stride_ln", i64), ("ln_gamma", vp), ("ln_beta", vp), ("ln_eps", f32)]
 
 
 class CombineArgs(C.Structure):
@@ -101,7 +102,8 @@ class CombineArgs(C.Structure):
 
 class LinearF32Args(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("w", vp), ("ldw", i64), ("bias", vp), ("y", vp), ("ldy", i64),
-                ("M", i64), ("N", i32), ("K", i32)]
+                ("M", i64), ("N", i32), ("K", i32),
+                ("x2", vp), ("ldx2", i64), ("w2", vp), ("ldw2", i64), ("K2", i32), ("x2_fp16", i32)]
 
 
 _lib = None
@@ -146,7 +148,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 11:
+        if lib.pio_abi_version() != 12:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

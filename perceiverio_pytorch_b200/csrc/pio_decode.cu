@@ -28,6 +28,23 @@
 
 namespace pio {
 
+// Developer aid (compiled out unless -DPIO_DECODE_TRACE): CTAs 0 and 1 record (tag, clock64) pairs at the pipeline's
+// hand-off points; the first launch prints them to stderr (tools/trace_decode.py).  Tags: 1000 + 10 j + e MMA issuer,
+// 2000 + 10 j + e softmax warp 4 of the leader, 3000 + ... of its peer (clock64 is per SM: compare within one CTA only).
+#ifdef PIO_DECODE_TRACE
+__device__ unsigned long long g_dec_trace[3 * 2 * 512];
+#define DT(slot, tag)                                                                     \
+  do {                                                                                    \
+    if (blockIdx.x < 2 && blockIdx.y == 0 && lane == 0 && dtn < 512) {                    \
+      g_dec_trace[((slot) * 512 + dtn) * 2] = (unsigned long long)(tag);                  \
+      g_dec_trace[((slot) * 512 + dtn) * 2 + 1] = (unsigned long long)clock64();          \
+      ++dtn;                                                                              \
+    }                                                                                     \
+  } while (0)
+#else
+#define DT(slot, tag)
+#endif
+
 struct DecodeParams {
   int B, Nq, Nk, dqk, dv;
   int fp16;
@@ -42,12 +59,14 @@ struct DecodeParams {
   const float* bias;
   const float* residual; long long ldr, strideR;
   float* out; long long ldo, strideO;
+  uint16_t* out_ln; long long ld_ln, stride_ln;     // fused LayerNorm of the output rows (16-bit), or nullptr
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 };
 
 constexpr int DEC_BN = 64;             // keys per tile
 constexpr int DEC_KCHUNK = 32 * 128;   // one 64-column chunk of this CTA's 32 keys of a K tile
 constexpr int DEC_VCHUNK = 64 * 128;   // one 64-column chunk of this CTA's V columns, 64 keys
-constexpr int DEC_BAR_BYTES = 512 + 2048;
+constexpr int DEC_BAR_BYTES = 512 + 3072;   // mbarriers + three [2 halves][128 rows] fp32 exchange slots
 
 // D[tmem] (+)= A[tmem] * B[smem] on a CTA pair (A: 16-bit pairs packed in 32-bit TMEM columns of either CTA)
 __device__ __forceinline__ void umma_ts_2cta_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -88,6 +107,9 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+#ifdef PIO_DECODE_TRACE
+  int dtn = 0;
+#endif
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_decode_kernel: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
@@ -188,6 +210,7 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       auto issue_s = [&](int j) {
         mbar_wait(&k_full[ks_stage], k_phase);
         tc_fence_after();
+        DT(0, 1000 + 10 * j + 0);
         const uint32_t d = tmem_base + (uint32_t)((j & 1) * BN);
         const uint32_t b0 = k_lo + (uint32_t)((ks_stage * k_stage) >> 4);
         for (int ks = 0; ks < dqk_steps; ++ks) {
@@ -200,6 +223,7 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           umma_commit_2cta_mcast(&k_empty[ks_stage], 0x3);   // this K stage is free in both CTAs
           umma_commit_2cta_mcast(&s_full[j & 1], 0x3);       // S_j is complete in both CTAs' TMEM
         }
+        DT(0, 1000 + 10 * j + 1);
         if (++ks_stage == p.kst) { ks_stage = 0; k_phase ^= 1u; }
       };
       mbar_wait(q_full, 0);
@@ -208,8 +232,10 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);   // overwrites S_{j-1} / P_{j-1}: in order after PV_{j-1}, which consumed P_{j-1}
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        DT(0, 1000 + 10 * j + 2);
         mbar_wait(&v_full[vs_stage], v_phase);
         tc_fence_after();
+        DT(0, 1000 + 10 * j + 3);
         const uint32_t a0 = tmem_base + (uint32_t)((j & 1) * BN);   // P_j overlays the first BN/2 columns of S_j
         const uint32_t b0 = v_lo + (uint32_t)((vs_stage * v_stage) >> 4);
 #pragma unroll
@@ -230,6 +256,7 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           umma_commit_2cta_mcast(&v_empty[vs_stage], 0x3);
           umma_commit_2cta_mcast(&pv_done[j & 1], 0x3);
         }
+        DT(0, 1000 + 10 * j + 4);
         if (++vs_stage == p.vst) { vs_stage = 0; v_phase ^= 1u; }
       }
     }
@@ -256,10 +283,12 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const uint32_t t_s = tmem_base + (uint32_t)((j & 1) * BN + half * HC) + lane_off;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (warp == 4) DT(1 + (int)crank, 2000 + 1000 * (int)crank + 10 * j + 0);
       const bool tail = (k0 + HC > p.Nk) || (km != nullptr);
       uint32_t r[HC];
       tmem_ld32(t_s, r);
       tmem_wait_ld();
+      if (warp == 4) DT(1 + (int)crank, 2000 + 1000 * (int)crank + 10 * j + 1);
       if (tail) {
 #pragma unroll
         for (int i = 0; i < HC; ++i) {
@@ -286,6 +315,7 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         pair_sync();
         tmax = fmaxf(tmax, slot[(half ^ 1) * 128 + row]);
       }
+      if (warp == 4) DT(1 + (int)crank, 2000 + 1000 * (int)crank + 10 * j + 2);
       tmax *= p.scale_log2;
       float m_use = m;
       const bool grow = tmax > m + 8.0f;
@@ -344,6 +374,7 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
+      if (warp == 4) DT(1 + (int)crank, 2000 + 1000 * (int)crank + 10 * j + 3);
       if (lane == 0) mbar_arrive_cluster_release((j & 1) ? p_full_leader1 : p_full_leader0);
     }
     // ---- epilogue: total row sum = both halves' partial sums ----
@@ -359,37 +390,120 @@ pio_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const float inv = (keep && l > 0.f) ? 1.0f / l : 0.0f;
     float* orow = p.out + (long long)b * p.strideO + (long long)q * p.ldo;
     const float* rrow = p.residual ? p.residual + (long long)b * p.strideR + (long long)q * p.ldr : nullptr;
+    const bool al_out = (reinterpret_cast<uintptr_t>(orow) & 15u) == 0;
+    const bool al_res = rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15u) == 0;
+    const bool al_bias = p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
+    // v[0..31] = the block output for columns c .. c+31 of this thread's row (0 beyond dv): O / l + bias (+ residual)
+    auto fill_chunk = [&](int c, const uint32_t (&r)[32], float (&v)[32]) {
+      if (c + 32 <= p.dv && al_res && al_bias) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 t = make_float4(__uint_as_float(r[4 * g]) * inv, __uint_as_float(r[4 * g + 1]) * inv,
+                                 __uint_as_float(r[4 * g + 2]) * inv, __uint_as_float(r[4 * g + 3]) * inv);
+          if (p.bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c) + g);
+            t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+          }
+          if (rrow) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + c) + g);
+            t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+          }
+          v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = 0.f;
+          if (c + i < p.dv) {
+            t = __uint_as_float(r[i]) * inv;
+            if (p.bias) t += __ldg(p.bias + c + i);
+            if (rrow) t += __ldg(rrow + c + i);
+          }
+          v[i] = t;
+        }
+      }
+    };
+    float st1 = 0.f, st2 = 0.f;   // fused LayerNorm: this half's partial sum / sum of squares of the output row
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_off + c, r);
       tmem_wait_ld();
       if (q < p.Nq) {
-        const bool vec = (c + 32 <= p.dv) && ((reinterpret_cast<uintptr_t>(orow + c) & 15u) == 0) &&
-                         (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow + c) & 15u) == 0) &&
-                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + c) & 15u) == 0);
-        if (vec) {
+        float v[32];
+        fill_chunk(c, r, v);
+        if (p.out_ln != nullptr) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 v = make_float4(__uint_as_float(r[4 * g]) * inv, __uint_as_float(r[4 * g + 1]) * inv,
-                                   __uint_as_float(r[4 * g + 2]) * inv, __uint_as_float(r[4 * g + 3]) * inv);
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c) + g);
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-            }
-            if (rrow) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + c) + g);
-              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-            }
-            reinterpret_cast<float4*>(orow + c)[g] = v;
+          for (int i = 0; i < 32; ++i) {   // columns beyond dv hold zeros
+            st1 += v[i];
+            st2 = fmaf(v[i], v[i], st2);
           }
+        }
+        if (c + 32 <= p.dv && al_out) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(orow + c)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c + i < p.dv) {
-              float v = __uint_as_float(r[i]) * inv;
-              if (p.bias) v += __ldg(p.bias + c + i);
-              if (rrow) v += __ldg(rrow + c + i);
-              orow[c + i] = v;
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.dv) orow[c + i] = v[i];
+        }
+      }
+    }
+    if (p.out_ln != nullptr) {
+      // ---- second pass: the row statistics of both halves, then the normalised 16-bit row (the MLP's operand) ----
+      float* slot = xchg + ((ntiles + 1) & 1) * 256;   // the other exchange slot (the row-sum exchange used ntiles & 1)
+      float* slot2 = xchg + 512;                       // a third [2][128] slot (DEC_BAR_BYTES)
+      slot[half * 128 + row] = st1;
+      slot2[half * 128 + row] = st2;
+      pair_sync();
+      st1 += slot[(half ^ 1) * 128 + row];
+      st2 += slot2[(half ^ 1) * 128 + row];
+      const float inv_c = 1.0f / (float)p.dv;
+      const float mean = st1 * inv_c;
+      const float rstd = rsqrtf(fmaxf(st2 * inv_c - mean * mean, 0.f) + p.ln_eps);
+      const float nmr = -mean * rstd;
+      uint16_t* lrow = p.out_ln + (long long)b * p.stride_ln + (long long)q * p.ld_ln;
+      const bool al_ln = (reinterpret_cast<uintptr_t>(lrow) & 15u) == 0 &&
+                         (p.ln_gamma == nullptr || (reinterpret_cast<uintptr_t>(p.ln_gamma) & 15u) == 0) &&
+                         (p.ln_beta == nullptr || (reinterpret_cast<uintptr_t>(p.ln_beta) & 15u) == 0);
+      const int ln_end = half == 0 ? c_end : (int)p.ld_ln;   // the second half also zeroes the pad columns
+      for (int c = c_begin; c < ln_end; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_o + lane_off + c, r);
+        tmem_wait_ld();
+        if (q < p.Nq) {
+          float v[32];
+          fill_chunk(c, r, v);
+          if (c + 32 <= p.dv && al_ln) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float y[8];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                float4 gm = make_float4(1.f, 1.f, 1.f, 1.f), bt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.ln_gamma) gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c) + 2 * g + h2);
+                if (p.ln_beta) bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c) + 2 * g + h2);
+                y[4 * h2] = fmaf(fmaf(v[8 * g + 4 * h2], rstd, nmr), gm.x, bt.x);
+                y[4 * h2 + 1] = fmaf(fmaf(v[8 * g + 4 * h2 + 1], rstd, nmr), gm.y, bt.y);
+                y[4 * h2 + 2] = fmaf(fmaf(v[8 * g + 4 * h2 + 2], rstd, nmr), gm.z, bt.z);
+                y[4 * h2 + 3] = fmaf(fmaf(v[8 * g + 4 * h2 + 3], rstd, nmr), gm.w, bt.w);
+              }
+              reinterpret_cast<uint4*>(lrow + c)[g] = make_uint4(pack16x2(y[0], y[1], p.fp16), pack16x2(y[2], y[3], p.fp16),
+                                                                 pack16x2(y[4], y[5], p.fp16), pack16x2(y[6], y[7], p.fp16));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int cc = c + i;
+              if (cc < p.ld_ln) {
+                float y = 0.f;
+                if (cc < p.dv) {
+                  y = fmaf(v[i], rstd, nmr);
+                  if (p.ln_gamma) y *= __ldg(p.ln_gamma + cc);
+                  if (p.ln_beta) y += __ldg(p.ln_beta + cc);
+                }
+                lrow[cc] = cvt16(y, p.fp16);
+              }
             }
           }
         }
@@ -466,6 +580,11 @@ extern "C" int pio_decoder_attention_fwd(const pio_decoder_attention_args* a, vo
   p.bias = a->bias;
   p.residual = a->residual; p.ldr = a->ldr; p.strideR = a->strideR;
   p.out = a->out; p.ldo = a->ldo; p.strideO = a->strideO;
+  p.out_ln = reinterpret_cast<uint16_t*>(a->out_ln); p.ld_ln = a->ld_ln; p.stride_ln = a->stride_ln;
+  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
+  PIO_REQUIRE(!a->out_ln || (a->ld_ln >= a->dv && a->ld_ln % 2 == 0 && (reinterpret_cast<uintptr_t>(a->out_ln) & 3u) == 0 &&
+                             a->stride_ln % 2 == 0),
+              "pio_decoder_attention_fwd: out_ln needs an even, 4-byte aligned row pitch >= dv");
 
   CUtensorMap tq, tk, tv;
   {
@@ -502,6 +621,25 @@ extern "C" int pio_decoder_attention_fwd(const pio_decoder_attention_args* a, vo
     PIO_CUDA_OK(launch_kernel(pio_decode_kernel, dim3(pairs * 2, (unsigned)a->B, 1), dim3(384, 1, 1), (size_t)smem_bytes, stream,
                               2, tq, tk, tv, p));
   }
+#ifdef PIO_DECODE_TRACE
+  {
+    static bool dumped = false;
+    if (!dumped) {
+      dumped = true;
+      cudaDeviceSynchronize();
+      static unsigned long long host[3 * 2 * 512];
+      cudaMemcpyFromSymbol(host, g_dec_trace, sizeof(host));
+      for (int s = 0; s < 3; ++s) {
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 512; ++i)
+          if (host[2 * (s * 512 + i)] != 0 && host[2 * (s * 512 + i) + 1] < t0) t0 = host[2 * (s * 512 + i) + 1];
+        for (int i = 0; i < 512; ++i)
+          if (host[2 * (s * 512 + i)] != 0)
+            fprintf(stderr, "DT %d %llu %llu\n", s, host[2 * (s * 512 + i)], host[2 * (s * 512 + i) + 1] - t0);
+      }
+    }
+  }
+#endif
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;

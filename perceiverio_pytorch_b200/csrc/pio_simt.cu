@@ -830,38 +830,119 @@ __global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args 
 template <int NOUT>
 __global__ void __launch_bounds__(256) pio_linear_f32_kernel(pio_linear_f32_args a) {
   pdl_sync();
+  constexpr int ROWS = 4;   // rows per warp pass: their loads are issued together (the kernel is bound by loads in flight)
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= a.M) return;
-  const float* xr = a.x + row * a.ldx;
-  float acc[NOUT];
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= a.M) return;
+  float acc[ROWS][NOUT];
 #pragma unroll
-  for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
-  for (int k0 = 0; k0 < a.K; k0 += 128) {
-    float xv[4];
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + lane + 32 * i;
-      xv[i] = (k < a.K) ? __ldg(xr + k) : 0.f;
+    for (int n = 0; n < NOUT; ++n) acc[r][n] = 0.f;
+  // rows beyond M are clamped to the last row (their results are not stored)
+  const float* xr[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) xr[r] = a.x + (row0 + r < a.M ? row0 + r : a.M - 1) * a.ldx;
+  int kdone = 0;
+  if (((a.ldx | a.ldw) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.w)) & 15u) == 0) {
+    // 16-byte loads: lane l owns the float4s l, l + 32, ... of each row (rows and weight rows are 16-byte aligned)
+    const int nk4 = a.K >> 2;
+#pragma unroll 2
+    for (int i = lane; i < nk4; i += 32) {
+      float4 xv[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) xv[r] = __ldg(reinterpret_cast<const float4*>(xr[r]) + i);
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        if (n < a.N) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w + (long long)n * a.ldw) + i);
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r)
+            acc[r][n] = fmaf(xv[r].x, wv.x, fmaf(xv[r].y, wv.y, fmaf(xv[r].z, wv.z, fmaf(xv[r].w, wv.w, acc[r][n]))));
+        }
+      }
     }
+    kdone = nk4 << 2;
+  }
+  for (int k = kdone + lane; k < a.K; k += 32) {
+    float xv[ROWS];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + lane + 32 * i;
-      if (k < a.K) {
+    for (int r = 0; r < ROWS; ++r) xv[r] = __ldg(xr[r] + k);
 #pragma unroll
-        for (int n = 0; n < NOUT; ++n)
-          if (n < a.N) acc[n] = fmaf(xv[i], __ldg(a.w + (long long)n * a.ldw + k), acc[n]);
+    for (int n = 0; n < NOUT; ++n) {
+      if (n < a.N) {
+        const float wv = __ldg(a.w + (long long)n * a.ldw + k);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r][n] = fmaf(xv[r], wv, acc[r][n]);
+      }
+    }
+  }
+  if (a.x2 != nullptr) {
+    // second operand: 16-bit rows times their own fp32 weights (the decoder tail: final_layer folded into fc2)
+    const uint16_t* hr[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      hr[r] = reinterpret_cast<const uint16_t*>(a.x2) + (row0 + r < a.M ? row0 + r : a.M - 1) * a.ldx2;
+    int k2done = 0;
+    if ((a.ldx2 & 7) == 0 && (a.ldw2 & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a.x2) | reinterpret_cast<uintptr_t>(a.w2)) & 15u) == 0) {
+      const int nk8 = a.K2 >> 3;
+#pragma unroll 2
+      for (int i = lane; i < nk8; i += 32) {
+        uint4 hv[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) hv[r] = __ldg(reinterpret_cast<const uint4*>(hr[r]) + i);
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          if (n < a.N) {
+            const float4* w4 = reinterpret_cast<const float4*>(a.w2 + (long long)n * a.ldw2) + 2 * i;
+            const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+              const uint32_t hw[4] = {hv[r].x, hv[r].y, hv[r].z, hv[r].w};
+              float xv[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                xv[2 * e] = cvt16_back((uint16_t)(hw[e] & 0xffffu), a.x2_fp16);
+                xv[2 * e + 1] = cvt16_back((uint16_t)(hw[e] >> 16), a.x2_fp16);
+              }
+              acc[r][n] = fmaf(xv[0], w0.x, fmaf(xv[1], w0.y, fmaf(xv[2], w0.z, fmaf(xv[3], w0.w, acc[r][n]))));
+              acc[r][n] = fmaf(xv[4], w1.x, fmaf(xv[5], w1.y, fmaf(xv[6], w1.z, fmaf(xv[7], w1.w, acc[r][n]))));
+            }
+          }
+        }
+      }
+      k2done = nk8 << 3;
+    }
+    for (int k = k2done + lane; k < a.K2; k += 32) {
+      float xv[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) xv[r] = cvt16_back(__ldg(hr[r] + k), a.x2_fp16);
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        if (n < a.N) {
+          const float wv = __ldg(a.w2 + (long long)n * a.ldw2 + k);
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r) acc[r][n] = fmaf(xv[r], wv, acc[r][n]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int n = 0; n < NOUT; ++n) acc[n] = warp_sum(acc[n]);
-  if (lane < a.N) {
-    float v = 0.f;
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-    for (int n = 0; n < NOUT; ++n)
-      if (n == lane) v = acc[n];
-    a.y[row * a.ldy + lane] = v + (a.bias ? __ldg(a.bias + lane) : 0.f);
+    for (int n = 0; n < NOUT; ++n) acc[r][n] = warp_sum(acc[r][n]);
+  if (lane < a.N) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (row0 + r < a.M) {
+        float v = 0.f;
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n)
+          if (n == lane) v = acc[r][n];
+        a.y[(row0 + r) * a.ldy + lane] = v + (a.bias ? __ldg(a.bias + lane) : 0.f);
+      }
+    }
   }
 }
 
@@ -939,11 +1020,14 @@ extern "C" int pio_linear_f32(const pio_linear_f32_args* a, void* stream_) {
   PIO_REQUIRE(a && a->x && a->w && a->y, "pio_linear_f32: null pointer");
   PIO_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "pio_linear_f32: bad shape");
   PIO_REQUIRE(a->ldx >= a->K && a->ldw >= a->K && a->ldy >= a->N, "pio_linear_f32: bad leading dimension");
+  PIO_REQUIRE(!a->x2 || (a->w2 && a->K2 > 0 && a->ldx2 >= a->K2 && a->ldw2 >= a->K2),
+              "pio_linear_f32: the second operand needs its weights and leading dimensions");
   if (a->N > 16) return fail(PIO_ERR_UNSUPPORTED, "pio_linear_f32 covers N <= 16 (got %d); use pio_gemm_bf16", a->N);
-  const long long blocks = (a->M + 7) / 8;
+  const long long blocks = (a->M + 31) / 32;   // 8 warps x 4 rows per block
   PIO_REQUIRE(blocks < (1ll << 31), "pio_linear_f32: too many rows");
   {
-    ProfileScope prof(KF_LINEAR_F32, 2.0 * a->M * a->N * (double)a->K, (double)a->M * (4.0 * a->K + 4.0 * a->N), stream);
+    ProfileScope prof(KF_LINEAR_F32, 2.0 * a->M * a->N * (double)(a->K + (a->x2 ? a->K2 : 0)),
+                      (double)a->M * (4.0 * a->K + 4.0 * a->N + (a->x2 ? 2.0 * a->K2 : 0.0)), stream);
     if (a->N <= 2) pio_linear_f32_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(*a);
     else if (a->N <= 4) pio_linear_f32_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(*a);
     else if (a->N <= 8) pio_linear_f32_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(*a);

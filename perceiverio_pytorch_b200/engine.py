@@ -408,12 +408,41 @@ def attention(q, ldq, qcol, k, ldk, kcol, v, ldv, vcol, *, B, H, Nq, Nk, dqk, dv
 # blocks
 # ---------------------------------------------------------------------------------------------------------------
 
-def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False, stats_out=None):
+class PreparedTail:
+    """A decoder whose final projection has only a handful of outputs (optical flow: 322 -> 2, perceiver.py:179):
+    final(x + fc2(h)) = x Wfin^T + h (Wfin W2)^T + (Wfin b2 + bfin), so fc2, its fp32 output array and the separate head
+    collapse into one fp32 pass over x and h (pio_linear_f32 with a second operand; all weights stay fp32)."""
+
+    def __init__(self, mlp, final_layer):
+        d = torch.float64
+        wfin, w2 = final_layer.weight.detach().to(d), mlp.fc2.weight.detach().to(d)
+        b = wfin @ mlp.fc2.bias.detach().to(d)
+        if final_layer.bias is not None:
+            b = b + final_layer.bias.detach().to(d)
+        self.wfin = self._pitch4(wfin.float())
+        self.w2 = self._pitch4((wfin @ w2).float())
+        self.bias = b.float().contiguous()
+
+    @staticmethod
+    def _pitch4(w: torch.Tensor) -> torch.Tensor:
+        """[n, k] view of a buffer whose row pitch is a multiple of 4 floats (16-byte aligned rows: vector loads)."""
+        n, k = w.shape
+        buf = torch.zeros((n, (k + 3) // 4 * 4), dtype=torch.float32, device=w.device)
+        buf[:, :k] = w
+        return buf[:, :k]
+
+
+def mlp_block(pm: PreparedMLP, x_f32: torch.Tensor, ln_w, ln_b, *, want_bf16_out=False, stats_out=None, xn=None,
+              tail: Optional[PreparedTail] = None):
     """x + fc2(gelu(fc1(LN(x)))) on a flat fp32 [M, C] matrix.  Returns (fp32 [M, cout], bf16 copy or None).
     `stats_out` (ops.empty_row_stats(M, cout)) additionally receives the per-row partial (sum, sum of squares) of the
-    result — the producer side of the fused LayerNorm of the next block."""
-    xn = ops.layernorm_bf16(x_f32, ln_w, ln_b)
+    result — the producer side of the fused LayerNorm of the next block.  `xn`: LN(x) when a producer kernel already
+    wrote it.  `tail`: return final_layer(x + fc2(...)) [M, n_out] instead (see PreparedTail)."""
+    if xn is None:
+        xn = ops.layernorm_bf16(x_f32, ln_w, ln_b)
     _, h = ops.linear(xn, pm.cin, pm.w1, pm.hidden, pm.b1, act=1)
+    if tail is not None:
+        return ops.linear_f32(x_f32, tail.wfin, tail.bias, x2=h, w2=tail.w2), None
     if stats_out is None:
         return ops.linear(h, pm.hidden, pm.w2, pm.cout, pm.b2, residual=x_f32, want_f32=True, want_bf16=want_bf16_out)
     m = h.shape[0]
@@ -502,11 +531,13 @@ def use_query_fold(pa: PreparedAttention, Nq: int, Nk: int) -> bool:
     return pa.qfold is not None and Nq >= QFOLD_MIN_QUERIES and Nq >= 2 * Nk
 
 
-def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep, residual):
+def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep, residual,
+                               ln=None):
     """Attention + output projection (+ query residual) of a single-head cross-attend through the query-side fold and
     the query-tiled decoder kernel (pio_decoder_attention_fwd).  qn: 16-bit [(1|B)*Nq, pad8(Cq)] (its first pad column
     becomes the constant one that carries the per-key logit bias), kvn: 16-bit [B*Nk, pad8(Ck)].
-    Returns the fp32 block output [B*Nq, O] before the MLP."""
+    Returns the fp32 block output [B*Nq, O] before the MLP — and, with ln = (gamma, beta, eps), its LayerNorm as 16-bit
+    rows, written by the same kernel."""
     f = pa.qfold
     qn[:, pa.Cq] = 1.0
     _, kvp = ops.linear(kvn, pa.Ck, f["w"], f["n"], f["b"])      # [B*Nk, pad8(n)]: K' | b' | 0.. | V'
@@ -518,7 +549,7 @@ def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_b
                                  ldq=ldq, ldk=ld, ldv=ld, strideQ=0 if q_bcast else Nq * ldq, strideK=Nk * ld,
                                  strideV=Nk * ld, scale=pa.scale, key_mask=key_mask, row_keep=row_keep, bias=pa.bf,
                                  residual=residual, ldr=residual.stride(1) if residual is not None else 0,
-                                 strideR=(residual.stride(0) if B > 1 else 0) if residual is not None else 0)
+                                 strideR=(residual.stride(0) if B > 1 else 0) if residual is not None else 0, ln=ln)
 
 
 def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual, row_keep=None):
@@ -554,7 +585,7 @@ def _as_u8(mask: Optional[torch.Tensor]):
 def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torch.Tensor, inputs_kv: torch.Tensor,
                           ln_q, ln_kv, ln2, *, use_query_residual: bool, key_mask=None, row_keep=None,
                           want_bf16_out=False, shard=None, stats_out=None,
-                          general: Optional[GeneralAttentionArgs] = None):
+                          general: Optional[GeneralAttentionArgs] = None, tail: Optional[PreparedTail] = None):
     """CrossAttention.forward (transformer_primitives.py:371-406).
 
     inputs_q fp32 [B, Nq, Cq] (batch stride may be 0), inputs_kv fp32 [B, Nk, Ck].  `shard`, if given, is a
@@ -585,9 +616,10 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     else:
         res = None
     if general is None and shard is None and use_query_fold(pa, Nq, Nk):
-        x = cross_attention_query_fold(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
-                                       residual=res)
-        y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
+        x, xn = cross_attention_query_fold(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
+                                           residual=res, ln=(ln2.weight, ln2.bias, ln2.eps))
+        y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, xn=xn,
+                             tail=tail)
         return y32.view(B, Nq, -1), y16
     if general is not None:
         assert shard is None and not pa.folded
@@ -601,5 +633,5 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
                                             num_splits=shard.local_splits if shard.local_splits > 0 else None)
         o = shard.combine(parts, row_keep=rk)
     x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk)
-    y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out)
+    y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, tail=tail)
     return y32.view(B, Nq, -1), y16

@@ -194,14 +194,21 @@ def linear(x: torch.Tensor, K: int, w: torch.Tensor, N: int, bias: Optional[torc
 
 
 @_device_guard
-def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """y = x @ w^T + bias in fp32 on CUDA cores, for N <= 16 output channels (x fp32 [M, K], w fp32 [N, K])."""
-    _need_cuda(x, w, bias)
+def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, x2: Optional[torch.Tensor] = None,
+               w2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ w^T + bias (+ x2 @ w2^T) in fp32 on CUDA cores, for N <= 16 output channels (x fp32 [M, K], w fp32 [N, K];
+    x2 16-bit [M, >= K2], w2 fp32 [N, K2])."""
+    _need_cuda(x, w, bias, x2, w2)
     assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.stride(-1) == 1 and w.stride(-1) == 1
     m, k = x.shape
     n = w.shape[0]
     y = torch.empty((m, n), dtype=torch.float32, device=x.device)
-    a = _lib.LinearF32Args(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(y), n, m, n, k)
+    if x2 is not None:
+        assert x2.dtype in (BF16, torch.float16) and w2.dtype == torch.float32 and x2.shape[0] == m and w2.shape[0] == n
+        extra = (_ptr(x2), x2.stride(0), _ptr(w2), w2.stride(0), w2.shape[1], 1 if x2.dtype == torch.float16 else 0)
+    else:
+        extra = (None, 0, None, 0, 0, 0)
+    a = _lib.LinearF32Args(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(y), n, m, n, k, *extra)
     _lib.check(_lib.load().pio_linear_f32(C.byref(a), _stream()), "pio_linear_f32")
     return y
 
@@ -286,21 +293,28 @@ def decoder_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: i
                       ldq: int, ldk: int, ldv: int, strideQ: int, strideK: int, strideV: int, scale: float,
                       key_mask: Optional[torch.Tensor] = None, row_keep: Optional[torch.Tensor] = None,
                       bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                      ldr: int = 0, strideR: int = 0) -> torch.Tensor:
+                      ldr: int = 0, strideR: int = 0, ln=None):
     """Query-tiled single-head decoder attention (pio_decoder_attention_fwd): returns fp32 [B * Nq, dv] (row pitch a
-    multiple of 4 floats) = softmax(scale Q K^T) V + bias (+ residual)."""
+    multiple of 4 floats) = softmax(scale Q K^T) V + bias (+ residual).  ln = (gamma, beta, eps): additionally returns
+    LayerNorm(out) as 16-bit rows [B * Nq, pad8(dv)] (written by the kernel's epilogue) -> (out, out_ln)."""
     _need_cuda(Q, K, V, key_mask, row_keep, bias, residual)
     assert Q.dtype == K.dtype == V.dtype and Q.dtype in (BF16, torch.float16)
     out = empty_f32_rows(B * Nq, dv, Q.device)
     ldo = out.stride(0)
+    out_ln = None
+    ln_args = (None, 0, 0, None, None, 0.0)
+    if ln is not None:
+        _need_cuda(ln[0], ln[1])
+        out_ln = torch.empty((B * Nq, pad8(dv)), dtype=Q.dtype, device=Q.device)
+        ln_args = (_ptr(out_ln), out_ln.stride(0), Nq * out_ln.stride(0), _ptr(ln[0]), _ptr(ln[1]), float(ln[2]))
     a = _lib.DecoderAttentionArgs(_ptr(Q), ldq, strideQ, _ptr(K), ldk, strideK, _ptr(V), ldv, strideV,
                                   B, Nq, Nk, dqk, dv, scale,
                                   _ptr(key_mask), key_mask.stride(0) if key_mask is not None else 0,
                                   _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
                                   _ptr(bias), _ptr(residual), ldr, strideR, _ptr(out), ldo, Nq * ldo,
-                                  1 if Q.dtype == torch.float16 else 0)
+                                  1 if Q.dtype == torch.float16 else 0, *ln_args)
     _lib.check(_lib.load().pio_decoder_attention_fwd(C.byref(a), _stream()), "pio_decoder_attention_fwd")
-    return out
+    return out if ln is None else (out, out_ln)
 
 
 @_device_guard

@@ -231,8 +231,16 @@ class PerceiverDecoder(nn.Module):
         # the wide final projection consumes bf16 rows: let the MLP's last GEMM write them next to the fp32 result
         want16 = (self._final_project and n_out > 16 and engine.fast()
                   and self.query_channels % 16 == 0)
+        tail = None
+        if self._final_project and n_out <= 16 and engine.fast():
+            # a handful of output channels (optical flow: 322 -> 2): the head is folded into the MLP's second layer and
+            # evaluated in fp32 on CUDA cores together with it.  The head is 0.01 % of the FLOPs but its 16-bit rounding
+            # alone would cost 1.2e-2 of the 1e-2 error budget in bf16.
+            tail = engine.prepared(self, "tail", lambda: engine.PreparedTail(self.decoding_cross_attn.mlp, self.final_layer))
         y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
-                                                              want_bf16_out=want16)
+                                                              want_bf16_out=want16, tail=tail)
+        if tail is not None:
+            return y32
         if not self._final_project:
             return y32 if y32.is_contiguous() else y32.contiguous()   # odd widths carry a 16-byte row pitch inside
         B, Nq, C = y32.shape

@@ -300,7 +300,7 @@ class CrossAttention(nn.Module):
         return (general.matrix, y) if return_matrix else y
 
     def _forward_factored(self, inputs_q, inputs_kv, *, key_mask=None, row_keep=None, want_bf16_out=False,
-                          shard=None, stats_out=None, general=None):
+                          shard=None, stats_out=None, general=None, tail=None):
         _check_inference(self, *self._dropout_probs)
         if engine.PRECISION == "bf16x3":
             ops._need_cuda(inputs_q, inputs_kv)
@@ -320,4 +320,4 @@ class CrossAttention(nn.Module):
         return engine.cross_attention_block(pa, pm, inputs_q, inputs_kv, self.layer_norm_q, self.layer_norm_kv,
                                             self.layer_norm2, use_query_residual=self._use_query_residual,
                                             key_mask=key_mask, row_keep=row_keep, want_bf16_out=want_bf16_out,
-                                            shard=shard, stats_out=stats_out, general=general)
+                                            shard=shard, stats_out=stats_out, general=general, tail=tail)

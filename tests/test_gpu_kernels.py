@@ -314,6 +314,20 @@ def test_decoder_attention_pair_kernel(B, Nq, Nk, dqk, dv, masks, fp16):
                                 row_keep=rk.to(torch.uint8) if rk is not None else None, bias=bias,
                                 residual=res, ldr=res.stride(1) if res is not None else 0,
                                 strideR=res.stride(0) if res is not None else 0)
+    # the same launch with the fused LayerNorm of the output rows (the MLP's operand)
+    g, bt = 1 + 0.1 * torch.randn(dv, device="cuda"), 0.1 * torch.randn(dv, device="cuda")
+    out2, out_ln = ops.decoder_attention(Q, K, V, B=B, Nq=Nq, Nk=Nk, dqk=dqk, dv=dv, ldq=Q.stride(1), ldk=K.stride(1),
+                                         ldv=V.stride(1), strideQ=Q.stride(0), strideK=K.stride(0), strideV=V.stride(0),
+                                         scale=scale, key_mask=km.to(torch.uint8) if km is not None else None,
+                                         row_keep=rk.to(torch.uint8) if rk is not None else None, bias=bias,
+                                         residual=res, ldr=res.stride(1) if res is not None else 0,
+                                         strideR=res.stride(0) if res is not None else 0, ln=(g, bt, 1e-5))
+    assert torch.equal(out2, out)
+    ln_ref = torch.nn.functional.layer_norm(out.reshape(B * Nq, dv), (dv,), g, bt, 1e-5)
+    assert out_ln.shape == (B * Nq, pad8(dv)) and out_ln.dtype == dt
+    assert float((out_ln[:, :dv].float() - ln_ref).abs().max()) <= (4e-3 if fp16 else 3e-2) * float(ln_ref.abs().max())
+    if out_ln.shape[1] > dv:
+        assert float(out_ln[:, dv:].float().abs().max()) == 0.0
     out = out.reshape(B, Nq, dv)
     qf, kf, vf = Q[:, :, :dqk].float(), K[:, :, :dqk].float(), V[:, :, :dv].float()
     s = torch.einsum("bqd,bkd->bqk", qf, kf) * scale
@@ -331,3 +345,18 @@ def test_decoder_attention_pair_kernel(B, Nq, Nk, dqk, dv, masks, fp16):
     err = float((out - ref).abs().max() / ref.abs().max())
     assert torch.isfinite(out).all()
     assert err < (2e-3 if fp16 else 1e-2), err
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_linear_f32_with_second_16bit_operand(fp16):
+    """pio_linear_f32 with x2 / w2: y = x W^T + x2 W2^T + b — the decoder tail (final_layer folded into fc2)."""
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(11)
+    M, K, K2, N = 5000, 322, 322, 2
+    dt = torch.float16 if fp16 else torch.bfloat16
+    x = torch.randn(M, K + 2, device="cuda")[:, :K]                 # a row pitch that is not K
+    x2 = torch.randn(M, ops.pad8(K2), device="cuda").to(dt)
+    w, w2, b = torch.randn(N, K, device="cuda"), torch.randn(N, K2, device="cuda"), torch.randn(N, device="cuda")
+    y = ops.linear_f32(x, w, b, x2=x2, w2=w2)
+    ref = (x.double() @ w.double().t() + x2[:, :K2].double() @ w2.double().t() + b.double()).float()
+    assert _rel(y, ref) < 1e-5
