@@ -624,6 +624,73 @@ __global__ void __launch_bounds__(256) pio_softmax_kernel(pio_softmax_args a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Long rows without the general arguments (the multimodal encoder's explicit-S path: 784 rows x 52,097 keys): one
+// 512-thread block per row, TWO passes with 16-byte loads — pass 1 keeps an online (max, sum) pair per thread (one read of
+// the row instead of two), pass 2 re-reads the row (L2: a row is <= 208 KB) and writes four 16-bit probabilities per
+// 8-byte store.  HBM/L2-bound: 8 cols bytes in + 2 ldp bytes out per row.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) pio_softmax_long_kernel(pio_softmax_args a) {
+  pdl_sync();
+  __shared__ float red_m[16], red_l[16];
+  const long long row_id = blockIdx.x;
+  const int b = (int)(row_id / a.rows);
+  const int r = (int)(row_id % a.rows);
+  const float4* s4 = reinterpret_cast<const float4*>(a.S + (long long)b * a.strideS + (long long)r * a.lds);
+  uint2* p2 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.P) + (long long)b * a.strideP + (long long)r * a.ldp);
+  const uint8_t* km = a.key_mask ? a.key_mask + (long long)b * a.stride_km : nullptr;
+  const bool keep = a.row_keep ? a.row_keep[(long long)b * a.stride_rk + r] != 0 : true;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nvec = (a.cols + 3) >> 2;
+  const int nvec_out = (int)(a.ldp >> 2);
+  auto load4 = [&](int c4, float (&v)[4]) {
+    const float4 t = __ldg(s4 + c4);
+    const int c = 4 * c4;
+    v[0] = t.x * a.scale; v[1] = t.y * a.scale; v[2] = t.z * a.scale; v[3] = t.w * a.scale;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c + e >= a.cols || (km && !km[c + e])) v[e] = -INFINITY;
+  };
+  float m = -INFINITY, l = 0.f;
+  if (keep) {
+    for (int c4 = tid; c4 < nvec; c4 += 512) {
+      float v[4];
+      load4(c4, v);
+      const float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+      if (mx > m) {
+        l *= __expf(m - mx);      // m == -inf: l is 0 and exp(-inf) = 0
+        m = mx;
+      }
+      if (m != -INFINITY) l += (__expf(v[0] - m) + __expf(v[1] - m)) + (__expf(v[2] - m) + __expf(v[3] - m));
+    }
+  }
+  // block-wide merge of the (max, sum) pairs
+  {
+    const float wm = warp_max(m);
+    l = (m == -INFINITY) ? 0.f : l * __expf(m - wm);
+    l = warp_sum(l);
+    if (lane == 0) { red_m[warp] = wm; red_l[warp] = l; }
+  }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) M = fmaxf(M, red_m[i]);
+  float L = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) L += (red_m[i] == -INFINITY) ? 0.f : red_l[i] * __expf(red_m[i] - M);
+  const float inv = (M != -INFINITY && L > 0.f) ? 1.0f / L : 0.0f;   // wiped / fully masked rows are written as zeros
+  for (int c4 = tid; c4 < nvec_out; c4 += 512) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (inv != 0.f && c4 < nvec) {
+      float v[4];
+      load4(c4, v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = __expf(v[e] - M) * inv;
+    }
+    p2[c4] = make_uint2(pack16x2(o[0], o[1], a.fp16), pack16x2(o[2], o[3], a.fp16));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Row softmax for rows of up to 2048 columns (the decoders: 256 .. 2048 latents as keys): one warp per row, the row
 // lives in registers (lane l owns the float4 at columns 4 (l + 32 i)), S is read exactly once with 16-byte loads and P
 // is written with 8-byte stores.  HBM-bound: 4 cols bytes in + 2 ldp bytes out per row.
@@ -1225,6 +1292,9 @@ extern "C" int pio_softmax_bf16(const pio_softmax_args* a, void* stream_) {
       else if (need <= 4) pio_softmax_warp_kernel<4><<<wblocks, 256, 0, stream>>>(*a);
       else if (need <= 8) pio_softmax_warp_kernel<8><<<wblocks, 256, 0, stream>>>(*a);
       else pio_softmax_warp_kernel<16><<<wblocks, 256, 0, stream>>>(*a);
+    } else if (!a->split && !a->dense_mask && !a->bias && !a->P_f32 && a->lds % 4 == 0 && a->strideS % 4 == 0 &&
+               a->ldp % 4 == 0 && a->strideP % 4 == 0 && aligned16(a->S) && (reinterpret_cast<uintptr_t>(a->P) & 7u) == 0) {
+      pio_softmax_long_kernel<<<(unsigned)blocks, 512, 0, stream>>>(*a);
     } else {
       pio_softmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a);
     }

@@ -343,8 +343,31 @@ def _materialised_attention_h1(q, k, vT, *, B, Nq, Nk, dqk, dv, scale, key_mask,
     P = ops.softmax_bf16(S, Nk, scale, key_mask, row_keep)          # [B, Nq, pad8(Nk)]
     del S
     ldo = pad8(dv)
+    ldp = P.shape[-1]
+    tiles = B * ((Nq + 255) // 256) * ((dv + 255) // 256)
+    if B == 1 and tiles * 4 <= 74 and Nk >= 16384:
+        # few query rows, very long key axis (the multimodal encoder: 784 x 704 outputs over 52,097 keys = 12 tiles of
+        # the CTA-pair kernel): split the contraction over the key axis so that every SM pair gets a tile, and add the
+        # partial products with the partial-merge kernel (all maxima 0, all sums 1 / splits: a plain sum)
+        splits = min(32, 74 // tiles, Nk // 4096)
+        chunk = -(-Nk // splits) + 63 & ~63          # keys per split, a multiple of the 64-column K chunk
+        splits = -(-Nk // chunk)
+        Op = torch.empty((splits, 1, 1, Nq, dv), dtype=torch.float32, device=dev)
+        # the last split is shorter: zero-padded columns of P (ldp) and of V^T (nkp) beyond Nk contribute nothing, but the
+        # split must not read past the rows' pitch -> give it its own launch
+        full = splits - 1 if splits * chunk != Nk else splits
+        if full > 0:
+            ops.gemm(P, vT, M=Nq, N=dv, K=chunk, batch=full, strideA=chunk, strideB=chunk, lda=ldp, ldb=nkp,
+                     out_f32=Op, ldo32=dv, strideO32=Nq * dv)
+        if full < splits:
+            k0 = full * chunk
+            ops.gemm(P.view(-1)[k0:], vT.view(-1)[k0:], M=Nq, N=dv, K=Nk - k0, lda=ldp, ldb=nkp,
+                     out_f32=Op[full], ldo32=dv)
+        ml = torch.zeros((2, splits, 1, 1, Nq), dtype=torch.float32, device=dev)
+        ml[1].fill_(1.0 / splits)
+        return ops.attention_combine(Op, ml[0], ml[1])
     O = torch.empty((B, Nq, ldo), dtype=ops.dtype16(), device=dev)
-    ops.gemm(P, vT, M=Nq, N=dv, K=Nk, batch=B, strideA=Nq * P.shape[-1], strideB=dv * nkp, lda=P.shape[-1], ldb=nkp,
+    ops.gemm(P, vT, M=Nq, N=dv, K=Nk, batch=B, strideA=Nq * ldp, strideB=dv * nkp, lda=ldp, ldb=nkp,
              out_bf16=O, ldo16=ldo, strideO16=Nq * ldo)
     return O
 
