@@ -515,6 +515,20 @@ def run_gpu_arm(args):
                                 table.cpu()[None].expand(B, -1, -1)], dim=-1).contiguous().pin_memory()
         dense = measure(step_dense, host_dense, max(3, args.steps // 2), max(2, e2e_steps // 2))
 
+    # ---- multi-GPU records, outside the headline's timed region: the key-sharded encoder
+    #      cross-attend of BASELINE.json configs[4] and the batch-1 optical-flow composite; every rank takes part ----
+    mg = {}
+    if not args.no_multi_gpu_records:
+        try:
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import multi_gpu_records
+            mg["key_shard"] = multi_gpu_records.key_shard_record(world, rank, dev)
+            if world > 1:
+                mg["flow_b1"] = multi_gpu_records.flow_b1_record(world, rank, dev)
+        except Exception as ex:
+            mg["error"] = f"{type(ex).__name__}: {ex}"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -588,6 +602,7 @@ def run_gpu_arm(args):
                          "the host; the difference between the kernels' sum and ms_per_step is the graph's node-to-node "
                          "latency plus the clock recovery during the spin",
     }
+    result.update(mg)
     if dense is not None:
         result["dense_boundary"] = {
             "value": dense["value"], "ms_per_step": dense["ms_per_step"], "unit": "samples/s",
@@ -637,6 +652,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle check of sample 0 of the timed batch")
+    ap.add_argument("--no-multi-gpu-records", action="store_true",
+                    help="skip the key-sharded encoder sweep / batch-1 flow composite appended to the line")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the per-subsystem numbers of the language / flow / multimodal configs (N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 12
+#define PIO_ABI_VERSION 13
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -208,6 +208,10 @@ typedef struct pio_combine_args {
    * ignored.  The caller orders the ranks' writes before this launch (a symmetric-memory barrier on the stream). */
   const float* const* part_ptrs;
   int32_t fp16;                                                   /* 16-bit format of O: 0 = bf16, 1 = fp16 */
+  /* optional output: row_alive[b, i] = 1 if query row i of sample b was kept and saw at least one valid key on some
+   * part (else the row is wiped, transformer_primitives.py:168-175).  With it the key-sharded encoder needs no separate
+   * "does any rank hold a valid key" reduction: the partial sums carry that information. */
+  uint8_t* row_alive; int64_t stride_ra;
 } pio_combine_args;
 int pio_attention_combine(const pio_combine_args* a, void* stream);
 

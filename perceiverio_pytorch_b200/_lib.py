@@ -97,7 +97,8 @@ class CombineArgs(C.Structure):
                 ("parts", i32), ("B", i32), ("H", i32), ("Nq", i32), ("dv", i32),
                 ("row_keep", vp), ("stride_rk", i64),
                 ("O", vp), ("ldo", i64), ("strideO", i64),
-                ("O_out_part", vp), ("m_out", vp), ("l_out", vp), ("part_ptrs", vp), ("fp16", i32)]
+                ("O_out_part", vp), ("m_out", vp), ("l_out", vp), ("part_ptrs", vp), ("fp16", i32),
+                ("row_alive", vp), ("stride_ra", i64)]
 
 
 class LinearF32Args(C.Structure):
@@ -148,7 +149,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 12:
+        if lib.pio_abi_version() != 13:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -802,6 +802,10 @@ __global__ void __launch_bounds__(256) pio_combine_kernel(pio_combine_args a) {
       w[p] = (M != -INFINITY && w[p] != -INFINITY) ? __expf(w[p] - M) : 0.f;
       if (w[p] != 0.f) L += *lp_[p] * w[p];
     }
+  // whether this query row saw any valid key on any part (the reference wipes rows that did not, :168-175); the key
+  // mask is shared by the heads, so head 0 speaks for the row
+  if (a.row_alive && h == 0 && lane == 0)
+    a.row_alive[(long long)b * a.stride_ra + q] = (keep && M != -INFINITY && L > 0.f) ? 1 : 0;
   if (a.O_out_part) {  // merged, still un-normalised partial (referenced to M)
     if (lane == 0) {
       a.m_out[row] = M;
@@ -855,6 +859,8 @@ __global__ void __launch_bounds__(256) pio_combine_many_kernel(pio_combine_args 
       if (mp != -INFINITY) L += __ldg(a.l_part + p * sm + row) * __expf(mp - M);
     }
   }
+  if (a.row_alive && h == 0 && lane == 0)
+    a.row_alive[(long long)b * a.stride_ra + q] = (keep && M != -INFINITY && L > 0.f) ? 1 : 0;
   if (a.O_out_part) {
     if (lane == 0) {
       a.m_out[row] = M;

@@ -654,7 +654,8 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
         parts, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km,
                                             row_keep=None, partial=True,
                                             num_splits=shard.local_splits if shard.local_splits > 0 else None)
-        o = shard.combine(parts, row_keep=rk)
+        # the wipe of rows without any valid key (on any rank) comes out of the merged sums: no reduction of the mask
+        o, rk = shard.combine(parts, row_keep=rk, want_alive=True)
     x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk)
     y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, tail=tail)
     return y32.view(B, Nq, -1), y16

@@ -321,7 +321,8 @@ def decoder_attention(Q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, B: i
 def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp: Optional[torch.Tensor], *,
                       row_keep: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                       part_stride_O: int = 0, part_stride_ml: int = 0, shape=None,
-                      merged_out=None, normalised: bool = True, part_ptrs_dev: int = 0, device=None):
+                      merged_out=None, normalised: bool = True, part_ptrs_dev: int = 0, device=None,
+                      row_alive: Optional[torch.Tensor] = None):
     """Merge partials -> O bf16 [B, Nq, pad8(H*dv)] and/or a merged un-normalised partial.
 
     Op/mp/lp are [parts, B, H, Nq, dv] / [parts, B, H, Nq] tensors, or flat buffers with explicit part strides and
@@ -338,7 +339,8 @@ def attention_combine(Op: Optional[torch.Tensor], mp: Optional[torch.Tensor], lp
                          _ptr(row_keep), row_keep.stride(0) if row_keep is not None else 0,
                          _ptr(out), ldo, out.stride(0) if out is not None else 0,
                          _ptr(mo[0]), _ptr(mo[1]), _ptr(mo[2]), C.c_void_p(part_ptrs_dev) if part_ptrs_dev else None,
-                         1 if (out is not None and out.dtype == torch.float16) else 0)
+                         1 if (out is not None and out.dtype == torch.float16) else 0,
+                         _ptr(row_alive), row_alive.stride(0) if row_alive is not None else 0)
     _lib.check(_lib.load().pio_attention_combine(C.byref(a), _stream()), "pio_attention_combine")
     return out
 

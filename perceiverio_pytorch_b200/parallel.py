@@ -115,22 +115,30 @@ class KeyShard:
         return t, h
 
     # -- the exchange step ------------------------------------------------------------------------------------
-    def combine(self, parts, row_keep=None):
+    def combine(self, parts, row_keep=None, want_alive: bool = False):
         """parts = (O_part [S,B,H,Nq,dv], m [S,B,H,Nq], l [S,B,H,Nq]) from this rank's attention kernel.
-        Returns the normalised attention output bf16 [B, Nq, pad8(H*dv)], identical on every rank."""
+        Returns the normalised attention output bf16 [B, Nq, pad8(H*dv)], identical on every rank — and, with
+        want_alive, the u8 [B, Nq] flags of the rows that saw a valid key on SOME rank (what the reference's wipe of
+        fully masked rows needs; derived from the merged sums, so no extra reduction over the ranks)."""
         from . import ops
         Op, mp, lp = parts
         S, B, H, Nq, dv = Op.shape
         rows = B * H * Nq
         n = rows * (dv + 2)
+        alive = torch.empty((B, Nq), dtype=torch.uint8, device=Op.device) if want_alive else None
         if self.exchange == "peer" and self.world > 1:
             buf, hdl = self._peer_buffer(n, Op.device)
             o, m, l = packed_views(buf, rows, dv)
             # this rank's (merged) partial goes straight into its symmetric buffer
             ops.attention_combine(Op, mp, lp, normalised=False, merged_out=(o, m, l))
             hdl.barrier(channel=0)   # every rank's partial is complete and visible
-            return ops.attention_combine(None, None, None, row_keep=row_keep, shape=(self.world, B, H, Nq, dv),
-                                         part_ptrs_dev=int(hdl.buffer_ptrs_dev), device=Op.device)
+            out = ops.attention_combine(None, None, None, row_keep=row_keep, shape=(self.world, B, H, Nq, dv),
+                                        part_ptrs_dev=int(hdl.buffer_ptrs_dev), device=Op.device, row_alive=alive)
+            if torch.cuda.is_current_stream_capturing():
+                # a captured forward re-uses THIS buffer on every replay (the alternation above happens at capture time
+                # only), so the peers must have finished reading it before the next replay overwrites it
+                hdl.barrier(channel=1)
+            return (out, alive) if want_alive else out
         if S == 1:
             packed = pack_partial(Op[0], mp[0], lp[0])
         else:
@@ -138,9 +146,10 @@ class KeyShard:
             o, m, l = packed_views(packed, rows, dv)
             ops.attention_combine(Op, mp, lp, normalised=False, merged_out=(o, m, l))
         allp = self.gather_packed(packed)                      # [world, n]
-        return ops.attention_combine(allp, allp.view(-1)[rows * dv:], allp.view(-1)[rows * dv + rows:],
-                                     row_keep=row_keep, part_stride_O=n, part_stride_ml=n,
-                                     shape=(self.world, B, H, Nq, dv))
+        out = ops.attention_combine(allp, allp.view(-1)[rows * dv:], allp.view(-1)[rows * dv + rows:],
+                                    row_keep=row_keep, part_stride_O=n, part_stride_ml=n,
+                                    shape=(self.world, B, H, Nq, dv), row_alive=alive)
+        return (out, alive) if want_alive else out
 
 
 def shard_encoder_keys(encoder, group=None, local_splits: int = 0, exchange: str = "nccl"):

@@ -109,10 +109,11 @@ class PerceiverEncoder(nn.Module):
         row_keep = None
         if input_mask is not None:
             key_mask = input_mask.to(torch.bool)
-            any_key = key_mask.any(dim=1, keepdim=True)
-            if self.key_shard is not None:
-                any_key = self.key_shard.any_over_ranks(any_key)
-            row_keep = any_key.expand(latents.shape[0], latents.shape[1])
+            if self.key_shard is None:
+                any_key = key_mask.any(dim=1, keepdim=True)
+                row_keep = any_key.expand(latents.shape[0], latents.shape[1])
+            # key-sharded: whether a sample has a valid key on ANY rank comes out of the merged partial sums
+            # (pio_combine_args.row_alive), so the exchange stays ONE step
         use_cache = (self.cache_latents and self.key_shard is None and inputs.is_cuda
                      and not torch.cuda.is_current_stream_capturing())
         if use_cache:

@@ -223,6 +223,16 @@ def test_key_sharded_encoder_matches_unsharded_single_rank():
         sharded = enc(xc, enc.latents(xc), input_mask=mc)
     assert rel_err(sharded.cpu(), plain.cpu())[0] <= 5e-3
     assert rel_err(sharded.cpu(), ref)[0] <= BF16_TOL
+    # a sample without ANY valid key: the wipe comes out of the merged partial sums (pio_combine_args.row_alive), not
+    # out of a reduction of the mask over the ranks
+    params, inputs, meta, expected = load_golden("encoder_h1_sample_fully_masked")
+    m = _build_ours(meta)
+    m.load_state_dict(params, strict=True)
+    m = m.cuda()
+    parallel.shard_encoder_keys(m, group=None, local_splits=2)
+    with torch.inference_mode():
+        got = m(inputs["inputs"].cuda(), m.latents(inputs["inputs"].cuda()), input_mask=inputs["input_mask"].cuda())
+    assert rel_err(got.cpu(), expected)[0] <= BF16_TOL
 
 
 # ---------------------------------------------------------------------------------------------------------------
