@@ -15,7 +15,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libpio_b200.so")
-SOURCES = ["pio_host.cu", "pio_simt.cu", "pio_gemm.cu", "pio_gemm2.cu", "pio_flash.cu", "pio_flash2.cu", "pio_decode.cu"]
+SOURCES = ["pio_host.cu", "pio_simt.cu", "pio_gemm.cu", "pio_gemm2.cu", "pio_flash.cu", "pio_flash2.cu", "pio_decode.cu", "pio_flash_qt.cu"]
 HEADERS = ["pio_common.cuh", "pio_host.h", os.path.join("..", "..", "include", "pio_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

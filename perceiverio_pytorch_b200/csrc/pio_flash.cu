@@ -107,7 +107,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_full[i], 8 * kArrivalsPerWarp);
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
@@ -342,7 +342,7 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      mbar_arrive_warp(&p_full[j & 1]);
     }
     // ---- epilogue: total row sum = both halves' partial sums ----
     {
@@ -495,6 +495,10 @@ extern "C" int pio_attention_supported(int32_t dqk, int32_t dv) {
 extern "C" int pio_attention_key_tile(int32_t dqk, int32_t dv, int32_t same_kv) {
   using namespace pio;
   const int nqc = (dqk + 63) / 64, nvc = (dv + 63) / 64;
+  if (same_kv && dqk == dv && flash_qt_key_tile(dqk) > 0) {
+    static const int off = [] { const char* e = getenv("PIO_FLASH_QT"); return (e && e[0] == '0') ? 1 : 0; }();
+    if (!off) return flash_qt_key_tile(dqk);
+  }
   if (same_kv && flash_shape_ok(dqk, dv, true)) {
     switch (nqc) {
       case 1: return FlashCfg<1, 1, true>::BN;
@@ -548,6 +552,7 @@ extern "C" int pio_attention_fwd(const pio_attention_args* a, void* stream_) {
   }
   const bool same = (a->K == a->V) && (a->ldk == a->ldv) && (a->dqk == a->dv) && (a->strideK == a->strideV);
   const int nqc = (a->dqk + 63) / 64, nvc = (a->dv + 63) / 64;
+  if (flash_qt_eligible(a)) return launch_flash_qt(a, dev, stream);   // query tile in TMEM (192 < d <= 272, K == V)
   if (same && flash_shape_ok(a->dqk, a->dv, true)) {
     switch (nqc) {
       case 1: return launch_flash<1, 1, true>(a, dev, stream);

@@ -131,10 +131,10 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[2 * i], 128);
-      mbar_init(&p_full[2 * i + 1], 128);
+      mbar_init(&p_full[2 * i], 4 * kArrivalsPerWarp);        // the four softmax warps of tile i
+      mbar_init(&p_full[2 * i + 1], 4 * kArrivalsPerWarp);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&o_ready[i], 128);
+      mbar_init(&o_ready[i], 4 * kArrivalsPerWarp);
       mbar_init(&epi_done[i], 1);
     }
     fence_mbar_init();
@@ -475,7 +475,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if (c == BN / 64 - 1) {   // first half of the key tile is in TMEM
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&p_full[2 * x]);
+            mbar_arrive_warp(&p_full[2 * x]);
           }
         }
         float lsum;
@@ -488,7 +488,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         l += lsum;
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[2 * x + 1]);
+        mbar_arrive_warp(&p_full[2 * x + 1]);
         if (quarter == 0) F2T(204 + 100 * x + 10 * j);
       }
       // ---- epilogue of the item: O_x / l -> bf16 ----
@@ -523,7 +523,7 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&o_ready[x]);   // warp 3 hands the tile to TMA; this thread goes straight on to the next item
+        mbar_arrive_warp(&o_ready[x]);   // warp 3 hands the tile to TMA; this thread goes straight on to the next item
         if (quarter == 0) F2T(251 + 100 * x);
         continue;
       }

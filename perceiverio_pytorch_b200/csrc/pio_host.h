@@ -80,6 +80,11 @@ int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t str
 bool flash2_eligible(const pio_attention_args* a);
 int launch_flash2(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream);
 
+// Query-tile-in-TMEM variant of the one-tile kernel for the folded encoder cross-attends (pio_flash_qt.cu)
+int flash_qt_key_tile(int d);
+bool flash_qt_eligible(const pio_attention_args* a);
+int launch_flash_qt(const pio_attention_args* a, const DeviceInfo& dev, cudaStream_t stream);
+
 // cudaLaunchKernelEx with an optional cluster width and programmatic dependent launch.
 // PDL: a grid that leaves SMs idle (fewer CTAs than SMs: the batch-1 towers, 40 .. 128 CTAs per kernel, 7 kernels per
 // layer) is launched with programmatic stream serialization, so its CTAs are scheduled and run their prologue (barrier
