@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 13
+#define PIO_ABI_VERSION 14
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -107,11 +107,13 @@ typedef struct pio_gemm_args {
   int32_t kernel;       /* 0 = auto, 1 = single-CTA kernel (128 x tile_n tiles), 2 = CTA-pair kernel (cta_group::2,
                            256 x 256 tiles, TMA epilogue; needs K-major B, exactly one output and 16-byte aligned
                            output / residual rows) */
-  /* LayerNorm fused into the projections around it (CTA-pair kernel, batch == 1; SelfAttention :281 / :292):
+  /* LayerNorm fused into the projections around it (both kernels, batch == 1; SelfAttention :281 / :292):
    *  - producer side (the GEMM that writes the fp32 residual stream x): additionally writes out_bf16 = bf16(x), the
    *    UN-normalised rows, and stores the partial statistics (sum_n x[m,n], sum_n x[m,n]^2) of every 128-column
-   *    half-tile of the row into its own slot: row_stats_out[m][2 * (n / 256) + (n % 256) / 128] (plain stores: no
-   *    atomics, nothing to zero, bit-reproducible; the caller passes row_stats_parts = 2 * ceil(N / 256));
+   *    half-tile of the row into its own slot: row_stats_out[m][2 * (n / T) + (n % T) / (T / 2)], T = the kernel's tile
+   *    width (256 in the CTA-pair kernel, 64 .. 256 in the single-CTA kernel); slots the chosen tile width does not use
+   *    are zeroed (plain stores: no atomics, nothing to zero beforehand, bit-reproducible).  The caller sizes the buffer
+   *    with pio_gemm_stats_parts(M, N) (or, with a forced tile width, 2 * ceil(N / T));
    *  - consumer side (the GEMM that multiplies LN(x) by W): A is that bf16(x), B is W' = W * diag(gamma), and the
    *    epilogue applies the normalisation per output row:
    *        v = rstd_m * (alpha * acc - mean_m * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k],
@@ -130,6 +132,10 @@ typedef struct pio_gemm_args {
   int32_t fp16;               /* 16-bit format of A, B and out_bf16: 0 = bf16, 1 = fp16 */
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
+/* Number of statistics slots per row that a fused-LayerNorm producer GEMM of shape M x N writes with the automatic
+ * kernel / tile choice on the current device (what to pass as row_stats_parts; larger values are allowed, the unused
+ * slots are zeroed — but the consumer reads every slot, so do not oversize). */
+int pio_gemm_stats_parts(int32_t M, int32_t N);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Row softmax for the materialised attention path: P[b, i, :] = softmax(scale * S[b, i, :]) with masked keys

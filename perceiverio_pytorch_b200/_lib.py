@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
     "pio_linear_f32", "pio_layernorm_concat_bf16", "pio_hash_words",
-    "pio_decoder_attention_fwd", "pio_decoder_attention_supported",
+    "pio_decoder_attention_fwd", "pio_decoder_attention_supported", "pio_gemm_stats_parts",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -139,6 +139,8 @@ def load(build_if_missing: bool = True):
             fn.argtypes = [C.POINTER(argt), C.c_void_p]
         lib.pio_hash_words.restype = C.c_int
         lib.pio_hash_words.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
+        lib.pio_gemm_stats_parts.restype = C.c_int
+        lib.pio_gemm_stats_parts.argtypes = [C.c_int32, C.c_int32]
         lib.pio_decoder_attention_supported.restype = C.c_int
         lib.pio_decoder_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_supported.restype = C.c_int
@@ -149,7 +151,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 13:
+        if lib.pio_abi_version() != 14:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

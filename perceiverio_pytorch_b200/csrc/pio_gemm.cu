@@ -32,6 +32,13 @@ struct GemmEpilogue {
   long long ldo32, strideO32;
   __nv_bfloat16* out_bf16;
   long long ldo16, strideO16;
+  // LayerNorm folded into the projections around it (pio_gemm_args; batch == 1): producer side ...
+  float* row_stats_out;          // [M][stats_parts][2]: this row's (sum, sum of squares) over one half-tile of columns
+  int stats_parts;
+  // ... consumer side
+  const float* row_stats_in;     // [M][stats_parts][2] of the A operand's rows
+  const float* ln_colsum;        // [N]
+  float ln_inv_c, ln_eps;
 };
 
 template <int BN>
@@ -220,6 +227,25 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + half * HALF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const float row_bias = (ep.bias_mode == 2 && row_ok) ? __ldg(ep.bias + row) : 0.0f;
+      // fused LayerNorm, consumer side: this row's mean / rstd from the partial statistics its producer left (added in a
+      // fixed order: bit-reproducible)
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ep.row_stats_in != nullptr && row_ok) {
+        const float2* sp = reinterpret_cast<const float2*>(ep.row_stats_in) + (long long)row * ep.stats_parts;
+        float s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < ep.stats_parts; ++j) {
+          const float2 st = __ldg(sp + j);
+          s1 += st.x;
+          s2 += st.y;
+        }
+        ln_mean = s1 * ep.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(s2 * ep.ln_inv_c - ln_mean * ln_mean, 0.f) + ep.ln_eps);
+      }
+      // producer side: partial statistics of the final rows, in the transposed mapping (lane -> 4 columns of rows
+      // i * 4 + lane / 8), accumulated over the warp's chunks and reduced over the 8 lanes of a row at the end
+      float st_sum[8], st_sq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_sum[i] = st_sq[i] = 0.f;
       float* o32_z = ep.out_f32 ? ep.out_f32 + z * ep.strideO32 : nullptr;
       __nv_bfloat16* o16_z = ep.out_bf16 ? ep.out_bf16 + z * ep.strideO16 : nullptr;
 #pragma unroll 1
@@ -246,6 +272,15 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ep.alpha, row_bias);
+        if (ep.row_stats_in != nullptr) {
+          // v = rstd * (acc - mean * colsum[n])   (the bias, which already holds W.beta, is added below)
+          const float nm = -ln_mean;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float cs = (col0 + j < ep.N) ? __ldg(ep.ln_colsum + col0 + j) : 0.f;
+            v[j] = ln_rstd * fmaf(nm, cs, v[j]);
+          }
+        }
         if (ep.bias_mode == 1) {
           if (full && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15u) == 0)) {
 #pragma unroll
@@ -313,6 +348,13 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                   if (gcol + 3 < ep.N) w.w += __ldg(rp + 3);
                 }
               }
+              if (ep.row_stats_out != nullptr) {
+                st_sum[i] += w.x;
+                st_sq[i] = fmaf(w.x, w.x, st_sq[i]);
+                if (gcol + 1 < ep.N) { st_sum[i] += w.y; st_sq[i] = fmaf(w.y, w.y, st_sq[i]); }
+                if (gcol + 2 < ep.N) { st_sum[i] += w.z; st_sq[i] = fmaf(w.z, w.z, st_sq[i]); }
+                if (gcol + 3 < ep.N) { st_sum[i] += w.w; st_sq[i] = fmaf(w.w, w.w, st_sq[i]); }
+              }
               if (o32_z) {
                 float* op = o32_z + static_cast<long long>(grow) * ep.ldo32 + gcol;
                 if (quad && vec32) {
@@ -339,6 +381,25 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
           __syncwarp();
+        }
+      }
+      if (ep.row_stats_out != nullptr) {
+        // one slot per (row, half-tile of columns): plain stores, no atomics; the warps of the first column tile also zero
+        // the slots beyond the ones this tile width produces (the caller sizes the buffer for the narrowest tiles)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            st_sum[i] += __shfl_xor_sync(0xffffffffu, st_sum[i], o);
+            st_sq[i] += __shfl_xor_sync(0xffffffffu, st_sq[i], o);
+          }
+          const int grow = row_base + i * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && grow < ep.M) {
+            float2* slots = reinterpret_cast<float2*>(ep.row_stats_out) + (long long)grow * ep.stats_parts;
+            slots[nt * 2 + half] = make_float2(st_sum[i], st_sq[i]);
+            if (nt == 0 && half == 0)
+              for (int s = 2 * ep.tiles_n; s < ep.stats_parts; ++s) slots[s] = make_float2(0.f, 0.f);
+          }
         }
       }
       tc_fence_before();
@@ -395,6 +456,15 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
   ep.residual = a->residual; ep.ldr = a->ldr; ep.strideR = a->strideR;
   ep.out_f32 = a->out_f32; ep.ldo32 = a->ldo32; ep.strideO32 = a->strideO32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); ep.ldo16 = a->ldo16; ep.strideO16 = a->strideO16;
+  ep.row_stats_out = a->row_stats_out;
+  ep.row_stats_in = a->row_stats_in;
+  ep.stats_parts = a->row_stats_parts > 0 ? a->row_stats_parts : 1;
+  ep.ln_colsum = a->ln_colsum;
+  ep.ln_inv_c = a->ln_channels > 0 ? 1.0f / (float)a->ln_channels : 0.f;
+  ep.ln_eps = a->ln_eps;
+  if (a->row_stats_out && ep.stats_parts < 2 * ep.tiles_n)
+    return fail(PIO_ERR_INVALID_ARGUMENT, "pio_gemm_bf16: row_stats_out needs row_stats_parts >= %d (got %d)", 2 * ep.tiles_n,
+                a->row_stats_parts);
 
   static PerDeviceOnce once;
   const cudaError_t attr_err = once.run(dev.device, [] {
@@ -419,6 +489,34 @@ static int launch_gemm(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream
 }
 
 }  // namespace pio
+
+namespace pio {
+// Tile selection of the automatic dispatch, shared by pio_gemm_bf16 and pio_gemm_stats_parts.
+static bool auto_wants_pair(long long M, long long N, long long batch, int sm_count) {
+  const long long pair_tiles = ((M + 255) / 256) * ((N + 255) / 256) * batch;
+  return pair_tiles * 3 >= (long long)(sm_count / 2);
+}
+static int auto_tile_n(long long M, long long N, long long batch, int sm_count) {
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  // small problems are bound by how many CTAs stream the weight matrix concurrently, not by tile efficiency: shrink
+  // the tile until at least half of the SMs have one (narrower tiles also get deeper operand rings)
+  const long long tiles_m = (M + 127) / 128 * batch;
+  while (bn > 64 && tiles_m * ((N + bn - 1) / bn) * 2 < sm_count) bn >>= 1;
+  return bn;
+}
+}  // namespace pio
+
+// Number of (sum, sum of squares) slots per row that the fused-LayerNorm producer GEMM of this shape writes with the
+// automatic kernel / tile choice (pio_gemm_args.row_stats_parts): two per column tile.
+extern "C" int pio_gemm_stats_parts(int32_t M, int32_t N) {
+  using namespace pio;
+  DeviceInfo dev;
+  int sm = 148;
+  if (get_device_info(&dev) == PIO_OK && dev.sm_count > 0) sm = dev.sm_count;
+  if (sm % 2 == 0 && auto_wants_pair(M, N, 1, sm)) return 2 * ((N + 255) / 256);
+  const int bn = auto_tile_n(M, N, 1, sm);
+  return 2 * ((N + bn - 1) / bn);
+}
 
 extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   using namespace pio;
@@ -448,22 +546,21 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
     if (a->kernel == 2 && !elig)
       return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the CTA-pair kernel needs K-major B, exactly one output and "
                                        "16-byte aligned output / residual rows");
-    const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
-    const bool want = a->kernel == 2 || a->row_stats_out || a->row_stats_in ||
-                      (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && pair_tiles * 3 >= (long long)(dev.sm_count / 2));
+    const bool want = a->kernel == 2 ||
+                      (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && auto_wants_pair(a->M, a->N, a->batch, dev.sm_count));
     if (elig && want) return launch_gemm2(a, dev, stream);
-    if (a->row_stats_out || a->row_stats_in)
-      return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the fused-LayerNorm epilogues exist in the CTA-pair kernel only "
-                                       "(batch 1, aligned outputs, enough 256 x 256 tiles)");
+    // the single-CTA kernel has the fused-LayerNorm epilogues too (small latent arrays), with these limits:
+    if (a->row_stats_out || a->row_stats_in) {
+      if (a->batch != 1 || a->b_mn_major)
+        return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: the fused-LayerNorm epilogues need batch == 1 and a K-major B");
+      if (a->row_stats_out && !(a->out_f32 || a->residual))
+        return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: row_stats_out belongs to the GEMM that writes the fp32 residual stream");
+      if (a->row_stats_in && (a->out_f32 || a->residual || !a->ln_colsum || a->ln_channels <= 0))
+        return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: row_stats_in needs a 16-bit-only output, ln_colsum and ln_channels");
+    }
   }
   int bn = a->tile_n;
-  if (bn == 0) {
-    bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
-    // small problems are bound by how many CTAs stream the weight matrix concurrently, not by tile efficiency: shrink
-    // the tile until at least half of the SMs have one (narrower tiles also get deeper operand rings)
-    const long long tiles_m = ((long long)a->M + 127) / 128 * a->batch;
-    while (bn > 64 && tiles_m * ((a->N + bn - 1) / bn) * 2 < dev.sm_count) bn >>= 1;
-  }
+  if (bn == 0) bn = auto_tile_n(a->M, a->N, a->batch, dev.sm_count);
   // cluster width along M: multicast pays when there are at least two M tiles to pair up
   int cl = a->cluster_m;
   if (cl == 0) cl = (a->M > 128) ? 2 : 1;

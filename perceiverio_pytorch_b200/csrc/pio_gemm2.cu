@@ -439,8 +439,10 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (KIND == G2_F32 && p.row_stats_out != nullptr && row < p.M) {
         // one slot per (row, 128-column half-tile): plain stores, no atomics, nothing to zero beforehand
-        reinterpret_cast<float2*>(p.row_stats_out)[(long long)row * p.stats_parts + nt * 2 + half] =
-            make_float2(st_sum, st_sq);
+        float2* slots = reinterpret_cast<float2*>(p.row_stats_out) + (long long)row * p.stats_parts;
+        slots[nt * 2 + half] = make_float2(st_sum, st_sq);
+        if (nt == 0 && half == 0)     // slots beyond this tile width's count (the caller sizes the buffer for 64-column tiles)
+          for (int s = 2 * p.tiles_n; s < p.stats_parts; ++s) slots[s] = make_float2(0.f, 0.f);
       }
     }
     if (lane == 0) bulk_wait_read<0>();   // staging slots must outlive the stores that read them
@@ -524,8 +526,8 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.ld_raw = a->ldo16;
   p.row_stats_in = (KIND == G2_BF16) ? a->row_stats_in : nullptr;
   p.stats_parts = a->row_stats_parts > 0 ? a->row_stats_parts : 1;
-  if (p.row_stats_out != nullptr && p.stats_parts != 2 * p.tiles_n)
-    return fail(PIO_ERR_INVALID_ARGUMENT, "pio_gemm_bf16: row_stats_out needs row_stats_parts == 2 * ceil(N / 256) = %d (got %d)",
+  if (p.row_stats_out != nullptr && p.stats_parts < 2 * p.tiles_n)
+    return fail(PIO_ERR_INVALID_ARGUMENT, "pio_gemm_bf16: row_stats_out needs row_stats_parts >= 2 * ceil(N / 256) = %d (got %d)",
                 2 * p.tiles_n, a->row_stats_parts);
   p.ln_colsum = a->ln_colsum;
   p.ln_inv_c = a->ln_channels > 0 ? 1.0f / (float)a->ln_channels : 0.f;

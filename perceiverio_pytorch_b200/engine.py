@@ -65,11 +65,12 @@ def fast() -> bool:
 
 
 # Tower LayerNorms folded into the projections around them when the latent array has at least
-# this many rows (the fused epilogues live in the CTA-pair GEMM kernel).  Below it the LayerNorm kernels cost little, and
-# the batch-1 flow tower (2048 rows) measured 9.2e-3 .. 9.5e-3 (run to run: the row statistics are accumulated with
-# atomics) against the 1e-2 bound with the fusion, 8.2e-3 without, so it stays on the exact two-pass LayerNorm.
+# this many rows.  Both GEMM kernels carry the fused epilogues and the row statistics are deterministic, so the threshold
+# is a performance choice only: for the batch-1 towers (256 .. 2048 rows) the fusion removes two of the seven launches of
+# a layer but measured no faster (language 2.46 vs 2.51 ms, flow 3.81 vs 3.76, multimodal 1.30 vs 1.24 per forward: the
+# LayerNorm kernels cost ~3 us there and the GEMM epilogues grow by as much), so they keep the two-pass LayerNorm.
 FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
-FUSE_LN_MIN_ROWS = 4096
+FUSE_LN_MIN_ROWS = int(os.environ.get("PIO_FUSE_LN_MIN_ROWS", "4096"))
 FUSE_LN_MAX_OFFSET = 1.0     # max |mean| / std of a residual-stream row the fused form accepts (perceiver.PerceiverEncoder)
 
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"

@@ -43,15 +43,16 @@ def empty_f32_rows(m: int, n: int, device) -> torch.Tensor:
     return t if n4 == n else t[:, :n]
 
 
-def stats_parts(n: int) -> int:
-    """Partial (sum, sum of squares) slots per row that a fused-LayerNorm producer GEMM with N = n output columns
-    writes: one per 128-column half of each 256-column tile (pio_gemm_args.row_stats_parts)."""
-    return 2 * ((n + 255) // 256)
+def stats_parts(m: int, n: int) -> int:
+    """Partial (sum, sum of squares) slots per row that the fused-LayerNorm producer GEMM of shape m x n writes with the
+    automatic kernel / tile choice: two per column tile (pio_gemm_stats_parts)."""
+    return int(_lib.load().pio_gemm_stats_parts(m, n))
 
 
-def empty_row_stats(m: int, n: int, device) -> torch.Tensor:
-    """[m, stats_parts(n), 2] fp32 buffer for pio_gemm_args.row_stats_out (every slot is written: no zeroing)."""
-    return torch.empty((m, stats_parts(n), 2), dtype=torch.float32, device=device)
+def empty_row_stats(m: int, n: int, device, parts: int = 0) -> torch.Tensor:
+    """[m, parts, 2] fp32 buffer for pio_gemm_args.row_stats_out (every slot is written: no zeroing); parts defaults to
+    stats_parts(m, n) — pass 2 * ceil(n / T) when the GEMM is forced to a tile width T."""
+    return torch.empty((m, parts or stats_parts(m, n), 2), dtype=torch.float32, device=device)
 
 
 def _ptr(t: Optional[torch.Tensor]):

@@ -157,7 +157,7 @@ class PerceiverEncoder(nn.Module):
         # Latent tower with the LayerNorms folded into the projections: every residual-stream
         # state travels as (fp32 rows, their raw bf16 copy, per-row sum / sum of squares); no LayerNorm kernel runs.
         M = B * N
-        stats = torch.empty((2 * len(layers) + 1, M, ops.stats_parts(C), 2), dtype=torch.float32, device=latents.device)
+        stats = torch.empty((2 * len(layers) + 1, M, ops.stats_parts(M, C), 2), dtype=torch.float32, device=latents.device)
         z, zb = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
                                                     shard=self.key_shard, want_bf16_out=True, stats_out=stats[0])
         x = z.view(M, C)

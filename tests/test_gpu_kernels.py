@@ -231,7 +231,7 @@ def test_gemm_fused_layernorm_epilogues():
     ops.gemm(h, w2, M=M, N=C, K=C, bias=b2, residual=res, ldr=C, out_f32=x, ldo32=C, out_bf16=xb, ldo16=C,
              row_stats_out=st_again, reverse_tiles=True)
     assert torch.equal(st, st_again)      # plain stores per half-tile: bit-reproducible, whatever the tile order
-    assert st.shape == (M, 2 * (C // 256), 2)
+    assert st.shape == (M, ops.stats_parts(M, C), 2) and st.shape[1] == 2 * (C // 256)
     parts = st
     st = st.sum(1)
     x_ref = h.float() @ w2.float().t() + b2 + res
@@ -254,6 +254,42 @@ def test_gemm_fused_layernorm_epilogues():
     with pytest.raises(RuntimeError, match="fused-LayerNorm"):
         ops.gemm(xb, wp, M=M // 2, N=N, K=C, batch=2, strideA=(M // 2) * C, strideB=0, bias=bias, out_bf16=y, ldo16=N,
                  strideO16=(M // 2) * N, row_stats_in=parts, ln_colsum=colsum, ln_channels=C)
+
+
+@pytest.mark.parametrize("M,C,N,kernel", [(256, 1280, 1536, 1), (784, 512, 512, 1), (2048, 512, 1536, 0), (300, 320, 200, 1)])
+def test_gemm_fused_layernorm_epilogues_small_latent_arrays(M, C, N, kernel):
+    """The same producer / consumer epilogues in the single-CTA kernel (the batch-1 towers: 256 .. 2048 latent rows),
+    whatever tile width the dispatch picks."""
+    from perceiverio_pytorch_b200 import ops
+    torch.manual_seed(M + C)
+    dev = "cuda"
+    h = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    w2 = (torch.randn(C, C, device=dev) / C ** 0.5).to(torch.bfloat16)
+    b2 = torch.randn(C, device=dev)
+    res = torch.randn(M, C, device=dev) * 2 + 0.3
+    x = torch.empty(M, C, device=dev)
+    xb = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+    # kernel = 1 forces the single-CTA kernel (tile width auto: >= 64 columns); two extra slots check the zero fill
+    parts = (ops.stats_parts(M, C) if kernel == 0 else 2 * ((C + 63) // 64)) + 2
+    st = ops.empty_row_stats(M, C, dev, parts=parts).fill_(float("nan"))
+    ops.gemm(h, w2, M=M, N=C, K=C, bias=b2, residual=res, ldr=C, out_f32=x, ldo32=C, out_bf16=xb, ldo16=C,
+             row_stats_out=st, kernel=kernel)
+    x_ref = h.float() @ w2.float().t() + b2 + res
+    assert _rel(x, x_ref) < 2e-3
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert torch.isfinite(st).all() and float(st[:, -2:].abs().max()) == 0.0
+    tot = st.sum(1)
+    assert _rel(tot[:, 0], x.sum(1)) < 1e-4 and _rel(tot[:, 1], (x * x).sum(1)) < 1e-4
+    gamma, beta = 1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)
+    w = torch.randn(N, C, device=dev) / C ** 0.5
+    b = torch.randn(N, device=dev)
+    wp = (w * gamma[None, :]).to(torch.bfloat16)
+    colsum = wp.double().sum(1).float()
+    y = torch.empty(M, ops.pad8(N), dtype=torch.bfloat16, device=dev)
+    ops.gemm(xb, wp, M=M, N=N, K=C, bias=b + w @ beta, act=1, out_bf16=y, ldo16=y.stride(0), row_stats_in=st,
+             ln_colsum=colsum, ln_channels=C, ln_eps=1e-5, kernel=kernel)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b)
+    assert _rel(y[:, :N].float(), ref) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,K,batch", [(1000, 520, 200, 1), (2048, 1024, 512, 1), (300, 256, 64, 3)])
