@@ -118,8 +118,9 @@ class PreparedAttention:
         # constant-one column of the query rows, which needs a free pad column: Cq % 8 != 0) and the kernel's output is
         # the block's output.  Wiped rows come out as bf, exactly as in the reference (P row = 0).
         self.qfold = None
-        if (allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck and self.Cq % 8 != 0
-                and ops.decoder_attention_supported(self.Cq + 1, self.O)):
+        pair_ok = self.Cq % 8 != 0 and ops.decoder_attention_supported(self.Cq + 1, self.O)   # pio_decode_kernel
+        wide_ok = self.Cq <= self.QK and self.O <= self.V    # explicit-S form: never more work than the unfolded block
+        if allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck and (pair_ok or wide_ok):
             wq64, wk64, wv64, wf64 = (t.double() for t in (wq, wk, wv, wf))
             koff = pad8(self.Cq + 1)
             n_ext = koff + self.O
@@ -131,7 +132,8 @@ class PreparedAttention:
             b_ext[self.Cq] = bq.double() @ bk.double()
             w_ext[koff:] = wf64 @ wv64
             b_ext[koff:] = wf64 @ bv.double()
-            self.qfold = dict(w=_bf16_weight(w_ext.float()), b=b_ext.float().contiguous(), koff=koff, n=n_ext)
+            self.qfold = dict(w=_bf16_weight(w_ext.float()), b=b_ext.float().contiguous(), koff=koff, n=n_ext,
+                              pair_ok=pair_ok)
         if self.folded:
             # S = (LN(q) Wq^T + bq) Wk . LN(x)^T  (the q.bk term is constant per row and cancels in the softmax)
             # out = (P . LN(x)) (Wf Wv)^T + (Wf bv + bf)          (rows of P sum to one)
@@ -552,7 +554,49 @@ QFOLD_MIN_QUERIES = 1024
 
 
 def use_query_fold(pa: PreparedAttention, Nq: int, Nk: int) -> bool:
-    return pa.qfold is not None and Nq >= QFOLD_MIN_QUERIES and Nq >= 2 * Nk
+    return pa.qfold is not None and pa.qfold["pair_ok"] and Nq >= QFOLD_MIN_QUERIES and Nq >= 2 * Nk
+
+
+def use_query_fold_explicit(pa: PreparedAttention, Nq: int, Nk: int) -> bool:
+    """The same fold for head sizes the decoder kernel does not cover (the classification decoder: 1024 channels), on
+    the explicit S / P path: proj_q and final disappear, S = LN(q) K'^T and out = P V' + b_f (+ residual) come straight
+    out of the two attention GEMMs."""
+    return pa.qfold is not None and not pa.qfold["pair_ok"] and not pa.folded and Nq >= Nk >= 64
+
+
+def cross_attention_query_fold_explicit(pa: PreparedAttention, q_src, ln_q, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep,
+                                        residual):
+    """q_src fp32 [(1|B)*Nq, Cq] (the un-normalised queries), kvn 16-bit [B*Nk, pad8(Ck)].  Returns the fp32 block output
+    [B*Nq, O] before the MLP."""
+    f = pa.qfold
+    dev = kvn.device
+    ldq = f["koff"]                                  # pad8(Cq + 1): room for the constant-one column that carries b'
+    qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias, eps=ln_q.eps, ld=ldq)
+    qn[:, pa.Cq] = 1.0
+    koff, ldkv = f["koff"], kvn.shape[-1]
+    _, kext = ops.linear(kvn, pa.Ck, f["w"][:koff], koff, f["b"][:koff])          # [B*Nk, koff]: K' | b' | 0..
+    nkp = pad8(Nk)
+    vT = torch.empty((B, pa.O, nkp), dtype=ops.dtype16(), device=dev)            # V'^T, operands of its projection swapped
+    if nkp != Nk:
+        vT[:, :, Nk:].zero_()
+    ops.gemm(f["w"][koff:], kvn, M=pa.O, N=Nk, K=pa.Ck, batch=B, strideA=0, strideB=Nk * ldkv, lda=f["w"].stride(0),
+             ldb=ldkv, bias=f["b"][koff:], bias_mode=2, out_bf16=vT, ldo16=nkp, strideO16=pa.O * nkp)
+    lds = (Nk + 3) // 4 * 4
+    S = torch.empty((B, Nq, lds), dtype=torch.float32, device=dev)
+    ops.gemm(qn, kext, M=Nq, N=Nk, K=pa.Cq + 1, batch=B, strideA=0 if q_bcast else Nq * ldq, strideB=Nk * koff, lda=ldq,
+             ldb=koff, out_f32=S, ldo32=lds, strideO32=Nq * lds)
+    P = ops.softmax_bf16(S, Nk, pa.scale, key_mask, row_keep)
+    del S
+    ldp = P.shape[-1]
+    x = ops.empty_f32_rows(B * Nq, pa.O, dev)
+    ldx = x.stride(0)
+    if residual is not None:
+        assert residual.stride(2) == 1
+    ops.gemm(P, vT, M=Nq, N=pa.O, K=Nk, batch=B, strideA=Nq * ldp, strideB=pa.O * nkp, lda=ldp, ldb=nkp, bias=pa.bf,
+             residual=residual, ldr=residual.stride(1) if residual is not None else 0,
+             strideR=(residual.stride(0) if B > 1 else 0) if residual is not None else 0,
+             out_f32=x, ldo32=ldx, strideO32=Nq * ldx)
+    return x
 
 
 def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep, residual,
@@ -633,12 +677,17 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
     q_src = inputs_q[0] if q_bcast else (inputs_q if inputs_q.is_contiguous() else inputs_q.contiguous()).view(B * Nq, Cq)
     if q_src.stride(-1) != 1:
         q_src = q_src.contiguous()
-    qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias)
     km, rk = _as_u8(key_mask), _as_u8(row_keep)
     if use_query_residual:
         res = inputs_q if inputs_q.stride(2) == 1 else inputs_q.contiguous()
     else:
         res = None
+    if general is None and shard is None and use_query_fold_explicit(pa, Nq, Nk):
+        x = cross_attention_query_fold_explicit(pa, q_src, ln_q, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km,
+                                                row_keep=rk, residual=res)
+        y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, tail=tail)
+        return y32.view(B, Nq, -1), y16
+    qn = ops.layernorm_bf16(q_src, ln_q.weight, ln_q.bias)
     if general is None and shard is None and use_query_fold(pa, Nq, Nk):
         x, xn = cross_attention_query_fold(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
                                            residual=res, ln=(ln2.weight, ln2.bias, ln2.eps))

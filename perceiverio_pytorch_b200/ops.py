@@ -101,15 +101,17 @@ def _device_guard(fn):
 @_device_guard
 def layernorm_bf16(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
                    normalize: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
-                   split: int = 0) -> torch.Tensor:
-    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [rows, pad8(C)].
+                   split: int = 0, ld: int = 0) -> torch.Tensor:
+    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [rows, pad8(C)] (or [rows, ld], ld >= pad8(C) a
+    multiple of 8: columns C .. ld-1 are zeros).
     split = 1 / 2 (validation precision): bf16 [rows, 3 * pad8(C)] laid out [hi | lo | hi] / [hi | hi | lo]."""
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.stride(-1) == 1
     c = x.shape[-1]
     x2 = x.reshape(-1, c) if x.dim() != 2 else x
     rows = x2.shape[0]
-    ldy = pad8(c) * (3 if split else 1)
+    assert not (ld and split) and (ld == 0 or (ld % 8 == 0 and ld >= pad8(c)))
+    ldy = ld if ld else pad8(c) * (3 if split else 1)
     if out is None:
         out = torch.empty((rows, ldy), dtype=BF16 if split else dtype16(), device=x.device)
     assert out.dtype == (BF16 if split else dtype16()) and out.shape[-1] == ldy and out.is_contiguous()

@@ -568,3 +568,25 @@ def test_query_fold_decoder_kernel_on_reference_goldens(name, mode, monkeypatch)
     assert calls, "the decoder kernel was not used"
     emax, el2 = rel_err(got.float().cpu(), expected)
     assert emax <= (BF16_TOL if mode == "bf16" else 2e-3), (name, mode, emax, el2)
+
+
+@pytest.mark.parametrize("name", ["decoder_small", "decoder_h1_querymask"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_query_fold_on_the_explicit_path_on_reference_goldens(name, mode, monkeypatch):
+    """The same fold without the decoder kernel (engine.cross_attention_query_fold_explicit: S = LN(q) K'^T, softmax,
+    out = P V' + b_f + residual — what the 1024-channel classification decoder takes), forced onto the fixtures."""
+    from perceiverio_pytorch_b200 import engine
+    params, inputs, meta, expected = load_golden(name)
+    m = _build_ours(meta)
+    m.load_state_dict(params, strict=True)
+    m = m.cuda()
+    calls = []
+    real = engine.cross_attention_query_fold_explicit
+    monkeypatch.setattr(engine, "cross_attention_query_fold_explicit", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    monkeypatch.setattr(engine, "use_query_fold", lambda pa, nq, nk: False)
+    monkeypatch.setattr(engine, "use_query_fold_explicit", lambda pa, nq, nk: pa.qfold is not None)
+    with engine.precision_scope(mode):
+        got = _run_ours(m, inputs, meta)
+    assert calls, "the explicit query-fold path was not used"
+    emax, el2 = rel_err(got.float().cpu(), expected)
+    assert emax <= (BF16_TOL if mode == "bf16" else 2e-3), (name, mode, emax, el2)
