@@ -272,7 +272,17 @@ def graph_gap_profile(runner, inputs, replays=3, between=None):
             k = n.split("(")[0].replace("void ", "").replace("pio::", "")
             by[k] = by.get(k, 0.0) + (e - s)
         top = sorted(by.items(), key=lambda kv: -kv[1])[:12]
+        # kernels launched with programmatic dependent launch start early and wait for their predecessor, so their own
+        # durations overlap; what a kernel adds to the dependency chain is the time from its predecessor's end to its end
+        chain = {}
+        by_end = sorted(evs, key=lambda t: t[1])
+        for i, (s, e, n) in enumerate(by_end):
+            k = n.split("(")[0].replace("void ", "").replace("pio::", "")
+            prev_end = by_end[i - 1][1] if i else s
+            chain[k] = chain.get(k, 0.0) + (e - max(s, prev_end))
+        chain_top = sorted(chain.items(), key=lambda kv: -kv[1])[:12]
         return {"replays": replays, "kernels_per_step": len(evs) / replays,
+                "by_kernel_chain_ms_per_step": {k: round(v / replays / 1e3, 4) for k, v in chain_top},
                 "span_ms_per_step": (evs[-1][1] - evs[0][0]) / replays / 1e3,
                 "kernel_ms_per_step": busy / replays / 1e3, "gap_ms_per_step": sum(inner) / replays / 1e3,
                 "gap_between_replays_ms_per_step": (sum(gaps) - sum(inner)) / replays / 1e3,

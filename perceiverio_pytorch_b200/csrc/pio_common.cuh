@@ -109,6 +109,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // (launch_dependents) and then waits for the previous grid's results before touching global memory (wait).
 // Both are no-ops unless the launch carries the programmatic-serialization attribute (pio_host.h: launch_kernel).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");

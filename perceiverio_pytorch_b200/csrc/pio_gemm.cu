@@ -41,6 +41,25 @@ struct GemmEpilogue {
   float ln_inv_c, ln_eps;
 };
 
+// Developer aid (compiled out unless -DPIO_GEMM_TRACE): CTA 0 records (tag, clock64, globaltimer) at the pipeline's
+// hand-off points of its latest launch; pio_debug_gemm_trace() copies them out (tools/trace_gemm.py).
+#ifdef PIO_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[4 * 128 * 3];
+#define GT(slot, tag)                                                                                         \
+  do {                                                                                                        \
+    if (blockIdx.x == 0 && lane == 0 && gtn < 128) {                                                          \
+      unsigned long long gt_ = 0;                                                                             \
+      if ((tag) < 10 || (tag) >= 400) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                 \
+      g_gemm_trace[((slot) * 128 + gtn) * 3] = (unsigned long long)(tag);                                     \
+      g_gemm_trace[((slot) * 128 + gtn) * 3 + 1] = (unsigned long long)clock64();                             \
+      g_gemm_trace[((slot) * 128 + gtn) * 3 + 2] = gt_;                                                       \
+      ++gtn;                                                                                                  \
+    }                                                                                                         \
+  } while (0)
+#else
+#define GT(slot, tag)
+#endif
+
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128;
@@ -74,6 +93,10 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef PIO_GEMM_TRACE
+  int gtn = 0;
+  if (warp == 0) GT(0, 1);
+#endif
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_gemm_kernel: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
@@ -111,25 +134,38 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // barriers / TMEM are set up; operands and residuals of the previous kernel are read from here on
+  if (warp == 0) GT(0, 2);
+  // barriers / TMEM are set up: let the next grid start its prologue; every role that touches global memory waits for
+  // the previous grid (pdl_wait) as late as it can, after the index arithmetic of its first tile
+  pdl_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int nt = t % ep.tiles_n;
-        const int mt = ((t / ep.tiles_n) % ep.m_groups) * CL + crank;
-        const int z = t / (ep.tiles_n * ep.m_groups);
-        const int m0 = mt * Cfg::BM, n0 = nt * BN;
-        for (int kc = 0; kc < num_k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // ================= TMA producer =================
+    // All 32 lanes run the schedule and the barrier waits, one elected lane issues the copies: inside an
+    // `if (lane == 0)` region every TMA / MMA instruction costs a divergent R2UR waterfall (~25 dependent instructions,
+    // ~200 clk per MMA measured), which bounds the K loop of the narrow tiles.
+    int stage = 0;
+    uint32_t phase = 0;
+    bool waited = false;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      const int nt = t % ep.tiles_n;
+      const int mt = ((t / ep.tiles_n) % ep.m_groups) * CL + crank;
+      const int z = t / (ep.tiles_n * ep.m_groups);
+      const int m0 = mt * Cfg::BM, n0 = nt * BN;
+      const int za = ep.a_bcast ? 0 : z, zb = ep.b_bcast ? 0 : z;
+      if (!waited) {
+        waited = true;
+        pdl_wait();
+        GT(0, 3);
+      }
+      for (int kc = 0; kc < num_k_chunks; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        GT(0, 100 + kc);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * Cfg::BK, m0, ep.a_bcast ? 0 : z);
-          const int zb = ep.b_bcast ? 0 : z;
+          tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * Cfg::BK, m0, za);
           if constexpr (CL == 1) {
             if constexpr (!B_MN) {
               tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * Cfg::BK, n0, zb);
@@ -152,44 +188,60 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                     kMask);
             }
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      const uint32_t idesc = make_idesc_f16(128, BN, idesc_fmt(ep.fp16), /*a K-major*/ 0, B_MN ? 1 : 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    // ================= MMA issuer =================
+    // Warp-converged like the producer; the descriptors advance as 32-bit low words (start address field), the high
+    // words (stride / version / swizzle) are loop constants.
+    const uint32_t idesc = make_idesc_f16(128, BN, idesc_fmt(ep.fp16), /*a K-major*/ 0, B_MN ? 1 : 0);
+    const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t db0 = B_MN ? make_smem_desc_sw128(smem_u32(smem) + Cfg::A_BYTES, 64 * 128, 1024)
+                              : make_smem_desc_sw128(smem_u32(smem) + Cfg::A_BYTES, 16, 1024);
+    const uint32_t a_lo0 = (uint32_t)da0, a_hi = (uint32_t)(da0 >> 32);
+    const uint32_t b_lo0 = (uint32_t)db0, b_hi = (uint32_t)(db0 >> 32);
+    constexpr uint32_t B_KSTEP = B_MN ? (16 * 128) >> 4 : 32 >> 4;   // low-word advance per 16-wide K step
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kc = 0; kc < num_k_chunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        GT(1, 200 + kc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kc = 0; kc < num_k_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const int krem = ep.K - kc * Cfg::BK;
-          const int ksteps = krem >= Cfg::BK ? 4 : (krem + 15) / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(sa + ks * 32, 16, 1024);
-            uint64_t db;
-            if constexpr (!B_MN) db = make_smem_desc_sw128(sb + ks * 32, 16, 1024);
-            else db = make_smem_desc_sw128(sb + ks * (16 * 128), 64 * 128, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kc | ks) != 0 ? 1u : 0u);
-          }
-          // frees the smem slot (in every CTA that multicasts into it) once these MMAs have read it
+        const uint32_t a_lo = a_lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+        const int krem = ep.K - kc * Cfg::BK;
+        if (krem >= Cfg::BK) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (elect_one())
+              umma_ss_lh(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * B_KSTEP, b_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+        } else {
+          const int ksteps = (krem + 15) / 16;
+          for (int ks = 0; ks < ksteps; ++ks)
+            if (elect_one())
+              umma_ss_lh(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * B_KSTEP, b_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+        }
+        // frees the smem slot (in every CTA that multicasts into it) once these MMAs have read it
+        if (elect_one()) {
           if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mcast(&empty_bar[stage], kMask);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      GT(1, 299);
     }
   } else if (warp >= 4) {
     // ================= Epilogue =================
@@ -204,6 +256,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                       ((ep.strideR & 3) == 0);
     const bool vec16 = ((ep.ldo16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7u) == 0) &&
                        ((ep.strideO16 & 3) == 0);
+    pdl_wait();
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int nt = t % ep.tiles_n;
@@ -223,9 +276,41 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (nt * BN + half * HALF_COLS + cc < ep.N)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + cc));
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BN + half * HALF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (warp == 4) GT(2, 300);
+      // the epilogue's global inputs of a chunk (residual block in the transposed mapping: lane -> 4 columns of rows
+      // i*4 + lane/8; bias and LayerNorm column sums of the chunk's 32 columns): the first chunk's are requested BEFORE
+      // the accumulator wait, so a small problem (one chunk per warp, one tile per CTA) does not pay their latency
+      // after its K loop
+      // (the LayerNorm column sums share the residual's registers: a fused-LayerNorm consumer has no residual input)
+      float4 resv[8], biasv[8];
+      float4 (&colv)[8] = resv;
+      bool res_fast = false, bias_fast = false, col_fast = false;
+      auto load_inputs = [&](int c) {
+        const int col0 = nt * BN + half * HALF_COLS + c * 32;
+        const bool full = (col0 + 32 <= ep.N);
+        res_fast = via_smem && res_z != nullptr && vecr && full;
+        if (res_fast) {
+          const float* rp0 = res_z + static_cast<long long>(row_base + (lane >> 3)) * ep.ldr + col0 + (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = row_base + i * 4 + (lane >> 3) < ep.M;
+            resv[i] = ok ? __ldg(reinterpret_cast<const float4*>(rp0 + static_cast<long long>(i * 4) * ep.ldr))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        bias_fast = ep.bias_mode == 1 && full && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15u) == 0);
+        if (bias_fast) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) biasv[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+        }
+        col_fast = !res_fast && ep.row_stats_in != nullptr && full &&
+                   ((reinterpret_cast<uintptr_t>(ep.ln_colsum + col0) & 15u) == 0);
+        if (col_fast) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) colv[j] = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0) + j);
+        }
+      };
+      if (nt * BN + half * HALF_COLS < ep.N) load_inputs(0);
       const float row_bias = (ep.bias_mode == 2 && row_ok) ? __ldg(ep.bias + row) : 0.0f;
       // fused LayerNorm, consumer side: this row's mean / rstd from the partial statistics its producer left (added in a
       // fixed order: bit-reproducible)
@@ -241,6 +326,10 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ln_mean = s1 * ep.ln_inv_c;
         ln_rstd = rsqrtf(fmaxf(s2 * ep.ln_inv_c - ln_mean * ln_mean, 0.f) + ep.ln_eps);
       }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 4) GT(2, 301);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + half * HALF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       // producer side: partial statistics of the final rows, in the transposed mapping (lane -> 4 columns of rows
       // i * 4 + lane / 8), accumulated over the warp's chunks and reduced over the 8 lanes of a row at the end
       float st_sum[8], st_sq[8];
@@ -253,39 +342,39 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int col0 = nt * BN + half * HALF_COLS + c * 32;
         if (col0 >= ep.N) break;  // warp-uniform
         const bool full = (col0 + 32 <= ep.N);
-        // residual for this chunk, in the transposed mapping (lane -> 4 columns of rows i*4 + lane/8): all eight
-        // 16-byte loads are issued up front so their HBM latency overlaps the TMEM read, the math and the transpose
-        const bool res_fast = via_smem && res_z != nullptr && vecr && full;
-        float4 resv[8];
-        if (res_fast) {
-          const float* rp0 = res_z + static_cast<long long>(row_base + (lane >> 3)) * ep.ldr + col0 + (lane & 7) * 4;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = row_base + i * 4 + (lane >> 3) < ep.M;
-            resv[i] = ok ? __ldg(reinterpret_cast<const float4*>(rp0 + static_cast<long long>(i * 4) * ep.ldr))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        // later chunks: all loads are issued up front so their latency overlaps the TMEM read, the math and the transpose
+        if (c > 0) load_inputs(c);
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_wait_ld();
+        if (warp == 4) GT(2, 310 + c);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ep.alpha, row_bias);
         if (ep.row_stats_in != nullptr) {
           // v = rstd * (acc - mean * colsum[n])   (the bias, which already holds W.beta, is added below)
           const float nm = -ln_mean;
+          if (col_fast) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float cs = (col0 + j < ep.N) ? __ldg(ep.ln_colsum + col0 + j) : 0.f;
-            v[j] = ln_rstd * fmaf(nm, cs, v[j]);
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] = ln_rstd * fmaf(nm, colv[j].x, v[4 * j]);
+              v[4 * j + 1] = ln_rstd * fmaf(nm, colv[j].y, v[4 * j + 1]);
+              v[4 * j + 2] = ln_rstd * fmaf(nm, colv[j].z, v[4 * j + 2]);
+              v[4 * j + 3] = ln_rstd * fmaf(nm, colv[j].w, v[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float cs = (col0 + j < ep.N) ? __ldg(ep.ln_colsum + col0 + j) : 0.f;
+              v[j] = ln_rstd * fmaf(nm, cs, v[j]);
+            }
           }
         }
         if (ep.bias_mode == 1) {
-          if (full && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15u) == 0)) {
+          if (bias_fast) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+              const float4 bq = biasv[j];
               v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
             }
           } else {
@@ -298,6 +387,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
+        if (warp == 4) GT(2, 320 + c);
         if (!via_smem) {
           // bf16-only output: 64 contiguous bytes per thread
           if (row_ok) {
@@ -382,6 +472,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           __syncwarp();
         }
+        if (warp == 4) GT(2, 330 + c);
       }
       if (ep.row_stats_out != nullptr) {
         // one slot per (row, half-tile of columns): plain stores, no atomics; the warps of the first column tile also zero
@@ -404,6 +495,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if (warp == 4) GT(2, 302);
     }
   }
 
@@ -414,6 +506,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    GT(3, 400);
   }
 }
 
@@ -508,6 +601,16 @@ static int auto_tile_n(long long M, long long N, long long batch, int sm_count) 
 
 // Number of (sum, sum of squares) slots per row that the fused-LayerNorm producer GEMM of this shape writes with the
 // automatic kernel / tile choice (pio_gemm_args.row_stats_parts): two per column tile.
+#ifdef PIO_GEMM_TRACE
+extern "C" int pio_debug_gemm_trace(unsigned long long* out) {   // out: 4 * 128 * 3 words; clears the device buffer
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, pio::g_gemm_trace, sizeof(pio::g_gemm_trace));
+  static unsigned long long zeros[4 * 128 * 3];
+  cudaMemcpyToSymbol(pio::g_gemm_trace, zeros, sizeof(zeros));
+  return 0;
+}
+#endif
+
 extern "C" int pio_gemm_stats_parts(int32_t M, int32_t N) {
   using namespace pio;
   DeviceInfo dev;
@@ -563,7 +666,9 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   if (bn == 0) bn = auto_tile_n(a->M, a->N, a->batch, dev.sm_count);
   // cluster width along M: multicast pays when there are at least two M tiles to pair up
   int cl = a->cluster_m;
-  if (cl == 0) cl = (a->M > 128) ? 2 : 1;
+  // (not for the narrow tiles of small problems: their K loop is bound by the tensor pipe's per-instruction floor, and a
+  // cluster costs ~1000 clk of start-up and ~1200 clk of tear-down synchronisation per launch)
+  if (cl == 0) cl = (a->M > 128 && bn > 64) ? 2 : 1;
   PIO_REQUIRE(cl == 1 || cl == 2 || cl == 4, "pio_gemm_bf16: cluster_m must be 0, 1, 2 or 4 (got %d)", a->cluster_m);
   if (cl == 4 && bn == 64 && a->b_mn_major) cl = 2;  // a 64-column MN-major tile is a single TMA box
 #define PIO_GEMM_DISPATCH(BN_, MN_)                                            \

@@ -65,12 +65,17 @@ def fast() -> bool:
 
 
 # Tower LayerNorms folded into the projections around them when the latent array has at least
-# this many rows.  Both GEMM kernels carry the fused epilogues and the row statistics are deterministic, so the threshold
-# is a performance choice only: for the batch-1 towers (256 .. 2048 rows) the fusion removes two of the seven launches of
-# a layer but measured no faster (language 2.46 vs 2.51 ms, flow 3.81 vs 3.76, multimodal 1.30 vs 1.24 per forward: the
-# LayerNorm kernels cost ~3 us there and the GEMM epilogues grow by as much), so they keep the two-pass LayerNorm.
+# FUSE_LN_MIN_ROWS rows, or — with fp16 operands — at least FUSE_LN_MIN_CHANNELS channels.  Both GEMM kernels carry the
+# fused epilogues and the row statistics are deterministic.  For the batch-1 towers the fusion removes two of the seven
+# launches of a layer: with 1280 channels (language, 256 rows) a LayerNorm launch costs 4.9 us of a 53 us layer and the
+# forward goes 1.95 -> 1.66 ms; with 512 channels (flow 2048 rows, multimodal 784 rows) it costs 2.5 - 2.8 us, the GEMM
+# epilogues grow by as much and nothing is gained (3.57 vs 3.55, 1.15 vs 1.17 ms per forward).  The fused form rounds x to
+# 16 bits before the mean is subtracted; at full size the language output moves from 7.9e-3 to 8.8e-3 of the 1e-2 bound
+# with bf16 operands (1.1e-3 -> 1.2e-3 with fp16), so the small towers take it only in the fp16 mode, where the margin is
+# an order of magnitude; the large ones (>= 4096 rows: 7.0e-3 at B = 8, classification) take it in both.
 FUSE_LN = os.environ.get("PIO_FUSE_LN", "1") != "0"
 FUSE_LN_MIN_ROWS = int(os.environ.get("PIO_FUSE_LN_MIN_ROWS", "4096"))
+FUSE_LN_MIN_CHANNELS = int(os.environ.get("PIO_FUSE_LN_MIN_CHANNELS", "1024"))
 FUSE_LN_MAX_OFFSET = 1.0     # max |mean| / std of a residual-stream row the fused form accepts (perceiver.PerceiverEncoder)
 
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"

@@ -75,7 +75,7 @@ class PerceiverEncoder(nn.Module):
         self.cache_latents = False
         self._latent_cache = None
         # Tower LayerNorms folded into the projections: None = automatic (latent arrays of at least
-        # engine.FUSE_LN_MIN_ROWS rows, and only while the residual stream passes the numerics check below), True / False
+        # engine.FUSE_LN_MIN_ROWS rows, or of engine.FUSE_LN_MIN_CHANNELS channels with fp16 operands, and only while the residual stream passes the numerics check below), True / False
         # force it.  The fused form rounds x to bf16 BEFORE the mean is subtracted, which scales that product's rounding
         # error by sqrt(1 + mean^2 / var) per row: harmless for residual streams centred near zero, not for rows with a
         # large common offset.  So the first fused forward after a parameter change measures max |mean| / std over every
@@ -137,7 +137,8 @@ class PerceiverEncoder(nn.Module):
         fused = None
         want = self.fuse_layernorm
         if want is None:
-            want = engine.FUSE_LN and B * N >= engine.FUSE_LN_MIN_ROWS
+            want = engine.FUSE_LN and (B * N >= engine.FUSE_LN_MIN_ROWS
+                                       or (C >= engine.FUSE_LN_MIN_CHANNELS and engine.PRECISION == "fp16"))
         pver = None
         if want and self.fuse_layernorm is None:
             pver = tuple((p.data_ptr(), p._version) for p in self.parameters())

@@ -123,11 +123,22 @@ def sustained_peak():
     return peak
 
 
-def measure_config(name, iters=10, eager=True):
+def measure_config(name, iters=10, eager=True, precision=None):
     """One config at full size -> dict (see module docstring).  `eager=False` skips the eagerly launched timings and the
     per-family profile (bench.py's `other_configs` only wants the replayed-graph numbers)."""
     peak = sustained_peak()
     cfg = CONFIGS[name]
+    from perceiverio_pytorch_b200 import engine
+    # the operand format each model runs with after swap_hot_path(model) (install._auto_precision): fp16 for the
+    # optical-flow regression head, bf16 otherwise; `precision` overrides
+    precision = precision or ("fp16" if name == "flow" else "bf16")
+    with engine.precision_scope(precision):
+        res = _measure_config(name, cfg, peak, iters, eager)
+    res["precision"] = precision
+    return res
+
+
+def _measure_config(name, cfg, peak, iters, eager):
     torch.manual_seed(0)
     enc = pio.PerceiverEncoder(**cfg["enc"]).eval()
     dec = pio.PerceiverDecoder(**cfg["dec"]).eval()
