@@ -171,13 +171,27 @@ pio_flash_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto issue_s = [&](int j, int stage) {
       const uint32_t d = tmem_base + (j & 1) * BN;
       const uint32_t b0 = k_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+      // this thread's issue rate bounds the kernel for the wide heads: widths that fill all but
+      // the last three K steps of their last chunk (322 -> 21 steps, 261 -> 17) get a straight-line sequence without the
+      // per-step bound check
+      constexpr int FAST_STEPS = 4 * NQC - 3;
+      if (dqk_steps_total == FAST_STEPS) {
 #pragma unroll
-      for (int ks = 0; ks < 4 * NQC; ++ks) {
-        if (ks < dqk_steps_total) {
+        for (int ks = 0; ks < FAST_STEPS; ++ks) {
           const int c = ks >> 2, kk = ks & 3;
           if (elect_one())
             umma_ss_lh(d, q_lo + (uint32_t)((c * 16384 + kk * 32) >> 4), q_hi,
                        b0 + (uint32_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4), k_hi, idesc_s, ks != 0 ? 1u : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 4 * NQC; ++ks) {
+          if (ks < dqk_steps_total) {
+            const int c = ks >> 2, kk = ks & 3;
+            if (elect_one())
+              umma_ss_lh(d, q_lo + (uint32_t)((c * 16384 + kk * 32) >> 4), q_hi,
+                         b0 + (uint32_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4), k_hi, idesc_s, ks != 0 ? 1u : 0u);
+          }
         }
       }
       if (elect_one()) umma_commit(&s_full[j & 1]);

@@ -171,13 +171,26 @@ pio_flash_qt_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     auto issue_s = [&](int j, int stage) {
       const uint32_t dst = tmem_base + (uint32_t)((j & 1) * BN);
       const uint32_t b0 = k_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+      // the issue rate of this thread bounds the kernel: the ImageNet-pixels width (261 -> 17 K
+      // steps) gets a straight-line sequence without the per-step bound check (9 -> 6 uniform instructions per MMA)
+      constexpr int FAST_STEPS = 4 * NQC - 3;
+      if (d_steps == FAST_STEPS) {
 #pragma unroll
-      for (int ks = 0; ks < 4 * NQC; ++ks) {
-        if (ks < d_steps) {
+        for (int ks = 0; ks < FAST_STEPS; ++ks) {
           const int c = ks >> 2, kk = ks & 3;
           if (elect_one())
             umma_ts_lh(dst, tmem_q + (uint32_t)(ks * 8), b0 + (uint32_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4), k_hi, idesc_s,
                        ks != 0 ? 1u : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 4 * NQC; ++ks) {
+          if (ks < d_steps) {
+            const int c = ks >> 2, kk = ks & 3;
+            if (elect_one())
+              umma_ts_lh(dst, tmem_q + (uint32_t)(ks * 8), b0 + (uint32_t)((c * Cfg::CHUNK_BYTES + kk * 32) >> 4), k_hi,
+                         idesc_s, ks != 0 ? 1u : 0u);
+          }
         }
       }
       if (elect_one()) umma_commit(&s_full[j & 1]);

@@ -91,7 +91,7 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;           // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
 #ifdef PIO_GEMM_TRACE
   int gtn = 0;
