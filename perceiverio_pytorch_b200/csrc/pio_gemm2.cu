@@ -49,14 +49,19 @@ struct Gemm2Params {
 enum { G2_BF16 = 0, G2_F32 = 1 };
 
 // fp32-output kind: operand stages vs depth of the per-warp residual prefetch ring (both live in shared memory)
+// G2_F32_CHUNK: columns per epilogue chunk (16: 64-byte fp32 rows per TMA box, 32: 128-byte rows — half the TMA row
+// requests per byte; the copy engine's request rate is what bounds this kind)
+#ifndef G2_F32_CHUNK
+#define G2_F32_CHUNK 32
+#endif
 #ifndef G2_F32_STAGES
 #define G2_F32_STAGES 4
 #endif
 #ifndef G2_F32_RES_SLOTS
-#define G2_F32_RES_SLOTS 2
+#define G2_F32_RES_SLOTS (G2_F32_CHUNK == 32 ? 1 : 2)
 #endif
 #ifndef G2_F32_OUT_SLOTS
-#define G2_F32_OUT_SLOTS 2
+#define G2_F32_OUT_SLOTS (G2_F32_CHUNK == 32 ? 1 : 2)
 #endif
 
 template <int KIND>
@@ -71,11 +76,11 @@ struct Gemm2Cfg {
   static constexpr int EPI_WARPS = 8;
   // staging slots: bf16 output 32 rows x 64 columns (128-byte rows, SWIZZLE_128B); fp32 32 rows x 16 columns (64-byte
   // rows, SWIZZLE_64B) so that two residual + two output slots per warp leave room for the fifth operand stage
-  static constexpr int SLOT_BYTES = (KIND == G2_F32) ? 2048 : 4096;
+  static constexpr int SLOT_BYTES = (KIND == G2_F32) ? 32 * G2_F32_CHUNK * 4 : 4096;
   static constexpr int RES_SLOTS = (KIND == G2_F32) ? G2_F32_RES_SLOTS : 0;
   static constexpr int OUT_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 2;
   // fused-LayerNorm producer: raw bf16 copy of the fp32 output, 32 rows x 16 columns (32-byte rows, no swizzle)
-  static constexpr int RAW_SLOT_BYTES = 1024;
+  static constexpr int RAW_SLOT_BYTES = 32 * G2_F32_CHUNK * 2;
   static constexpr int RAW_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 0;
   static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES + RAW_SLOTS * RAW_SLOT_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
@@ -215,7 +220,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_raw = my_out + Cfg::OUT_SLOTS * Cfg::SLOT_BYTES;
     uint64_t* my_res_full = res_full + ew * RS;
     const bool has_res = (KIND == G2_F32) && p.has_residual;
-    constexpr int CHUNK_COLS = (KIND == G2_F32) ? 16 : 64;
+    constexpr int CHUNK_COLS = (KIND == G2_F32) ? G2_F32_CHUNK : 64;
     constexpr int CHUNKS = 128 / CHUNK_COLS;           // chunks of this warp's column half per tile
     const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
@@ -285,6 +290,12 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
             v[32 + j] = fmaf(__uint_as_float(r2[j]), p.alpha, row_bias);
           }
+        } else if constexpr (CHUNK_COLS == 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * CHUNK_COLS, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
         } else {
           uint32_t r[16];
           tmem_ld16(t_row + c * CHUNK_COLS, r);
@@ -363,8 +374,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&my_res_full[slot], (use_idx / (uint32_t)RS) & 1u);
             const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 rq = *reinterpret_cast<const float4*>(rs + sw64_offset(lane, j));
+            for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+              const float4 rq = *reinterpret_cast<const float4*>(
+                  rs + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j)));
               v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
             }
           }
@@ -382,23 +394,23 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) bulk_wait_read<Cfg::OUT_SLOTS - 1>();   // the stores issued OUT_SLOTS chunks ago used these slots
           __syncwarp();
           if (p.raw_bf16 != nullptr) {
-            // bf16 copy of the un-normalised row segment (32 bytes per row) for the fused LayerNorm of the consumer
-            uint4* rp = reinterpret_cast<uint4*>(slot_raw + lane * 32);
-            if (p.fp16) {
-              rp[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
-                                 pack_f16x2(v[6], v[7]));
-              rp[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]),
-                                 pack_f16x2(v[14], v[15]));
-            } else {
-              rp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                 pack_bf16x2(v[6], v[7]));
-              rp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                 pack_bf16x2(v[14], v[15]));
-            }
+            // 16-bit copy of the un-normalised row segment for the fused LayerNorm of the consumer: 32-byte rows (no
+            // swizzle) with 16-column chunks, 64-byte rows (SWIZZLE_64B) with 32-column chunks
+            auto raw_out = [&](auto f16tag) {
+              constexpr bool F16 = decltype(f16tag)::value;
+#pragma unroll
+              for (int j = 0; j < CHUNK_COLS / 8; ++j) {
+                const uint4 q = make_uint4(pack16x2<F16>(v[8 * j], v[8 * j + 1]), pack16x2<F16>(v[8 * j + 2], v[8 * j + 3]),
+                                           pack16x2<F16>(v[8 * j + 4], v[8 * j + 5]), pack16x2<F16>(v[8 * j + 6], v[8 * j + 7]));
+                *reinterpret_cast<uint4*>(slot_raw + (CHUNK_COLS == 32 ? sw64_offset(lane, j) : lane * 32 + j * 16)) = q;
+              }
+            };
+            if (p.fp16) raw_out(std::true_type{});
+            else raw_out(std::false_type{});
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(slot_out + sw64_offset(lane, j)) =
+          for (int j = 0; j < CHUNK_COLS / 4; ++j)
+            *reinterpret_cast<float4*>(slot_out + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j))) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
@@ -483,23 +495,24 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   if (KIND == G2_F32) {
     const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
     const uint64_t strides[2] = {(uint64_t)a->ldo32 * 4, (uint64_t)(a->batch > 1 ? a->strideO32 : a->ldo32 * (int64_t)a->M) * 4};
-    const uint32_t box[3] = {16, 32, 1};
-    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, 64);
+    const uint32_t box[3] = {G2_F32_CHUNK, 32, 1};
+    constexpr int F32_SWZ = G2_F32_CHUNK == 32 ? 128 : 64;
+    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, F32_SWZ);
     if (rc != PIO_OK) return rc;
     tr = to;
     traw = to;
     if (a->out_bf16) {
       const uint64_t wdims[3] = {(uint64_t)a->N, (uint64_t)a->M, 1};
       const uint64_t wstrides[2] = {(uint64_t)a->ldo16 * 2, (uint64_t)a->ldo16 * (uint64_t)a->M * 2};
-      const uint32_t wbox[3] = {16, 32, 1};
-      rc = encode_tmap(&traw, a->out_bf16, false, 3, wdims, wstrides, wbox, 0);
+      const uint32_t wbox[3] = {G2_F32_CHUNK, 32, 1};
+      rc = encode_tmap(&traw, a->out_bf16, false, 3, wdims, wstrides, wbox, G2_F32_CHUNK == 32 ? 64 : 0);
       if (rc != PIO_OK) return rc;
     }
     if (a->residual) {
       const uint64_t rb = r_bcast ? 1 : a->batch;
       const uint64_t rdims[3] = {(uint64_t)a->N, (uint64_t)a->M, rb};
       const uint64_t rstrides[2] = {(uint64_t)a->ldr * 4, (uint64_t)(rb > 1 ? a->strideR : a->ldr * (int64_t)a->M) * 4};
-      rc = encode_tmap(&tr, a->residual, true, 3, rdims, rstrides, box, 64);
+      rc = encode_tmap(&tr, a->residual, true, 3, rdims, rstrides, box, F32_SWZ);
       if (rc != PIO_OK) return rc;
     }
   } else {
