@@ -52,6 +52,15 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
     v[i] = (c < nvec) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
+  // gamma / beta are requested here, before the reductions: left inside the output loop they cost a second memory round
+  // trip after the statistics (4 x 1280 in a dependent chain: 4.7 us with the affine, 2.6 us without)
+  float4 gv[NV], bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    gv[i] = (gamma && c < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    bv[i] = (beta && c < nvec) ? __ldg(reinterpret_cast<const float4*>(beta) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float mean = 0.f, rstd = 1.f;
   if (normalize) {
     mean = warp_sum(s) / (float)C;
@@ -78,14 +87,8 @@ __global__ void __launch_bounds__(128) pio_layernorm_vec_kernel(const float* __r
       if (c < nvec) {
         o.x = (v[i].x - mean) * rstd; o.y = (v[i].y - mean) * rstd;
         o.z = (v[i].z - mean) * rstd; o.w = (v[i].w - mean) * rstd;
-        if (gamma) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-          o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
-        }
-        if (beta) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-        }
+        o.x = fmaf(o.x, gv[i].x, bv[i].x); o.y = fmaf(o.y, gv[i].y, bv[i].y);
+        o.z = fmaf(o.z, gv[i].z, bv[i].z); o.w = fmaf(o.w, gv[i].w, bv[i].w);
       }
       const uint2 hi = make_uint2(pack16x2(o.x, o.y, f16), pack16x2(o.z, o.w, f16));
       yr[c] = hi;
