@@ -408,6 +408,50 @@ pio_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (col0 + j < ep.N) reinterpret_cast<uint16_t*>(op)[j] = cvt16(v[j], ep.fp16);
             }
           }
+        } else if (full && row_base + 32 <= ep.M && (res_z == nullptr || res_fast) && (o32_z == nullptr || vec32) &&
+                   (o16_z == nullptr || vec16)) {
+          // whole 32 x 32 block inside the matrix, every pointer vector-aligned (the residual-stream GEMMs of the latent
+          // towers): 16-byte shared-memory accesses in an XOR-swizzled layout (group g of row r at r * 8 + (g ^ (r & 7)):
+          // conflict-free both ways) and no per-element bounds checks — this loop is on the critical path of the
+          // one-tile-per-CTA problems
+          float4* xq = reinterpret_cast<float4*>(xp);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            xq[lane * 8 + (g ^ (lane & 7))] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          __syncwarp();
+          const int g = lane & 7;
+          float4 w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            w[i] = xq[rr * 8 + (g ^ (rr & 7))];
+          }
+          if (res_z != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              w[i].x += resv[i].x; w[i].y += resv[i].y; w[i].z += resv[i].z; w[i].w += resv[i].w;
+            }
+          }
+          if (ep.row_stats_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              st_sum[i] += (w[i].x + w[i].y) + (w[i].z + w[i].w);
+              st_sq[i] = fmaf(w[i].x, w[i].x, fmaf(w[i].y, w[i].y, fmaf(w[i].z, w[i].z, fmaf(w[i].w, w[i].w, st_sq[i]))));
+            }
+          }
+          if (o32_z != nullptr) {
+            float* op = o32_z + static_cast<long long>(row_base + (lane >> 3)) * ep.ldo32 + col0 + g * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(op + static_cast<long long>(i * 4) * ep.ldo32) = w[i];
+          }
+          if (o16_z != nullptr) {
+            __nv_bfloat16* op = o16_z + static_cast<long long>(row_base + (lane >> 3)) * ep.ldo16 + col0 + g * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint2*>(op + static_cast<long long>(i * 4) * ep.ldo16) =
+                  make_uint2(pack16x2(w[i].x, w[i].y, ep.fp16), pack16x2(w[i].z, w[i].w, ep.fp16));
+          }
+          __syncwarp();
         } else {
           // transpose the warp's 32x32 block through shared memory: afterwards lane l holds 4 consecutive columns
           // (l%8)*4.. of rows i*4 + l/8, so a warp instruction touches 4 rows x 128 contiguous bytes
