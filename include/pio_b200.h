@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PIO_ABI_VERSION 14
+#define PIO_ABI_VERSION 15
 
 typedef enum pio_status {
   PIO_OK = 0,
@@ -130,12 +130,25 @@ typedef struct pio_gemm_args {
   int32_t reverse_tiles;
   int32_t row_stats_parts;    /* partial statistics per row in row_stats_out / row_stats_in (see above) */
   int32_t fp16;               /* 16-bit format of A, B and out_bf16: 0 = bf16, 1 = fp16 */
+  /* Residual stream as a PAIR of 16-bit arrays instead of fp32 (CTA-pair kernel only, batch == 1; the producer GEMMs of
+   * the latent tower are bound by HBM bytes): value = hi + lo with hi = round16(v),
+   * lo = round16(v - hi) — 16 (bf16) or 22 (fp16) significant bits, and hi IS the raw 16-bit copy the fused-LayerNorm
+   * consumer multiplies, so the stream costs 4 bytes per element to write instead of 6.
+   *  - out_lo16 != NULL (with out_bf16 != NULL and out_f32 == NULL): out_bf16 = hi, out_lo16 = lo, both with pitch ldo16;
+   *  - residual_hi16 / residual_lo16 != NULL (with residual == NULL): v += hi + lo, both with pitch ldr16. */
+  void* out_lo16;
+  const void* residual_hi16;
+  const void* residual_lo16;
+  int64_t ldr16;
 } pio_gemm_args;
 int pio_gemm_bf16(const pio_gemm_args* a, void* stream);
 /* Number of statistics slots per row that a fused-LayerNorm producer GEMM of shape M x N writes with the automatic
  * kernel / tile choice on the current device (what to pass as row_stats_parts; larger values are allowed, the unused
  * slots are zeroed — but the consumer reads every slot, so do not oversize). */
 int pio_gemm_stats_parts(int32_t M, int32_t N);
+/* 1 if pio_gemm_bf16 runs an M x N problem (batch 1, tuning fields 0) on the CTA-pair kernel on the current device — the
+ * kernel that implements out_lo16 / residual_hi16 / residual_lo16 —, else 0. */
+int pio_gemm_pair_kernel(int32_t M, int32_t N);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Row softmax for the materialised attention path: P[b, i, :] = softmax(scale * S[b, i, :]) with masked keys

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "pio_layernorm_bf16", "pio_gemm_bf16", "pio_softmax_bf16",
     "pio_attention_fwd", "pio_attention_supported", "pio_attention_key_tile", "pio_attention_combine",
     "pio_linear_f32", "pio_layernorm_concat_bf16", "pio_hash_words",
-    "pio_decoder_attention_fwd", "pio_decoder_attention_supported", "pio_gemm_stats_parts",
+    "pio_decoder_attention_fwd", "pio_decoder_attention_supported", "pio_gemm_stats_parts", "pio_gemm_pair_kernel",
 )
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -48,7 +48,8 @@ class GemmArgs(C.Structure):
                 ("out_bf16", vp), ("ldo16", i64), ("strideO16", i64),
                 ("tile_n", i32), ("max_ctas", i32), ("cluster_m", i32), ("kernel", i32),
                 ("row_stats_out", vp), ("row_stats_in", vp), ("ln_colsum", vp), ("ln_channels", i32), ("ln_eps", f32),
-                ("reverse_tiles", i32), ("row_stats_parts", i32), ("fp16", i32)]
+                ("reverse_tiles", i32), ("row_stats_parts", i32), ("fp16", i32),
+                ("out_lo16", vp), ("residual_hi16", vp), ("residual_lo16", vp), ("ldr16", i64)]
 
 
 class SoftmaxArgs(C.Structure):
@@ -141,6 +142,8 @@ def load(build_if_missing: bool = True):
         lib.pio_hash_words.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.pio_gemm_stats_parts.restype = C.c_int
         lib.pio_gemm_stats_parts.argtypes = [C.c_int32, C.c_int32]
+        lib.pio_gemm_pair_kernel.restype = C.c_int
+        lib.pio_gemm_pair_kernel.argtypes = [C.c_int32, C.c_int32]
         lib.pio_decoder_attention_supported.restype = C.c_int
         lib.pio_decoder_attention_supported.argtypes = [C.c_int32, C.c_int32]
         lib.pio_attention_supported.restype = C.c_int
@@ -151,7 +154,7 @@ def load(build_if_missing: bool = True):
         lib.pio_profile_enable.argtypes = [C.c_int]
         lib.pio_profile_read.restype = C.c_int
         lib.pio_profile_read.argtypes = [C.POINTER(C.c_double), C.c_int]
-        if lib.pio_abi_version() != 14:
+        if lib.pio_abi_version() != 15:
             raise RuntimeError("libpio_b200.so ABI version mismatch")
         _lib = lib
     return _lib

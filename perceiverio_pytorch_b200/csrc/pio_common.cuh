@@ -48,6 +48,18 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
   return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
+// the two values of a packed 16-bit pair as floats (exact)
+template <bool F16>
+__device__ __forceinline__ void unpack16x2(uint32_t w, float& lo, float& hi) {
+  if constexpr (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ uint16_t cvt16(float v, int f16) { return (uint16_t)(pack16x2(v, 0.f, f16) & 0xffffu); }
 __device__ __forceinline__ float cvt16_back(uint16_t h, int f16) {
   return f16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);

@@ -665,6 +665,14 @@ extern "C" int pio_gemm_stats_parts(int32_t M, int32_t N) {
   return 2 * ((N + bn - 1) / bn);
 }
 
+extern "C" int pio_gemm_pair_kernel(int32_t M, int32_t N) {
+  using namespace pio;
+  DeviceInfo dev;
+  int sm = 148;
+  if (get_device_info(&dev) == PIO_OK && dev.sm_count > 0) sm = dev.sm_count;
+  return (sm % 2 == 0 && auto_wants_pair(M, N, 1, sm)) ? 1 : 0;
+}
+
 extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   using namespace pio;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -695,6 +703,14 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
                                        "16-byte aligned output / residual rows");
     const bool want = a->kernel == 2 ||
                       (a->kernel == 0 && a->tile_n == 0 && a->cluster_m == 0 && auto_wants_pair(a->M, a->N, a->batch, dev.sm_count));
+    if (a->out_lo16 || a->residual_hi16 || a->residual_lo16) {
+      // the 16-bit pair residual stream exists in the CTA-pair kernel only
+      if (!elig || a->kernel == 1)
+        return fail(PIO_ERR_UNSUPPORTED, "pio_gemm_bf16: out_lo16 / residual_hi16 / residual_lo16 need the CTA-pair kernel "
+                                         "(batch 1, K-major B, 16-byte aligned rows, out_bf16 with out_lo16, both residual "
+                                         "halves, no fp32 form of the same operand)");
+      return launch_gemm2(a, dev, stream);
+    }
     if (elig && want) return launch_gemm2(a, dev, stream);
     // the single-CTA kernel has the fused-LayerNorm epilogues too (small latent arrays), with these limits:
     if (a->row_stats_out || a->row_stats_in) {
@@ -710,8 +726,8 @@ extern "C" int pio_gemm_bf16(const pio_gemm_args* a, void* stream_) {
   if (bn == 0) bn = auto_tile_n(a->M, a->N, a->batch, dev.sm_count);
   // cluster width along M: multicast pays when there are at least two M tiles to pair up
   int cl = a->cluster_m;
-  // (not for the narrow tiles of small problems: their K loop is bound by the tensor pipe's per-instruction floor, and a
-  // cluster costs ~1000 clk of start-up and ~1200 clk of tear-down synchronisation per launch)
+  // (not for the narrow tiles of small problems: their K loop is bound by the MMA issue stream, not by operand traffic,
+  // and a cluster costs ~1000 clk of start-up and ~1200 clk of tear-down synchronisation per launch)
   if (cl == 0) cl = (a->M > 128 && bn > 64) ? 2 : 1;
   PIO_REQUIRE(cl == 1 || cl == 2 || cl == 4, "pio_gemm_bf16: cluster_m must be 0, 1, 2 or 4 (got %d)", a->cluster_m);
   if (cl == 4 && bn == 64 && a->b_mn_major) cl = 2;  // a 64-column MN-major tile is a single TMA box

@@ -40,6 +40,9 @@ struct Gemm2Params {
   int stats_parts;               // partials per row: 2 * tiles_n on the producer side, whatever the producer wrote on the consumer side
   __nv_bfloat16* raw_bf16;       // bf16 copy of the fp32 output (un-normalised rows), row pitch ld_raw
   long long ld_raw;
+  // residual stream as a pair of 16-bit arrays (pio_gemm_args.out_lo16 / residual_hi16 / residual_lo16)
+  int out_split;                 // outputs: hi through tmap_raw, lo through tmap_out (no fp32 output)
+  int res_split;                 // residual: hi through tmap_res, lo through tmap_res_lo
   // ... consumer side
   const float* row_stats_in;     // [M][stats_parts][2] of the A operand's rows
   const float* ln_colsum;        // [N]
@@ -94,7 +97,8 @@ template <int KIND>
 __global__ void __launch_bounds__(384, 1)
 pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                 const __grid_constant__ CUtensorMap tmap_raw, const Gemm2Params p) {
+                 const __grid_constant__ CUtensorMap tmap_raw, const __grid_constant__ CUtensorMap tmap_res_lo,
+                 const Gemm2Params p) {
   using Cfg = Gemm2Cfg<KIND>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* epi_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -238,7 +242,13 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int col = nt * Cfg::BN + half * 128 + pf_c * CHUNK_COLS;
       const uint32_t slot = pf_idx % (uint32_t)RS;
       mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
-      tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, p.r_bcast ? 0 : z);
+      if (KIND == G2_F32 && p.res_split) {
+        // hi and lo boxes (32 rows x CHUNK_COLS 16-bit values each) fill the two halves of the fp32-sized slot
+        tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, 0);
+        tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::SLOT_BYTES / 2, &tmap_res_lo, &my_res_full[slot], col, row, 0);
+      } else {
+        tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, p.r_bcast ? 0 : z);
+      }
       ++pf_idx;
       if (++pf_c == CHUNKS) { pf_c = 0; pf_t += num_pairs; }
     };
@@ -373,11 +383,35 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t slot = use_idx % (uint32_t)RS;
             mbar_wait(&my_res_full[slot], (use_idx / (uint32_t)RS) & 1u);
             const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
+            if (p.res_split) {
+              // value = hi + lo, two 16-bit rows of CHUNK_COLS * 2 bytes each
+              auto add_pair = [&](auto f16tag) {
+                constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
-            for (int j = 0; j < CHUNK_COLS / 4; ++j) {
-              const float4 rq = *reinterpret_cast<const float4*>(
-                  rs + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j)));
-              v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
+                for (int j = 0; j < CHUNK_COLS / 8; ++j) {
+                  const uint32_t off = CHUNK_COLS == 32 ? sw64_offset(lane, j) : lane * 32 + j * 16;
+                  const uint4 h = *reinterpret_cast<const uint4*>(rs + off);
+                  const uint4 l = *reinterpret_cast<const uint4*>(rs + Cfg::SLOT_BYTES / 2 + off);
+                  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    float h0, h1, l0, l1;
+                    unpack16x2<F16>(hw[k], h0, h1);
+                    unpack16x2<F16>(lw[k], l0, l1);
+                    v[8 * j + 2 * k] += h0 + l0;
+                    v[8 * j + 2 * k + 1] += h1 + l1;
+                  }
+                }
+              };
+              if (p.fp16) add_pair(std::true_type{});
+              else add_pair(std::false_type{});
+            } else {
+#pragma unroll
+              for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                const float4 rq = *reinterpret_cast<const float4*>(
+                    rs + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j)));
+                v[4 * j] += rq.x; v[4 * j + 1] += rq.y; v[4 * j + 2] += rq.z; v[4 * j + 3] += rq.w;
+              }
             }
           }
           if (p.row_stats_out != nullptr) {
@@ -400,18 +434,33 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               constexpr bool F16 = decltype(f16tag)::value;
 #pragma unroll
               for (int j = 0; j < CHUNK_COLS / 8; ++j) {
-                const uint4 q = make_uint4(pack16x2<F16>(v[8 * j], v[8 * j + 1]), pack16x2<F16>(v[8 * j + 2], v[8 * j + 3]),
-                                           pack16x2<F16>(v[8 * j + 4], v[8 * j + 5]), pack16x2<F16>(v[8 * j + 6], v[8 * j + 7]));
-                *reinterpret_cast<uint4*>(slot_raw + (CHUNK_COLS == 32 ? sw64_offset(lane, j) : lane * 32 + j * 16)) = q;
+                const uint32_t off = CHUNK_COLS == 32 ? sw64_offset(lane, j) : lane * 32 + j * 16;
+                uint32_t hw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hw[k] = pack16x2<F16>(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                *reinterpret_cast<uint4*>(slot_raw + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (p.out_split) {
+                  // the remainder after the 16-bit rounding, in the (otherwise unused) fp32 staging slot
+                  uint32_t lw[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    float h0, h1;
+                    unpack16x2<F16>(hw[k], h0, h1);
+                    lw[k] = pack16x2<F16>(v[8 * j + 2 * k] - h0, v[8 * j + 2 * k + 1] - h1);
+                  }
+                  *reinterpret_cast<uint4*>(slot_out + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
               }
             };
             if (p.fp16) raw_out(std::true_type{});
             else raw_out(std::false_type{});
           }
+          if (!p.out_split) {
 #pragma unroll
-          for (int j = 0; j < CHUNK_COLS / 4; ++j)
-            *reinterpret_cast<float4*>(slot_out + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j))) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CHUNK_COLS / 4; ++j)
+              *reinterpret_cast<float4*>(slot_out + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j))) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
           fence_proxy_async_smem();
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
           if (lane == 0) {
@@ -492,15 +541,34 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
     int rc = encode_tmap(&tb, a->B, false, 3, dims, strides, box);
     if (rc != PIO_OK) return rc;
   }
+  CUtensorMap trlo;
   if (KIND == G2_F32) {
-    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->ldo32 * 4, (uint64_t)(a->batch > 1 ? a->strideO32 : a->ldo32 * (int64_t)a->M) * 4};
     const uint32_t box[3] = {G2_F32_CHUNK, 32, 1};
     constexpr int F32_SWZ = G2_F32_CHUNK == 32 ? 128 : 64;
-    int rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, F32_SWZ);
+    constexpr int B16_SWZ = G2_F32_CHUNK == 32 ? 64 : 0;
+    int rc;
+    if (a->out_lo16) {
+      // split output: the "out" map addresses the lo array (16-bit, the geometry of the raw copy)
+      const uint64_t wdims[3] = {(uint64_t)a->N, (uint64_t)a->M, 1};
+      const uint64_t wstrides[2] = {(uint64_t)a->ldo16 * 2, (uint64_t)a->ldo16 * (uint64_t)a->M * 2};
+      rc = encode_tmap(&to, a->out_lo16, false, 3, wdims, wstrides, box, B16_SWZ);
+    } else {
+      const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
+      const uint64_t strides[2] = {(uint64_t)a->ldo32 * 4, (uint64_t)(a->batch > 1 ? a->strideO32 : a->ldo32 * (int64_t)a->M) * 4};
+      rc = encode_tmap(&to, a->out_f32, true, 3, dims, strides, box, F32_SWZ);
+    }
     if (rc != PIO_OK) return rc;
     tr = to;
     traw = to;
+    trlo = to;
+    if (a->residual_hi16) {
+      const uint64_t rdims[3] = {(uint64_t)a->N, (uint64_t)a->M, 1};
+      const uint64_t rstrides[2] = {(uint64_t)a->ldr16 * 2, (uint64_t)a->ldr16 * (uint64_t)a->M * 2};
+      rc = encode_tmap(&tr, a->residual_hi16, false, 3, rdims, rstrides, box, B16_SWZ);
+      if (rc != PIO_OK) return rc;
+      rc = encode_tmap(&trlo, a->residual_lo16, false, 3, rdims, rstrides, box, B16_SWZ);
+      if (rc != PIO_OK) return rc;
+    }
     if (a->out_bf16) {
       const uint64_t wdims[3] = {(uint64_t)a->N, (uint64_t)a->M, 1};
       const uint64_t wstrides[2] = {(uint64_t)a->ldo16 * 2, (uint64_t)a->ldo16 * (uint64_t)a->M * 2};
@@ -523,6 +591,7 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
     if (rc != PIO_OK) return rc;
     tr = to;
     traw = to;
+    trlo = to;
   }
   Gemm2Params p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
@@ -532,7 +601,9 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.a_bcast = a_bcast; p.b_bcast = b_bcast; p.r_bcast = r_bcast;
   p.bias = a->bias; p.bias_mode = a->bias ? a->bias_mode : 0;
   p.act = a->act; p.alpha = a->alpha;
-  p.has_residual = a->residual != nullptr;
+  p.has_residual = a->residual != nullptr || a->residual_hi16 != nullptr;
+  p.out_split = (KIND == G2_F32 && a->out_lo16 != nullptr) ? 1 : 0;
+  p.res_split = (KIND == G2_F32 && a->residual_hi16 != nullptr) ? 1 : 0;
   p.reverse = a->reverse_tiles ? 1 : 0;
   p.row_stats_out = (KIND == G2_F32) ? a->row_stats_out : nullptr;
   p.raw_bf16 = (KIND == G2_F32) ? reinterpret_cast<__nv_bfloat16*>(a->out_bf16) : nullptr;
@@ -560,10 +631,10 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   if (a->max_ctas > 0 && a->max_ctas / 2 < pairs) pairs = a->max_ctas / 2 > 0 ? a->max_ctas / 2 : 1;
   if (total < pairs) pairs = (int)total;
   {
-    const double bytes = (KIND == G2_F32 ? 4.0 * (a->residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
+    const double bytes = (KIND == G2_F32 ? 4.0 * (p.has_residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
     ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, bytes, stream);
     PIO_CUDA_OK(launch_kernel(pio_gemm2_kernel<KIND>, dim3((unsigned)(pairs * 2), 1, 1), dim3(384, 1, 1), Cfg::SMEM_BYTES,
-                              stream, 2, ta, tb, to, tr, traw, p));
+                              stream, 2, ta, tb, to, tr, traw, trlo, p));
   }
   g_launch_count.fetch_add(1);
   PIO_CUDA_OK(cudaGetLastError());
@@ -573,7 +644,17 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
 // Whether the CTA-pair kernel can run this problem (layout / alignment rules of its TMA epilogue).
 bool gemm2_eligible(const pio_gemm_args* a) {
   if (a->b_mn_major) return false;
-  const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
+  const bool split_out = a->out_lo16 != nullptr, split_res = a->residual_hi16 != nullptr || a->residual_lo16 != nullptr;
+  if (split_out || split_res) {
+    // 16-bit pair residual stream: batch 1, 16-byte aligned rows, never mixed with the fp32 form of the same operand
+    if (a->batch != 1) return false;
+    if (split_out && (a->out_f32 || !a->out_bf16 || !aligned16(a->out_lo16))) return false;
+    if (split_res && (a->residual || !a->residual_hi16 || !a->residual_lo16 || !aligned16(a->residual_hi16) ||
+                      !aligned16(a->residual_lo16) || a->ldr16 % 8 != 0 || a->ldr16 < a->N))
+      return false;
+    if (split_res && !split_out && !a->out_f32) return false;
+  }
+  const bool f32 = a->out_f32 != nullptr || split_out, b16 = a->out_bf16 != nullptr;
   if (!f32 && !b16) return false;
   if (f32 && b16) {
     // fp32 output plus its raw bf16 copy (fused-LayerNorm producer): staged per 16-column chunk, TMA-stored
@@ -584,8 +665,10 @@ bool gemm2_eligible(const pio_gemm_args* a) {
   if (a->row_stats_out && !f32) return false;
   if (a->row_stats_in && (f32 || !a->ln_colsum || a->ln_channels <= 0)) return false;
   if (f32) {
-    if (!aligned16(a->out_f32) || a->ldo32 % 4 != 0 || a->ldo32 < a->N) return false;
-    if (a->batch > 1 && (a->strideO32 % 4 != 0 || a->strideO32 <= 0)) return false;
+    if (!split_out) {
+      if (!aligned16(a->out_f32) || a->ldo32 % 4 != 0 || a->ldo32 < a->N) return false;
+      if (a->batch > 1 && (a->strideO32 % 4 != 0 || a->strideO32 <= 0)) return false;
+    }
     if (a->residual) {
       if (!aligned16(a->residual) || a->ldr % 4 != 0 || a->ldr < a->N) return false;
       if (a->batch > 1 && a->strideR % 4 != 0) return false;
@@ -599,7 +682,7 @@ bool gemm2_eligible(const pio_gemm_args* a) {
 }
 
 int launch_gemm2(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {
-  if (a->out_f32) return launch_gemm2_kind<G2_F32>(a, dev, stream);
+  if (a->out_f32 || a->out_lo16) return launch_gemm2_kind<G2_F32>(a, dev, stream);
   return launch_gemm2_kind<G2_BF16>(a, dev, stream);
 }
 

@@ -78,6 +78,9 @@ FUSE_LN_MIN_ROWS = int(os.environ.get("PIO_FUSE_LN_MIN_ROWS", "4096"))
 FUSE_LN_MIN_CHANNELS = int(os.environ.get("PIO_FUSE_LN_MIN_CHANNELS", "1024"))
 FUSE_LN_MAX_OFFSET = 1.0     # max |mean| / std of a residual-stream row the fused form accepts (perceiver.PerceiverEncoder)
 
+# Residual stream of the fused tower as a pair of 16-bit arrays between its producer GEMMs (pio_gemm_args.out_lo16) when
+# every one of them runs on the CTA-pair kernel (ops.gemm_uses_pair_kernel): 4 instead of 6 bytes written per element.
+SPLIT_STREAM = os.environ.get("PIO_SPLIT_STREAM", "1") != "0"
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"
 REVERSE_FC1 = os.environ.get("PIO_REVERSE_FC1", "1") != "0"   # fc1 too: the out-projection wrote its operand front to back
 
@@ -215,38 +218,57 @@ class PreparedFusedLayer:
                 and _streaming_ok(self.H, self.dqk, self.dv))
 
 
-def self_attention_block_fused(pf: PreparedFusedLayer, x: torch.Tensor, xb: torch.Tensor, st: torch.Tensor, *,
-                               B: int, N: int, st_mid: torch.Tensor, st_out: Optional[torch.Tensor]):
-    """SelfAttention.forward with fused LayerNorms.  x fp32 [M, C] (the residual stream), xb = bf16(x) [M, C],
-    st = per-row partial (sum, sum of squares) of x, [M, parts, 2] (ops.empty_row_stats); st_mid / st_out are such
-    buffers for the two residual-stream states this block produces (st_out None: the block's output feeds no further
-    fused LayerNorm).  Each producer GEMM fills every slot with plain stores and each consumer adds a row's slots in
-    index order, so the tower is bit-reproducible.
-    Returns (y fp32 [M, C], bf16(y) or None)."""
-    M, C = x.shape
-    dev = x.device
+def self_attention_block_fused(pf: PreparedFusedLayer, x: Optional[torch.Tensor], xb: torch.Tensor, st: torch.Tensor, *,
+                               B: int, N: int, st_mid: torch.Tensor, st_out: Optional[torch.Tensor],
+                               x_lo: Optional[torch.Tensor] = None, split: bool = False, split_out: bool = False):
+    """SelfAttention.forward with fused LayerNorms.  The residual stream comes in either as x fp32 [M, C] with xb = its
+    16-bit rounding, or — x None — as the pair (xb, x_lo) with value xb + x_lo (pio_gemm_args.out_lo16: what the producer
+    GEMMs of a large tower write instead of fp32 + raw copy, 4 bytes per element instead of 6; they are bound by HBM
+    bytes).  st = per-row partial (sum, sum of squares) of the stream, [M, parts, 2]
+    (ops.empty_row_stats); st_mid / st_out are such buffers for the two stream states this block produces (st_out None:
+    the block's output feeds no further fused LayerNorm).  Each producer GEMM fills every slot with plain stores and each
+    consumer adds a row's slots in index order, so the tower is bit-reproducible.
+    split: carry the state between the two halves of the block as a pair; split_out: return the block's output as a pair.
+    Returns (y fp32 [M, C] or None, 16-bit y (the rounding / the hi half) or None, lo half or None)."""
+    M, C = xb.shape
+    dev = xb.device
+    d16 = ops.dtype16()
     nqkv = 2 * pf.QK + pf.V
     ld = pad8(nqkv)
-    qkv = torch.empty((M, ld), dtype=ops.dtype16(), device=dev)
+    qkv = torch.empty((M, ld), dtype=d16, device=dev)
     ops.gemm(xb, pf.wqkv, M=M, N=nqkv, K=C, lda=xb.stride(0), bias=pf.bqkv, out_bf16=qkv, ldo16=ld,
              row_stats_in=st, ln_colsum=pf.cs_qkv, ln_channels=C, ln_eps=pf.eps1)
     o = attention(qkv, ld, 0, qkv, ld, pf.QK, qkv, ld, 2 * pf.QK, B=B, H=pf.H, Nq=N, Nk=N, dqk=pf.dqk, dv=pf.dv,
                   scale=pf.scale)
     o2 = o.view(M, -1)
-    x1 = torch.empty((M, C), dtype=torch.float32, device=dev)
-    x1b = torch.empty((M, C), dtype=ops.dtype16(), device=dev)
-    ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, residual=x, ldr=x.stride(0), out_f32=x1, ldo32=C,
-             out_bf16=x1b, ldo16=C, row_stats_out=st_mid)
-    h = torch.empty((M, pad8(pf.hidden)), dtype=ops.dtype16(), device=dev)
+    res_in = dict(residual=x, ldr=x.stride(0)) if x is not None else dict(residual_hi16=xb, residual_lo16=x_lo, ldr16=C)
+    x1b = torch.empty((M, C), dtype=d16, device=dev)
+    if split:
+        x1, x1l = None, torch.empty((M, C), dtype=d16, device=dev)
+        ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, out_bf16=x1b, ldo16=C, out_lo16=x1l, row_stats_out=st_mid,
+                 **res_in)
+        res_mid = dict(residual_hi16=x1b, residual_lo16=x1l, ldr16=C)
+    else:
+        x1 = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, out_f32=x1, ldo32=C, out_bf16=x1b, ldo16=C,
+                 row_stats_out=st_mid, **res_in)
+        res_mid = dict(residual=x1, ldr=C)
+    h = torch.empty((M, pad8(pf.hidden)), dtype=d16, device=dev)
     ops.gemm(x1b, pf.w1, M=M, N=pf.hidden, K=C, bias=pf.b1, act=1, out_bf16=h, ldo16=h.stride(0),
              row_stats_in=st_mid, ln_colsum=pf.cs_1, ln_channels=C, ln_eps=pf.eps2, reverse_tiles=REVERSE_FC1)
-    y = torch.empty((M, C), dtype=torch.float32, device=dev)
-    yb = torch.empty((M, C), dtype=ops.dtype16(), device=dev) if st_out is not None else None
     # fc2 walks its tiles back to front: fc1 and the out-projection wrote h and x1 front to back, so their last rows are
     # what L2 still holds; and the rows fc2 writes last (the first ones) are where the next QKV projection starts
-    ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, residual=x1, ldr=C, out_f32=y, ldo32=C,
-             out_bf16=yb, ldo16=C if yb is not None else 0, row_stats_out=st_out, reverse_tiles=REVERSE_FC2)
-    return y, yb
+    if split_out:
+        yb = torch.empty((M, C), dtype=d16, device=dev)
+        yl = torch.empty((M, C), dtype=d16, device=dev)
+        ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, out_bf16=yb, ldo16=C, out_lo16=yl, row_stats_out=st_out,
+                 reverse_tiles=REVERSE_FC2, **res_mid)
+        return None, yb, yl
+    y = torch.empty((M, C), dtype=torch.float32, device=dev)
+    yb = torch.empty((M, C), dtype=d16, device=dev) if st_out is not None else None
+    ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, out_f32=y, ldo32=C,
+             out_bf16=yb, ldo16=C if yb is not None else 0, row_stats_out=st_out, reverse_tiles=REVERSE_FC2, **res_mid)
+    return y, yb, None
 
 
 def _versions(module):

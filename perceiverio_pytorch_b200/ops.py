@@ -49,6 +49,11 @@ def stats_parts(m: int, n: int) -> int:
     return int(_lib.load().pio_gemm_stats_parts(m, n))
 
 
+def gemm_uses_pair_kernel(m: int, n: int) -> bool:
+    """Whether pio_gemm_bf16 runs an M x N problem (batch 1, default tuning fields) on the CTA-pair kernel."""
+    return _lib.load().pio_gemm_pair_kernel(m, n) == 1
+
+
 def empty_row_stats(m: int, n: int, device, parts: int = 0) -> torch.Tensor:
     """[m, parts, 2] fp32 buffer for pio_gemm_args.row_stats_out (every slot is written: no zeroing); parts defaults to
     stats_parts(m, n) — pass 2 * ceil(n / T) when the GEMM is forced to a tile width T."""
@@ -159,9 +164,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
          tile_n: int = 0, max_ctas: int = 0, cluster_m: Optional[int] = None, kernel: Optional[int] = None,
          row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None,
          ln_colsum: Optional[torch.Tensor] = None, ln_channels: int = 0, ln_eps: float = 1e-5,
-         reverse_tiles: bool = False, row_stats_parts: int = 0) -> None:
+         reverse_tiles: bool = False, row_stats_parts: int = 0,
+         out_lo16: Optional[torch.Tensor] = None, residual_hi16: Optional[torch.Tensor] = None,
+         residual_lo16: Optional[torch.Tensor] = None, ldr16: int = 0) -> None:
     """Raw batched GEMM + epilogue; see pio_gemm_args in include/pio_b200.h."""
-    _need_cuda(A, B, bias, residual, out_f32, out_bf16)
+    _need_cuda(A, B, bias, residual, out_f32, out_bf16, out_lo16, residual_hi16, residual_lo16)
     assert A.dtype == B.dtype and A.dtype in (BF16, torch.float16)
     lda = A.stride(-2) if lda is None else lda
     ldb = B.stride(-2) if ldb is None else ldb
@@ -176,7 +183,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, batch: int
                       GEMM_CLUSTER_M if cluster_m is None else cluster_m,
                       GEMM_KERNEL if kernel is None else kernel,
                       _ptr(row_stats_out), _ptr(row_stats_in), _ptr(ln_colsum), ln_channels, ln_eps,
-                      1 if reverse_tiles else 0, row_stats_parts, 1 if A.dtype == torch.float16 else 0)
+                      1 if reverse_tiles else 0, row_stats_parts, 1 if A.dtype == torch.float16 else 0,
+                      _ptr(out_lo16), _ptr(residual_hi16), _ptr(residual_lo16), ldr16)
     _lib.check(_lib.load().pio_gemm_bf16(C.byref(a), _stream()), "pio_gemm_bf16")
 
 

@@ -162,11 +162,16 @@ class PerceiverEncoder(nn.Module):
         z, zb = self.cross_attend._forward_factored(latents, inputs, key_mask=key_mask, row_keep=row_keep,
                                                     shard=self.key_shard, want_bf16_out=True, stats_out=stats[0])
         x = z.view(M, C)
+        # large towers (every producer GEMM on the CTA-pair kernel) carry the stream between their GEMMs as a 16-bit
+        # (hi, lo) pair; the tower's input and its output — the latents the caller gets — stay fp32
+        split = engine.SPLIT_STREAM and ops.gemm_uses_pair_kernel(M, C)
+        x_lo = None
         for i in range(len(layers)):
             pf = fused[i % len(self.self_attends)]
             last = i == len(layers) - 1
-            x, zb = engine.self_attention_block_fused(pf, x, zb, stats[2 * i], B=B, N=N, st_mid=stats[2 * i + 1],
-                                                      st_out=None if last else stats[2 * i + 2])
+            x, zb, x_lo = engine.self_attention_block_fused(pf, x, zb, stats[2 * i], B=B, N=N, st_mid=stats[2 * i + 1],
+                                                            st_out=None if last else stats[2 * i + 2], x_lo=x_lo,
+                                                            split=split, split_out=split and not last)
         if (pver is not None and (self._fuse_ln_checked is None or self._fuse_ln_checked[0] != pver)
                 and not torch.cuda.is_current_stream_capturing()):
             s = stats[:2 * len(layers)].sum(2)                       # [states, M, 2]: (sum, sum of squares) per row

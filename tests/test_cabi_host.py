@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.pio_abi_version() == 14
+    assert lib.pio_abi_version() == 15
 
 
 @pytest.mark.parametrize("struct,cname", [("LayerNormArgs", "pio_layernorm_args"), ("GemmArgs", "pio_gemm_args"),

@@ -396,3 +396,53 @@ def test_linear_f32_with_second_16bit_operand(fp16):
     y = ops.linear_f32(x, w, b, x2=x2, w2=w2)
     ref = (x.double() @ w.double().t() + x2[:, :K2].double() @ w2.double().t() + b.double()).float()
     assert _rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("f16", [False, True])
+def test_gemm_pair_kernel_split_residual_stream(f16):
+    """pio_gemm_args.out_lo16 / residual_hi16 / residual_lo16: the fp32 residual stream of the large towers as a pair of
+    16-bit arrays (value = hi + lo).  The pair output equals the fp32 output to 2^-16 (bf16) / 2^-21 (fp16) per element,
+    hi is exactly the raw 16-bit copy, the statistics are those of the fp32 values, and a pair residual input gives
+    the same result as its fp32 sum."""
+    from perceiverio_pytorch_b200 import engine, ops
+    with engine.precision_scope("fp16" if f16 else "bf16"):
+        d16 = ops.dtype16()
+        M, N, K = 2048 + 96, 1024, 512          # a partial last row tile
+        assert ops.gemm_uses_pair_kernel(M, N)
+        torch.manual_seed(3)
+        A = torch.randn(M, K, device="cuda").to(d16)
+        W = (torch.randn(N, K, device="cuda") * K ** -0.5).to(d16)
+        bias = torch.randn(N, device="cuda")
+        x = torch.randn(M, N, device="cuda") * 3.0
+        parts = ops.stats_parts(M, N)
+        y32 = torch.empty(M, N, device="cuda")
+        yraw = torch.empty(M, N, device="cuda", dtype=d16)
+        st32 = ops.empty_row_stats(M, N, "cuda", parts)
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual=x, ldr=N, out_f32=y32, ldo32=N, out_bf16=yraw, ldo16=N,
+                 row_stats_out=st32)
+        # pair output from an fp32 residual
+        hi = torch.empty(M, N, device="cuda", dtype=d16)
+        lo = torch.empty(M, N, device="cuda", dtype=d16)
+        st = ops.empty_row_stats(M, N, "cuda", parts)
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual=x, ldr=N, out_bf16=hi, ldo16=N, out_lo16=lo, row_stats_out=st)
+        assert torch.equal(hi, yraw)
+        assert torch.equal(st, st32)
+        tol = 2.0 ** (-20 if f16 else -15)
+        err = ((hi.float() + lo.float()) - y32).abs().max() / y32.abs().max()
+        assert err <= tol, err
+        # pair residual in, fp32 out: the same as the fp32 residual hi + lo
+        xs = hi.float() + lo.float()
+        z_ref = torch.empty(M, N, device="cuda")
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual=xs, ldr=N, out_f32=z_ref, ldo32=N)
+        z = torch.empty(M, N, device="cuda")
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_f32=z, ldo32=N)
+        assert (z - z_ref).abs().max() <= 1e-6 * z_ref.abs().max()
+        # pair in, pair out, back to front
+        hi2 = torch.empty(M, N, device="cuda", dtype=d16)
+        lo2 = torch.empty(M, N, device="cuda", dtype=d16)
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_bf16=hi2, ldo16=N,
+                 out_lo16=lo2, reverse_tiles=True)
+        assert ((hi2.float() + lo2.float()) - z_ref).abs().max() <= tol * z_ref.abs().max()
+        # the single-CTA kernel does not implement the pair stream: it must say so
+        with pytest.raises(RuntimeError, match="CTA-pair kernel"):
+            ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual=x, ldr=N, out_bf16=hi, ldo16=N, out_lo16=lo, kernel=1)

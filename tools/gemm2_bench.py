@@ -16,6 +16,9 @@ with torch.inference_mode():
     st = ops.empty_row_stats(M, C, dev)
     out = {}
     out["producer_res_f32_raw_stats"] = chain_time(lambda i: ops.gemm(a[i & 1], w[i % 4], M=M, N=C, K=C, bias=b, residual=x[i & 1], ldr=C, out_f32=y32[i & 1], ldo32=C, out_bf16=y16[i & 1], ldo16=C, row_stats_out=st), 20)
+    hi = [torch.empty(M, C, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    lo = [torch.empty(M, C, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    out["producer_pair_in_pair_out_stats"] = chain_time(lambda i: ops.gemm(a[i & 1], w[i % 4], M=M, N=C, K=C, bias=b, residual_hi16=hi[i & 1], residual_lo16=lo[i & 1], ldr16=C, out_bf16=hi[1 - (i & 1)], ldo16=C, out_lo16=lo[1 - (i & 1)], row_stats_out=st), 20)
     out["producer_res_f32"] = chain_time(lambda i: ops.gemm(a[i & 1], w[i % 4], M=M, N=C, K=C, bias=b, residual=x[i & 1], ldr=C, out_f32=y32[i & 1], ldo32=C), 20)
     out["producer_f32_only"] = chain_time(lambda i: ops.gemm(a[i & 1], w[i % 4], M=M, N=C, K=C, bias=b, out_f32=y32[i & 1], ldo32=C), 20)
     out["consumer_fc1_gelu"] = chain_time(lambda i: ops.gemm(a[i & 1], w[i % 4], M=M, N=C, K=C, bias=b, act=1, out_bf16=y16[i & 1], ldo16=C), 20)
