@@ -67,6 +67,22 @@ enum { G2_BF16 = 0, G2_F32 = 1 };
 #define G2_F32_OUT_SLOTS (G2_F32_CHUNK == 32 ? 1 : 2)
 #endif
 
+// Developer aid (compiled out unless -DPIO_GEMM2_TRACE): warp 4 of CTA 0 records (tag, clock64) pairs of its epilogue;
+// pio_debug_gemm2_trace() copies them out (tools/trace_gemm2.py).
+#ifdef PIO_GEMM2_TRACE
+__device__ unsigned long long g_gemm2_trace[1024 * 2];
+#define G2T(tag)                                                                       \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && warp == 4 && lane == 0 && g2n < 1024) {                     \
+      g_gemm2_trace[g2n * 2] = (unsigned long long)(tag);                              \
+      g_gemm2_trace[g2n * 2 + 1] = (unsigned long long)clock64();                      \
+      ++g2n;                                                                           \
+    }                                                                                  \
+  } while (0)
+#else
+#define G2T(tag)
+#endif
+
 template <int KIND>
 struct Gemm2Cfg {
   static constexpr int BM = 128;       // rows per CTA (256 per pair)
@@ -84,7 +100,8 @@ struct Gemm2Cfg {
   static constexpr int OUT_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 2;
   // fused-LayerNorm producer: raw bf16 copy of the fp32 output, 32 rows x 16 columns (32-byte rows, no swizzle)
   static constexpr int RAW_SLOT_BYTES = 32 * G2_F32_CHUNK * 2;
-  static constexpr int RAW_SLOTS = (KIND == G2_F32) ? G2_F32_OUT_SLOTS : 0;
+  // (with the pair stream the fp32 slot holds two lo buffers, so two raw (hi) slots make that output path double-buffered)
+  static constexpr int RAW_SLOTS = (KIND == G2_F32) ? (G2_F32_OUT_SLOTS > 2 ? G2_F32_OUT_SLOTS : 2) : 0;
   static constexpr int WARP_EPI_BYTES = (RES_SLOTS + OUT_SLOTS) * SLOT_BYTES + RAW_SLOTS * RAW_SLOT_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
   static constexpr int BAR_BYTES = 512;
@@ -114,6 +131,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // the shuffle makes the warp index provably warp-uniform, so the role code can use the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+#ifdef PIO_GEMM2_TRACE
+  int g2n = 0;
+#endif
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pio_gemm2_kernel: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
@@ -229,30 +249,39 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
 
-    // residual prefetch cursor (lane 0): the stream of (tile, chunk) boxes this warp will consume, RES_SLOTS ahead
-    int pf_t = pair_id, pf_c = 0;
+    // residual prefetch cursor: the stream of (tile, chunk) boxes this warp will consume, RES_SLOTS ahead.  Run by the
+    // whole warp with one elected lane per TMA instruction (inside an `if (lane == 0)` region the four copies of a chunk
+    // and the cursor arithmetic cost 800 - 1900 clk of a 4100-clk chunk); the tile coordinates — three integer
+    // divisions — are computed once per tile, not per chunk
+    int pf_t = pair_id, pf_c = 0, pf_row = 0, pf_col = 0, pf_z = 0;
     uint32_t pf_idx = 0;
     auto issue_res = [&]() {
       if (pf_t >= total_tiles) return;
-      const int t = p.reverse ? total_tiles - 1 - pf_t : pf_t;
-      const int nt = t % p.tiles_n;
-      const int mp = (t / p.tiles_n) % p.m_pairs;
-      const int z = t / (p.tiles_n * p.m_pairs);
-      const int row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
-      const int col = nt * Cfg::BN + half * 128 + pf_c * CHUNK_COLS;
-      const uint32_t slot = pf_idx % (uint32_t)RS;
-      mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
-      if (KIND == G2_F32 && p.res_split) {
-        // hi and lo boxes (32 rows x CHUNK_COLS 16-bit values each) fill the two halves of the fp32-sized slot
-        tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, 0);
-        tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::SLOT_BYTES / 2, &tmap_res_lo, &my_res_full[slot], col, row, 0);
-      } else {
-        tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, row, p.r_bcast ? 0 : z);
+      if (pf_c == 0) {
+        const int t = p.reverse ? total_tiles - 1 - pf_t : pf_t;
+        const int nt = t % p.tiles_n;
+        const int mp = (t / p.tiles_n) % p.m_pairs;
+        pf_z = p.r_bcast ? 0 : t / (p.tiles_n * p.m_pairs);
+        pf_row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
+        pf_col = nt * Cfg::BN + half * 128;
       }
+      const int col = pf_col + pf_c * CHUNK_COLS;
+      const uint32_t slot = pf_idx % (uint32_t)RS;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
+        if (KIND == G2_F32 && p.res_split) {
+          // hi and lo boxes (32 rows x CHUNK_COLS 16-bit values each) fill the two halves of the fp32-sized slot
+          tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, pf_row, 0);
+          tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::SLOT_BYTES / 2, &tmap_res_lo, &my_res_full[slot], col, pf_row, 0);
+        } else {
+          tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, pf_row, pf_z);
+        }
+      }
+      __syncwarp();
       ++pf_idx;
       if (++pf_c == CHUNKS) { pf_c = 0; pf_t += num_pairs; }
     };
-    if (has_res && lane == 0) {
+    if (has_res) {
       for (int i = 0; i < RS; ++i) issue_res();
     }
     uint32_t use_idx = 0;
@@ -283,7 +312,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;   // producer side: this row's partial statistics over the tile
+      G2T(100);
       mbar_wait(&tmem_full[acc], acc_phase);
+      G2T(101);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
@@ -313,6 +344,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, row_bias);
         }
+        G2T(310 + c);
         if (c == CHUNKS - 1) {
           // this warp has read its whole share of the accumulator: hand the TMEM buffer back to the MMA issuer
           tc_fence_before();
@@ -378,10 +410,12 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < CHUNK_COLS; ++j) v[j] = gelu_erf(v[j]);
         }
+        G2T(320 + c);
         if constexpr (KIND == G2_F32) {
           if (has_res) {
             const uint32_t slot = use_idx % (uint32_t)RS;
             mbar_wait(&my_res_full[slot], (use_idx / (uint32_t)RS) & 1u);
+            G2T(330 + c);
             const uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
             if (p.res_split) {
               // value = hi + lo, two 16-bit rows of CHUNK_COLS * 2 bytes each
@@ -423,10 +457,22 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 st_sq = fmaf(v[j], v[j], st_sq);
               }
           }
-          uint8_t* slot_out = my_out + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::SLOT_BYTES;
-          uint8_t* slot_raw = my_raw + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::RAW_SLOT_BYTES;
-          if (lane == 0) bulk_wait_read<Cfg::OUT_SLOTS - 1>();   // the stores issued OUT_SLOTS chunks ago used these slots
+          G2T(340 + c);
+          // staging slots: OUT_SLOTS fp32 buffers, or — pair stream — twice as many half-sized lo buffers
+          uint8_t* slot_out;
+          uint8_t* slot_raw;
+          if (p.out_split) {
+            constexpr uint32_t NS = 2 * Cfg::OUT_SLOTS < Cfg::RAW_SLOTS ? 2 * Cfg::OUT_SLOTS : Cfg::RAW_SLOTS;
+            slot_out = my_out + (use_idx % NS) * (Cfg::SLOT_BYTES / 2);
+            slot_raw = my_raw + (use_idx % NS) * Cfg::RAW_SLOT_BYTES;
+            if (elect_one()) bulk_wait_read<NS - 1>();
+          } else {
+            slot_out = my_out + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::SLOT_BYTES;
+            slot_raw = my_raw + (use_idx % (uint32_t)Cfg::OUT_SLOTS) * Cfg::RAW_SLOT_BYTES;
+            if (elect_one()) bulk_wait_read<Cfg::OUT_SLOTS - 1>();   // the stores issued OUT_SLOTS chunks ago used these slots
+          }
           __syncwarp();
+          G2T(350 + c);
           if (p.raw_bf16 != nullptr) {
             // 16-bit copy of the un-normalised row segment for the fused LayerNorm of the consumer: 32-byte rows (no
             // swizzle) with 16-column chunks, 64-byte rows (SWIZZLE_64B) with 32-column chunks
@@ -461,18 +507,22 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               *reinterpret_cast<float4*>(slot_out + (CHUNK_COLS == 32 ? sw128_offset(lane, j) : sw64_offset(lane, j))) =
                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          G2T(360 + c);
           fence_proxy_async_smem();
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
-          if (lane == 0) {
+          G2T(370 + c);
+          if (elect_one()) {
             tma_store_3d(&tmap_out, slot_out, col0, row0, z);
             if (p.raw_bf16 != nullptr) tma_store_3d(&tmap_raw, slot_raw, col0, row0, z);
             bulk_commit();
-            if (has_res) issue_res();   // refills the residual slot that was just consumed
           }
+          __syncwarp();
+          if (has_res) issue_res();   // refills the residual slot that was just consumed
+          G2T(380 + c);
           ++use_idx;
         } else {
           uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
-          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
+          if (elect_one()) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
           __syncwarp();
           // one uniform branch per 64-value chunk picks the conversion (no per-element select in the issue stream)
           auto stage_out = [&](auto f16tag) {
@@ -491,10 +541,11 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           else stage_out(std::false_type{});
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_3d(&tmap_out, slot_out, col0, row0, z);
             bulk_commit();
           }
+          __syncwarp();
           ++use_idx;
         }
       }
@@ -506,7 +557,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int s = 2 * p.tiles_n; s < p.stats_parts; ++s) slots[s] = make_float2(0.f, 0.f);
       }
     }
-    if (lane == 0) bulk_wait_read<0>();   // staging slots must outlive the stores that read them
+    if (elect_one()) bulk_wait_read<0>();   // staging slots must outlive the stores that read them (same thread as the commits)
   }
 
   __syncwarp();
@@ -640,6 +691,18 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;
 }
+
+}  // namespace pio
+#ifdef PIO_GEMM2_TRACE
+extern "C" int pio_debug_gemm2_trace(unsigned long long* out) {   // out: 1024 * 2 words; clears the device buffer
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, pio::g_gemm2_trace, sizeof(pio::g_gemm2_trace));
+  static unsigned long long zeros[1024 * 2];
+  cudaMemcpyToSymbol(pio::g_gemm2_trace, zeros, sizeof(zeros));
+  return 0;
+}
+#endif
+namespace pio {
 
 // Whether the CTA-pair kernel can run this problem (layout / alignment rules of its TMA epilogue).
 bool gemm2_eligible(const pio_gemm_args* a) {

@@ -1,0 +1,59 @@
+"""Developer aid: build the library with -DPIO_GEMM2_TRACE, run one producer GEMM of the bench tower (pair stream in /
+out, raw copy, row statistics) and print the epilogue timeline of warp 4 of CTA 0 (clock64 ticks): per 32-column chunk
+c: 310+c accumulator in registers, 320+c bias / activation done, 330+c residual arrived, 340+c residual added + statistics,
+350+c staging slot free, 360+c staging written, 370+c fence + warp sync, 380+c stores issued.
+Usage (GPU box):  python tools/trace_gemm2.py"""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+if __name__ == "__main__":
+    if os.environ.get("PIO_TRACE_CHILD") != "1":
+        env = dict(os.environ, PIO_NVCC_EXTRA="-DPIO_GEMM2_TRACE", PIO_TRACE_CHILD="1")
+        subprocess.run([sys.executable, "-m", "perceiverio_pytorch_b200.build", "--force"], check=True, env=env, cwd=ROOT)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, cwd=ROOT)
+        subprocess.run([sys.executable, "-m", "perceiverio_pytorch_b200.build", "--force"], check=True, cwd=ROOT)
+        sys.exit(r.returncode)
+    import torch
+    from perceiverio_pytorch_b200 import _lib, ops
+    M, C = 32768, 1024
+    dev = "cuda"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "pair"
+    a = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    w = (0.02 * torch.randn(C, C, device=dev)).to(torch.bfloat16)
+    b = torch.zeros(C, device=dev)
+    x = torch.randn(M, C, device=dev)
+    hi = [torch.randn(M, C, device=dev).to(torch.bfloat16) for _ in range(2)]
+    lo = [(0.01 * torch.randn(M, C, device=dev)).to(torch.bfloat16) for _ in range(2)]
+    y32 = torch.empty(M, C, device=dev)
+    st = ops.empty_row_stats(M, C, dev)
+    lib = _lib.load()
+    lib.pio_debug_gemm2_trace.argtypes = [ctypes.c_void_p]
+    buf = (ctypes.c_ulonglong * (1024 * 2))()
+
+    def launch():
+        if mode == "pair":
+            ops.gemm(a, w, M=M, N=C, K=C, bias=b, residual_hi16=hi[0], residual_lo16=lo[0], ldr16=C, out_bf16=hi[1], ldo16=C,
+                     out_lo16=lo[1], row_stats_out=st)
+        else:
+            ops.gemm(a, w, M=M, N=C, K=C, bias=b, residual=x, ldr=C, out_f32=y32, ldo32=C, out_bf16=hi[1], ldo16=C,
+                     row_stats_out=st)
+    with torch.inference_mode():
+        for _ in range(3):
+            launch()
+        torch.cuda.synchronize()
+        lib.pio_debug_gemm2_trace(buf)
+        launch()
+        torch.cuda.synchronize()
+        lib.pio_debug_gemm2_trace(buf)
+    ev = [(buf[2 * i], buf[2 * i + 1]) for i in range(1024) if buf[2 * i]]
+    t0 = ev[0][1]
+    print(f"producer GEMM {M}x{C}x{C} [{mode}]: epilogue of warp 4, CTA 0 (tag, clk since the first tag, delta)")
+    prev = t0
+    for tag, clk in ev[:120]:
+        print(f"  {tag:4d} {clk - t0:9d} {clk - prev:7d}")
+        prev = clk
