@@ -631,7 +631,7 @@ def run_gpu_arm(args):
             import bench_configs
             for name in ("language", "flow", "multimodal"):
                 r = bench_configs.measure_config(name, iters=10, eager=False)
-                result["other_configs"][name] = {k: r[k] for k in ("B", "inputs", "latents", "queries", "ms_graph", "tflops",
+                result["other_configs"][name] = {k: r[k] for k in ("B", "inputs", "latents", "queries", "precision", "ms_graph", "tflops",
                                                                    "frac_of_sustained_bf16_peak", "samples_per_s_graph",
                                                                    "launches_per_forward")}
         except Exception as ex:
