@@ -660,7 +660,7 @@ extern "C" int pio_gemm_stats_parts(int32_t M, int32_t N) {
   DeviceInfo dev;
   int sm = 148;
   if (get_device_info(&dev) == PIO_OK && dev.sm_count > 0) sm = dev.sm_count;
-  if (sm % 2 == 0 && auto_wants_pair(M, N, 1, sm)) return 2 * ((N + 255) / 256);
+  if (sm % 2 == 0 && auto_wants_pair(M, N, 1, sm)) return 4 * ((N + 255) / 256);   // the stream kernel's 64-column slices
   const int bn = auto_tile_n(M, N, 1, sm);
   return 2 * ((N + bn - 1) / bn);
 }

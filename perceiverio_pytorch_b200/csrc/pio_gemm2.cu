@@ -47,9 +47,16 @@ struct Gemm2Params {
   const float* row_stats_in;     // [M][stats_parts][2] of the A operand's rows
   const float* ln_colsum;        // [N]
   float ln_inv_c, ln_eps;
+  // L2 eviction priorities ("what L2 holds"): the 16-bit hi half of the residual stream of a large
+  // tower (67 MB at batch 64) is read four times and rewritten twice per layer — it is kept (evict_last) while the
+  // streams that are produced once and consumed once by the next kernel (QKV, attention output, MLP hidden) pass through
+  uint64_t hint_a, hint_b, hint_out, hint_res_hi, hint_res_lo, hint_out_hi, hint_out_lo;
 };
 
 enum { G2_BF16 = 0, G2_F32 = 1 };
+#ifndef PIO_L2_HINTS_DEFAULT
+#define PIO_L2_HINTS_DEFAULT 0
+#endif
 
 // fp32-output kind: operand stages vs depth of the per-warp residual prefetch ring (both live in shared memory)
 // G2_F32_CHUNK: columns per epilogue chunk (16: 64-byte fp32 rows per TMA box, 32: 128-byte rows — half the TMA row
@@ -73,14 +80,25 @@ enum { G2_BF16 = 0, G2_F32 = 1 };
 __device__ unsigned long long g_gemm2_trace[1024 * 2];
 #define G2T(tag)                                                                       \
   do {                                                                                 \
-    if (blockIdx.x == 0 && warp == 4 && lane == 0 && g2n < 1024) {                     \
+    if (blockIdx.x == 0 && warp == 4 && lane == 0 && g2n < 512) {                     \
       g_gemm2_trace[g2n * 2] = (unsigned long long)(tag);                              \
       g_gemm2_trace[g2n * 2 + 1] = (unsigned long long)clock64();                      \
       ++g2n;                                                                           \
     }                                                                                  \
   } while (0)
+// ... and the MMA issuer of CTA 0 (second half of the buffer): 500 before / 501 after the accumulator-free wait, 502 all
+// MMAs of the tile issued
+#define G2TM(tag)                                                                      \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && lane == 0 && g2n < 512) {                                   \
+      g_gemm2_trace[(512 + g2n) * 2] = (unsigned long long)(tag);                      \
+      g_gemm2_trace[(512 + g2n) * 2 + 1] = (unsigned long long)clock64();              \
+      ++g2n;                                                                           \
+    }                                                                                  \
+  } while (0)
 #else
 #define G2T(tag)
+#define G2TM(tag)
 #endif
 
 template <int KIND>
@@ -194,8 +212,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // both CTAs' bytes are credited to the leader's barrier, which expects the pair's total
           if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const uint32_t leader_bar = mapa_u32(&full_bar[stage], 0);
-          tma_load_3d_2cta(sa, &tmap_a, leader_bar, kc * Cfg::BK, m0, za);
-          tma_load_3d_2cta(sb, &tmap_b, leader_bar, kc * Cfg::BK, n0, zb);
+          tma_load_3d_2cta(sa, &tmap_a, leader_bar, kc * Cfg::BK, m0, za, p.hint_a);
+          tma_load_3d_2cta(sb, &tmap_b, leader_bar, kc * Cfg::BK, n0, zb, p.hint_b);
         }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -271,8 +289,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
         if (KIND == G2_F32 && p.res_split) {
           // hi and lo boxes (32 rows x CHUNK_COLS 16-bit values each) fill the two halves of the fp32-sized slot
-          tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, pf_row, 0);
-          tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::SLOT_BYTES / 2, &tmap_res_lo, &my_res_full[slot], col, pf_row, 0);
+          tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, pf_row, 0, p.hint_res_hi);
+          tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::SLOT_BYTES / 2, &tmap_res_lo, &my_res_full[slot], col, pf_row, 0, p.hint_res_lo);
         } else {
           tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res, &my_res_full[slot], col, pf_row, pf_z);
         }
@@ -512,8 +530,8 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();   // all lanes have written the staging slot and finished reading the residual slot
           G2T(370 + c);
           if (elect_one()) {
-            tma_store_3d(&tmap_out, slot_out, col0, row0, z);
-            if (p.raw_bf16 != nullptr) tma_store_3d(&tmap_raw, slot_raw, col0, row0, z);
+            tma_store_3d_hint(&tmap_out, slot_out, col0, row0, z, p.out_split ? p.hint_out_lo : p.hint_out);
+            if (p.raw_bf16 != nullptr) tma_store_3d_hint(&tmap_raw, slot_raw, col0, row0, z, p.hint_out_hi);
             bulk_commit();
           }
           __syncwarp();
@@ -542,7 +560,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            tma_store_3d(&tmap_out, slot_out, col0, row0, z);
+            tma_store_3d_hint(&tmap_out, slot_out, col0, row0, z, p.hint_out);
             bulk_commit();
           }
           __syncwarp();
@@ -568,6 +586,368 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// pio_gemm2_stream_kernel: the producer GEMMs of a large fused tower (out-projection, fc2) on the 16-bit (hi, lo)
+// residual stream — the residual comes in as two 16-bit arrays, the sum leaves as two 16-bit arrays (in place if the
+// caller passes the same arrays: every element is read and rewritten by the same epilogue warp) plus the per-row
+// LayerNorm statistics.  Same mainloop as pio_gemm2_kernel; the epilogue differs in three ways:
+//   * the residual slot (hi | lo, 2 + 2 KB) is overwritten in place by the output (hi | lo): every lane reads and
+//     writes only its own row, so there is no hazard and no separate staging buffer.  Two slots per warp give a
+//     residual prefetch one chunk ahead *and* a store in flight behind, in 8 KB per warp instead of 12 — which buys the
+//     fifth operand stage;
+//   * the bias row is requested before the accumulator load, the statistics run in independent chains;
+//   * EW_ = 8 or 16 epilogue warps (32 rows x 128 or 64 columns of the tile each).  A clock64 trace of the 8-warp general
+//     kernel showed ~16 400 clk of dependent epilogue chain per warp and tile against 8 200 clk of tensor time, which
+//     suggested sixteen warps; with them the issuer never waits for an accumulator (tools/trace_gemm2.py, tags 500-502)
+//     and the kernel is no faster: what the launch costs is set by the bytes it moves, not by who waits for whom
+//     ("additive").
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator, warp 3 idle, warps 4.. epilogue
+// (warp w: TMEM lanes 32*(w%4).., column slice (w-4)/4 of the 256-column tile).
+// ------------------------------------------------------------------------------------------------
+template <int EW_, int SLOTS_, int STAGES_>
+struct Gemm2StreamCfg {
+  static constexpr int BM = 128, BN = 256, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int EPI_WARPS = EW_;            // 8: 128-column slices, 16: 64-column slices
+  static constexpr int PARTS = EPI_WARPS / 4;
+  static constexpr int PART_COLS = 256 / PARTS;
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr int CHUNK = 32;                       // columns per epilogue step
+  static constexpr int HALF_BYTES = 32 * CHUNK * 2;      // one 16-bit box: 32 rows x 64 bytes (SWIZZLE_64B)
+  static constexpr int SLOT_BYTES = 2 * HALF_BYTES;      // hi | lo
+  static constexpr int SLOTS = SLOTS_;
+  static constexpr int EPI_BYTES = EPI_WARPS * SLOTS * SLOT_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <int EW_, int SLOTS_, int STAGES_>
+__global__ void __launch_bounds__((Gemm2StreamCfg<EW_, SLOTS_, STAGES_>::THREADS), 1)
+pio_gemm2_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ CUtensorMap tmap_out_lo, const __grid_constant__ CUtensorMap tmap_out_hi,
+                        const __grid_constant__ CUtensorMap tmap_res_hi, const __grid_constant__ CUtensorMap tmap_res_lo,
+                        const Gemm2Params p) {
+  using Cfg = Gemm2StreamCfg<EW_, SLOTS_, STAGES_>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* epi_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + Cfg::EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_empty + 2;              // [EPI_WARPS][SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + Cfg::EPI_WARPS * Cfg::SLOTS);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+#ifdef PIO_GEMM2_TRACE
+  int g2n = 0;
+#endif
+  const uint32_t crank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_tiles = p.m_pairs * p.tiles_n;
+  const int num_k_chunks = (p.K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out_lo);
+    tma_prefetch_desc(&tmap_out_hi);
+    tma_prefetch_desc(&tmap_res_hi);
+    tma_prefetch_desc(&tmap_res_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * Cfg::EPI_WARPS);
+    }
+    for (int i = 0; i < Cfg::EPI_WARPS * Cfg::SLOTS; ++i) mbar_init(&res_full[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int seq = pair_id; seq < total_tiles; seq += num_pairs) {
+      const int t = p.reverse ? total_tiles - 1 - seq : seq;
+      const int nt = t % p.tiles_n;
+      const int mp = t / p.tiles_n;
+      const int m0 = mp * 256 + (int)crank * Cfg::BM;
+      const int n0 = nt * Cfg::BN + (int)crank * (Cfg::BN / 2);
+      for (int kc = 0; kc < num_k_chunks; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t leader_bar = mapa_u32(&full_bar[stage], 0);
+          tma_load_3d_2cta(sa, &tmap_a, leader_bar, kc * Cfg::BK, m0, 0, p.hint_a);
+          tma_load_3d_2cta(sb, &tmap_b, leader_bar, kc * Cfg::BK, n0, 0, p.hint_b);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0) {
+      // ================= MMA issuer (leader CTA) =================
+      const uint32_t idesc = make_idesc_f16(256, Cfg::BN, idesc_fmt(p.fp16), 0, 0);
+      const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint32_t d_lo = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        G2TM(500);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        G2TM(501);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+        for (int kc = 0; kc < num_k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = d_lo + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (elect_one())
+              umma_ss_2cta_lh(d_tmem, a_lo + ks * 2, d_hi, b_lo + ks * 2, d_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+          }
+          if (elect_one()) umma_commit_2cta_mcast(&empty_bar[stage], 0x3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) umma_commit_2cta_mcast(&tmem_full[acc], 0x3);
+        G2TM(502);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= Epilogue (both CTAs) =================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int part = ew >> 2;                          // column slice of the tile
+    constexpr int CHUNKS = Cfg::PART_COLS / Cfg::CHUNK;
+    uint8_t* my = epi_base + ew * (Cfg::SLOTS * Cfg::SLOT_BYTES);
+    uint64_t* my_res_full = res_full + ew * Cfg::SLOTS;
+    const uint32_t tmem_empty_leader0 = mapa_u32(&tmem_empty[0], 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(&tmem_empty[1], 0);
+
+    // residual prefetch cursor over this warp's (tile, chunk) stream
+    int pf_t = pair_id, pf_c = 0, pf_row = 0, pf_col = 0;
+    uint32_t pf_idx = 0;
+    auto issue_res = [&]() {
+      if (pf_t >= total_tiles) return;
+      if (pf_c == 0) {
+        const int t = p.reverse ? total_tiles - 1 - pf_t : pf_t;
+        const int nt = t % p.tiles_n;
+        const int mp = t / p.tiles_n;
+        pf_row = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
+        pf_col = nt * Cfg::BN + part * Cfg::PART_COLS;
+      }
+      const int col = pf_col + pf_c * Cfg::CHUNK;
+      const uint32_t slot = pf_idx % (uint32_t)Cfg::SLOTS;
+      if (elect_one()) {
+        // the store that last used this slot (two chunks ago) must have finished reading it
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(&my_res_full[slot], Cfg::SLOT_BYTES);
+        tma_load_3d(my + slot * Cfg::SLOT_BYTES, &tmap_res_hi, &my_res_full[slot], col, pf_row, 0, p.hint_res_hi);
+        tma_load_3d(my + slot * Cfg::SLOT_BYTES + Cfg::HALF_BYTES, &tmap_res_lo, &my_res_full[slot], col, pf_row, 0, p.hint_res_lo);
+      }
+      __syncwarp();
+      ++pf_idx;
+      if (++pf_c == CHUNKS) { pf_c = 0; pf_t += num_pairs; }
+    };
+    issue_res();   // chunk 0; chunk g + 1 is requested at the start of chunk g
+
+    auto run = [&](auto f16tag) {
+      constexpr bool F16 = decltype(f16tag)::value;
+      uint32_t use_idx = 0;
+      int it = 0;
+      for (int seq = pair_id; seq < total_tiles; seq += num_pairs, ++it) {
+        const int t = p.reverse ? total_tiles - 1 - seq : seq;
+        const int nt = t % p.tiles_n;
+        const int mp = t / p.tiles_n;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        const int row0 = mp * 256 + (int)crank * Cfg::BM + quarter * 32;
+        const int row = row0 + lane;
+        float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+        const uint32_t t_row = tmem_base + acc * Cfg::BN + part * Cfg::PART_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int col0 = nt * Cfg::BN + part * Cfg::PART_COLS + c * Cfg::CHUNK;
+          const bool full = col0 + Cfg::CHUNK <= p.N;
+          // bias row segment: requested first, so that its latency hides behind the accumulator load
+          float4 bq[Cfg::CHUNK / 4];
+          if (p.bias_mode == 1 && full) {
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK / 4; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK / 4; ++j) {
+              bq[j].x = (p.bias_mode == 1 && col0 + 4 * j + 0 < p.N) ? __ldg(p.bias + col0 + 4 * j + 0) : 0.f;
+              bq[j].y = (p.bias_mode == 1 && col0 + 4 * j + 1 < p.N) ? __ldg(p.bias + col0 + 4 * j + 1) : 0.f;
+              bq[j].z = (p.bias_mode == 1 && col0 + 4 * j + 2 < p.N) ? __ldg(p.bias + col0 + 4 * j + 2) : 0.f;
+              bq[j].w = (p.bias_mode == 1 && col0 + 4 * j + 3 < p.N) ? __ldg(p.bias + col0 + 4 * j + 3) : 0.f;
+            }
+          }
+          if (c == 0) {
+            G2T(100);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            G2T(101);
+            tc_fence_after();
+          }
+          uint32_t r[Cfg::CHUNK];
+          tmem_ld32(t_row + c * Cfg::CHUNK, r);
+          tmem_wait_ld();
+          G2T(310 + c);
+          if (c == CHUNKS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+          }
+          if (Cfg::SLOTS > 1) issue_res();   // next chunk's residual into the other slot (its last store was committed a chunk ago)
+          G2T(320 + c);
+          float v[Cfg::CHUNK];
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 4; ++j) {
+            v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), p.alpha, bq[j].x);
+            v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bq[j].y);
+            v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, bq[j].z);
+            v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, bq[j].w);
+          }
+          const uint32_t slot = use_idx % (uint32_t)Cfg::SLOTS;
+          uint8_t* rs = my + slot * Cfg::SLOT_BYTES;
+          mbar_wait(&my_res_full[slot], (use_idx / (uint32_t)Cfg::SLOTS) & 1u);
+          G2T(330 + c);
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+            const uint32_t off = sw64_offset(lane, j);
+            const uint4 h = *reinterpret_cast<const uint4*>(rs + off);
+            const uint4 l = *reinterpret_cast<const uint4*>(rs + Cfg::HALF_BYTES + off);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float h0, h1, l0, l1;
+              unpack16x2<F16>(hw[k], h0, h1);
+              unpack16x2<F16>(lw[k], l0, l1);
+              v[8 * j + 2 * k] += h0 + l0;
+              v[8 * j + 2 * k + 1] += h1 + l1;
+            }
+          }
+          if (p.row_stats_out != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CHUNK; j += 2) {
+                s1[0] += v[j];
+                s1[1] += v[j + 1];
+                s2[0] = fmaf(v[j], v[j], s2[0]);
+                s2[1] = fmaf(v[j + 1], v[j + 1], s2[1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::CHUNK; ++j)
+                if (col0 + j < p.N) {
+                  s1[0] += v[j];
+                  s2[0] = fmaf(v[j], v[j], s2[0]);
+                }
+            }
+          }
+          G2T(340 + c);
+          // hi = round16(v) (the raw copy the next projection reads), lo = round16(v - hi): written over the residual
+          // this lane has just read (its own row only)
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+            const uint32_t off = sw64_offset(lane, j);
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              hw[k] = pack16x2<F16>(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+              float h0, h1;
+              unpack16x2<F16>(hw[k], h0, h1);
+              lw[k] = pack16x2<F16>(v[8 * j + 2 * k] - h0, v[8 * j + 2 * k + 1] - h1);
+            }
+            *reinterpret_cast<uint4*>(rs + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(rs + Cfg::HALF_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          G2T(360 + c);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_3d_hint(&tmap_out_hi, rs, col0, row0, 0, p.hint_out_hi);
+            tma_store_3d_hint(&tmap_out_lo, rs + Cfg::HALF_BYTES, col0, row0, 0, p.hint_out_lo);
+            bulk_commit();
+          }
+          __syncwarp();
+          if (Cfg::SLOTS == 1) issue_res();  // single slot: the next residual follows the store through the same buffer
+          G2T(380 + c);
+          ++use_idx;
+        }
+        if (p.row_stats_out != nullptr && row < p.M) {
+          // one slot per (row, column slice): plain stores, nothing to zero beforehand
+          float2* slots = reinterpret_cast<float2*>(p.row_stats_out) + (long long)row * p.stats_parts;
+          slots[nt * Cfg::PARTS + part] = make_float2(s1[0] + s1[1], s2[0] + s2[1]);
+          if (nt == 0 && part == 0)
+            for (int s = Cfg::PARTS * p.tiles_n; s < p.stats_parts; ++s) slots[s] = make_float2(0.f, 0.f);
+        }
+      }
+    };
+    if (p.fp16) run(std::true_type{});
+    else run(std::false_type{});
+    if (elect_one()) bulk_wait_read<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int EW_, int SLOTS_, int STAGES_>
+static int launch_gemm2_stream(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to_lo, const CUtensorMap& to_hi,
+                               const CUtensorMap& tr_hi, const CUtensorMap& tr_lo, const Gemm2Params& p, int pairs,
+                               const DeviceInfo& dev, cudaStream_t stream) {
+  using SCfg = Gemm2StreamCfg<EW_, SLOTS_, STAGES_>;
+  static PerDeviceOnce once_s;
+  const cudaError_t e2 = once_s.run(dev.device, [] {
+    return cudaFuncSetAttribute(pio_gemm2_stream_kernel<EW_, SLOTS_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SCfg::SMEM_BYTES);
+  });
+  if (e2 != cudaSuccess) return fail(PIO_ERR_CUDA, "cudaFuncSetAttribute(gemm2 stream) failed: %s", cudaGetErrorString(e2));
+  ProfileScope prof(KF_GEMM, 2.0 * p.M * p.N * (double)p.K, 8.0 * p.M * (double)p.N, stream);
+  PIO_CUDA_OK(launch_kernel(pio_gemm2_stream_kernel<EW_, SLOTS_, STAGES_>, dim3((unsigned)(pairs * 2), 1, 1),
+                            dim3(SCfg::THREADS, 1, 1), SCfg::SMEM_BYTES, stream, 2, ta, tb, to_lo, to_hi, tr_hi, tr_lo, p));
+  g_launch_count.fetch_add(1);
+  PIO_CUDA_OK(cudaGetLastError());
+  return PIO_OK;
 }
 
 template <int KIND>
@@ -667,6 +1047,25 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   p.ln_colsum = a->ln_colsum;
   p.ln_inv_c = a->ln_channels > 0 ? 1.0f / (float)a->ln_channels : 0.f;
   p.ln_eps = a->ln_eps;
+  {
+    // PIO_L2_HINTS: bit mask of the policies below (0: every access with the default priority)
+    static const int use_hints = [] { const char* e = getenv("PIO_L2_HINTS"); return e ? atoi(e) : PIO_L2_HINTS_DEFAULT; }();
+    p.hint_a = p.hint_b = p.hint_out = p.hint_res_hi = p.hint_res_lo = p.hint_out_hi = p.hint_out_lo = kEvictNormal;
+    // only the towers whose stream does not fit L2 next to their other arrays need a policy at all
+    const bool big = (double)a->M * a->N * 2.0 >= 32e6 || (double)a->M * a->K * 2.0 >= 32e6;
+    if (use_hints && big && a->batch == 1) {
+      if (use_hints & 1) p.hint_b = kEvictLast;                // weights: a few MB, read by every CTA pair
+      if (p.row_stats_in != nullptr) {                         // fused-LayerNorm consumer: A is the hi half of the stream
+        if (use_hints & 2) p.hint_a = kEvictLast;
+        if (use_hints & 4) p.hint_out = kEvictFirst;           // QKV / MLP hidden: read once by the next kernel
+      }
+      if (p.out_split || p.res_split) {                        // producer on the (hi, lo) stream
+        if (use_hints & 8) p.hint_a = kEvictFirst;             // attention output / MLP hidden: this is its only read
+        if (use_hints & 2) p.hint_res_hi = p.hint_out_hi = kEvictLast;
+        if (use_hints & 16) p.hint_res_lo = p.hint_out_lo = kEvictFirst;   // lo is read here and overwritten at once
+      }
+    }
+  }
   static const int b_swap = [] { const char* e = getenv("PIO_GEMM2_BSWAP"); return (e && e[0] == '1') ? 1 : 0; }();
   p.b_swap = b_swap;
 
@@ -681,6 +1080,18 @@ static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cuda
   int pairs = dev.sm_count / 2;
   if (a->max_ctas > 0 && a->max_ctas / 2 < pairs) pairs = a->max_ctas / 2 > 0 ? a->max_ctas / 2 : 1;
   if (total < pairs) pairs = (int)total;
+  if constexpr (KIND == G2_F32 && G2_F32_CHUNK == 32) {
+    // the (hi, lo) residual stream in and out: the 16-warp epilogue kernel (PIO_GEMM2_STREAM=0 keeps the general one)
+    static const int use_stream = [] { const char* e = getenv("PIO_GEMM2_STREAM"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (use_stream && p.out_split && p.res_split && a->out_bf16 && a->batch == 1 && p.bias_mode <= 1 && p.act == 0 &&
+        (p.row_stats_out == nullptr || p.stats_parts >= 4 * p.tiles_n)) {
+      // 8 epilogue warps, two in-place slots each, five operand stages; PIO_G2S_CFG=1: sixteen warps / three stages
+      // (measured slower: the operand ring is what the freed shared memory is worth)
+      static const int cfg = [] { const char* e = getenv("PIO_G2S_CFG"); return e ? atoi(e) : 0; }();
+      if (cfg == 1) return launch_gemm2_stream<16, 2, 3>(ta, tb, to, traw, tr, trlo, p, pairs, dev, stream);
+      return launch_gemm2_stream<8, 2, 5>(ta, tb, to, traw, tr, trlo, p, pairs, dev, stream);
+    }
+  }
   {
     const double bytes = (KIND == G2_F32 ? 4.0 * (p.has_residual ? 2 : 1) : 2.0) * a->M * (double)a->N * a->batch;
     ProfileScope prof(KF_GEMM, 2.0 * a->M * a->N * (double)a->K * a->batch, bytes, stream);

@@ -81,6 +81,7 @@ FUSE_LN_MAX_OFFSET = 1.0     # max |mean| / std of a residual-stream row the fus
 # Residual stream of the fused tower as a pair of 16-bit arrays between its producer GEMMs (pio_gemm_args.out_lo16) when
 # every one of them runs on the CTA-pair kernel (ops.gemm_uses_pair_kernel): 4 instead of 6 bytes written per element.
 SPLIT_STREAM = os.environ.get("PIO_SPLIT_STREAM", "1") != "0"
+STREAM_INPLACE = os.environ.get("PIO_STREAM_INPLACE", "1") != "0"   # ... updated in place from the second producer on
 REVERSE_FC2 = os.environ.get("PIO_REVERSE_FC2", "1") != "0"
 REVERSE_FC1 = os.environ.get("PIO_REVERSE_FC1", "1") != "0"   # fc1 too: the out-projection wrote its operand front to back
 
@@ -242,9 +243,13 @@ def self_attention_block_fused(pf: PreparedFusedLayer, x: Optional[torch.Tensor]
                   scale=pf.scale)
     o2 = o.view(M, -1)
     res_in = dict(residual=x, ldr=x.stride(0)) if x is not None else dict(residual_hi16=xb, residual_lo16=x_lo, ldr16=C)
-    x1b = torch.empty((M, C), dtype=d16, device=dev)
+    # a pair that comes in is updated in place (each element is read and rewritten by the same epilogue warp): one
+    # (hi, lo) pair per tower instead of three, and the hi half — read by both projections and both producers of a
+    # layer — is the working set the kernels ask L2 to keep (pio_gemm2.cu, hint_*)
+    inplace = STREAM_INPLACE and split and x is None
+    x1b = xb if inplace else torch.empty((M, C), dtype=d16, device=dev)
     if split:
-        x1, x1l = None, torch.empty((M, C), dtype=d16, device=dev)
+        x1, x1l = None, (x_lo if inplace else torch.empty((M, C), dtype=d16, device=dev))
         ops.gemm(o2, pf.wf, M=M, N=C, K=pf.V, bias=pf.bf, out_bf16=x1b, ldo16=C, out_lo16=x1l, row_stats_out=st_mid,
                  **res_in)
         res_mid = dict(residual_hi16=x1b, residual_lo16=x1l, ldr16=C)
@@ -259,8 +264,8 @@ def self_attention_block_fused(pf: PreparedFusedLayer, x: Optional[torch.Tensor]
     # fc2 walks its tiles back to front: fc1 and the out-projection wrote h and x1 front to back, so their last rows are
     # what L2 still holds; and the rows fc2 writes last (the first ones) are where the next QKV projection starts
     if split_out:
-        yb = torch.empty((M, C), dtype=d16, device=dev)
-        yl = torch.empty((M, C), dtype=d16, device=dev)
+        yb = x1b if (STREAM_INPLACE and split) else torch.empty((M, C), dtype=d16, device=dev)
+        yl = x1l if (STREAM_INPLACE and split) else torch.empty((M, C), dtype=d16, device=dev)
         ops.gemm(h, pf.w2, M=M, N=C, K=pf.hidden, bias=pf.b2, out_bf16=yb, ldo16=C, out_lo16=yl, row_stats_out=st_out,
                  reverse_tiles=REVERSE_FC2, **res_mid)
         return None, yb, yl

@@ -162,8 +162,22 @@ def _query_reads_inputs(output_query) -> bool:
                 and getattr(output_query, "_position_encoding", None) is None)
 
 
+def _post_linear(posts, decoder):
+    """The Linear a single '__default' postprocessor applies first, if the decoder can absorb it (N3)."""
+    if not posts or list(posts.keys()) != ["__default"] or not hasattr(decoder, "fuses_post_linear"):
+        return None
+    post = posts["__default"]
+    kind = type(post).__name__
+    lin = None
+    if kind == "ClassificationPostprocessor" and getattr(post, "_project", False):
+        lin = getattr(post, "linear", None)
+    elif kind == "ProjectionPostprocessor":
+        lin = getattr(post, "projection", None)
+    return lin if lin is not None and decoder.fuses_post_linear(lin) else None
+
+
 def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_points=None, pos=None, input_mask=None,
-                         query_mask=None, only_needed_queries: bool = False):
+                         query_mask=None, only_needed_queries: bool = False, fuse_postprocessor: bool = True):
     """`PerceiverIO.forward` (perceiver.py:287-325) for a single image modality with the input glue fused: the
     preprocessor's features and position table reach the encoder as a `PositionedInput`.  Falls back to the module's
     own forward whenever the configuration is not covered (several modalities, channel padding, modality masking).
@@ -171,7 +185,12 @@ def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_p
     only_needed_queries (off by default): the classification wrapper decodes 1000 output
     queries and its postprocessor keeps query 0 only (postprocessors.py:187).  Decoder rows do not interact (each query
     attends over the latents and goes through the MLP and the final projection on its own), so decoding just the kept
-    row gives the same logits for 1/1000 of the decoder work."""
+    row gives the same logits for 1/1000 of the decoder work.
+
+    fuse_postprocessor (N3, on by default): `ClassificationPostprocessor.linear` / `ProjectionPostprocessor.projection`
+    (postprocessors.py:176-187, :200-208) is composed with the decoder's `final_layer` — post(final(x)) is one affine map
+    — so the [B, Nq, out] intermediate and one GEMM disappear; what is left of the postprocessor (keeping query 0) is
+    applied here."""
     own = type(perceiver).forward     # the class's forward: `perceiver.forward` may be this very function (install.py)
     mp = perceiver._multi_preprocessor
     preps = getattr(mp, "_preprocessors", None) if mp is not None else None
@@ -198,6 +217,13 @@ def perceiver_io_forward(perceiver, inputs: torch.Tensor, *, subsampled_output_p
         decoder_query = decoder_query[:, :1]
         query_mask = None if query_mask is None else query_mask[:, :1]
         query_sizes = {"__default": 1}
+    # N3: a classification / projection postprocessor starts with its own Linear on the decoder's projected outputs
+    # (postprocessors.py:176-187, :200-208); the decoder composes it with final_layer into one map
+    post_linear = _post_linear(posts, perceiver._decoder) if fuse_postprocessor else None
+    if post_linear is not None:
+        outputs = perceiver._decoder(decoder_query, latents, query_mask=query_mask, post_linear=post_linear)
+        kind = type(posts["__default"]).__name__
+        return outputs[:, 0, :] if kind == "ClassificationPostprocessor" else outputs
     outputs = perceiver._decoder(decoder_query, latents, query_mask=query_mask)
     if perceiver._output_postprocessors:
         if type(outputs) is torch.Tensor:

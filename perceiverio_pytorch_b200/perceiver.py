@@ -189,6 +189,41 @@ class PerceiverEncoder(nn.Module):
         return x.view(B, N, C)
 
 
+class _ComposedFinal(nn.Module):
+    """final_layer followed by a postprocessor's own Linear (postprocessors.py:176-187 `ClassificationPostprocessor.linear`,
+    :200-208 `ProjectionPostprocessor.projection`) as ONE affine map: post(final(x)) = x (Wp Wf)^T + (Wp bf + bp), composed
+    in fp64 (SURVEY.md section 8(f), N3).  Quacks like the nn.Linear the decoder's tail code expects (`weight`, `bias`);
+    holds the source layers (and the MLP whose second layer the narrow-head fold absorbs) as sub-modules so that
+    engine.prepared() sees every parameter the derived weights depend on.  Lives in the decoder's __dict__, not in its
+    module tree: the decoder's state_dict stays the reference's."""
+
+    def __init__(self, final_layer: nn.Linear, post: nn.Linear, mlp: nn.Module):
+        super().__init__()
+        self.final_layer, self.post, self.mlp = final_layer, post, mlp
+        self._ver = None
+        self._w = self._b = None
+
+    def _refresh(self):
+        ver = tuple((p.data_ptr(), p._version, p.device) for p in (*self.final_layer.parameters(), *self.post.parameters()))
+        if ver != self._ver:
+            d = torch.float64
+            wf, wp = self.final_layer.weight.detach().to(d), self.post.weight.detach().to(d)
+            b = wp @ self.final_layer.bias.detach().to(d) if self.final_layer.bias is not None else wp.new_zeros(wp.shape[0])
+            if self.post.bias is not None:
+                b = b + self.post.bias.detach().to(d)
+            self._w, self._b, self._ver = (wp @ wf).float().contiguous(), b.float().contiguous(), ver
+
+    @property
+    def weight(self) -> torch.Tensor:
+        self._refresh()
+        return self._w
+
+    @property
+    def bias(self) -> torch.Tensor:
+        self._refresh()
+        return self._b
+
+
 class PerceiverDecoder(nn.Module):
     """Cross-attention-based decoder (reference: perceiver.py:110-180)."""
 
@@ -221,18 +256,36 @@ class PerceiverDecoder(nn.Module):
         # arithmetic mode of this module's forward: None = the global engine.PRECISION, or "bf16" / "fp16" / "bf16x3"
         self.precision = None
 
-    def forward(self, query, latents, *, query_mask=None):
+    def forward(self, query, latents, *, query_mask=None, post_linear: nn.Linear = None):
+        """Reference signature (perceiver.py:166) plus `post_linear`: a postprocessor's Linear to apply to the decoder's
+        output inside its last projection (N3: `final_layer` and the Linear composed into one map, no intermediate
+        [B, Nq, out] array and one GEMM less).  Ignored — the caller applies it — unless the decoder projects."""
         with engine.precision_scope(self.precision):
-            return self._forward(query, latents, query_mask=query_mask)
+            return self._forward(query, latents, query_mask=query_mask, post_linear=post_linear)
 
-    def _forward(self, query, latents, *, query_mask=None):
+    def fuses_post_linear(self, post_linear) -> bool:
+        return bool(self._final_project and isinstance(post_linear, nn.Linear)
+                    and post_linear.in_features == self._output_num_channels)
+
+    def _final(self, post_linear):
+        if post_linear is None:
+            return self.final_layer, self._output_num_channels
+        held = self.__dict__.get("_pio_composed")
+        if held is None or held.post is not post_linear or held.final_layer is not self.final_layer:
+            held = _ComposedFinal(self.final_layer, post_linear, self.decoding_cross_attn.mlp)
+            self.__dict__["_pio_composed"] = held
+        return held, post_linear.out_features
+
+    def _forward(self, query, latents, *, query_mask=None, post_linear=None):
         ops._need_cuda(query, latents)
         if query.dtype != torch.float32:
             query = query.float()       # e.g. fp16 activations under the reference's autocast (flow_perceiver.py:129)
         if latents.dtype != torch.float32:
             latents = latents.float()
         row_keep = query_mask.to(torch.bool) if query_mask is not None else None
-        n_out = self._output_num_channels
+        if post_linear is not None and not self.fuses_post_linear(post_linear):
+            raise ValueError("PerceiverDecoder: post_linear must be an nn.Linear over this decoder's projected outputs")
+        fin, n_out = self._final(post_linear) if self._final_project else (None, self._output_num_channels)
         if query.shape[0] == 0 or query.shape[1] == 0:   # empty batch / no output queries: nothing to launch
             return query.new_empty(query.shape[0], query.shape[1], n_out if self._final_project else query.shape[2])
         # the wide final projection consumes bf16 rows: let the MLP's last GEMM write them next to the fp32 result
@@ -243,7 +296,9 @@ class PerceiverDecoder(nn.Module):
             # a handful of output channels (optical flow: 322 -> 2): the head is folded into the MLP's second layer and
             # evaluated in fp32 on CUDA cores together with it.  The head is 0.01 % of the FLOPs but its 16-bit rounding
             # alone would cost 1.2e-2 of the 1e-2 error budget in bf16.
-            tail = engine.prepared(self, "tail", lambda: engine.PreparedTail(self.decoding_cross_attn.mlp, self.final_layer))
+            tail = (engine.prepared(self, "tail", lambda: engine.PreparedTail(self.decoding_cross_attn.mlp, fin))
+                    if fin is self.final_layer else
+                    engine.prepared(fin, "tail", lambda: engine.PreparedTail(self.decoding_cross_attn.mlp, fin)))
         y32, y16 = self.decoding_cross_attn._forward_factored(query, latents, key_mask=None, row_keep=row_keep,
                                                               want_bf16_out=want16, tail=tail)
         if tail is not None:
@@ -252,15 +307,15 @@ class PerceiverDecoder(nn.Module):
             return y32 if y32.is_contiguous() else y32.contiguous()   # odd widths carry a 16-byte row pitch inside
         B, Nq, C = y32.shape
         if engine.PRECISION == "bf16x3":
-            return validate.final_layer(self.final_layer, y32)
+            return validate.final_layer(fin, y32)
         if n_out <= 16:
             # a handful of output channels (optical flow: 322 -> 2): fp32 on CUDA cores.  The head is 0.01 % of the
             # FLOPs but its bf16 rounding alone would cost 1.2e-2 of the 1e-2 error budget.
-            bias = self.final_layer.bias.detach() if self.final_layer.bias is not None else None
-            out = ops.linear_f32(y32.view(B * Nq, C), self.final_layer.weight.detach(), bias)
+            bias = fin.bias.detach() if fin.bias is not None else None
+            out = ops.linear_f32(y32.view(B * Nq, C), fin.weight.detach(), bias)
             return out.view(B, Nq, -1)
-        w = engine.prepared(self.final_layer, "w", lambda: (engine._bf16_weight(self.final_layer.weight.detach()),
-                                                           self.final_layer.bias.detach().float().contiguous()))
+        w = engine.prepared(fin, "w", lambda: (engine._bf16_weight(fin.weight.detach()),
+                                               fin.bias.detach().float().contiguous()))
         if y16 is None:
             y16 = ops.layernorm_bf16(y32.view(B * Nq, C), None, None, normalize=False)
         out, _ = ops.linear(y16, C, w[0], n_out, w[1], want_f32=True, want_bf16=False)

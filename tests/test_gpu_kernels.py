@@ -231,7 +231,7 @@ def test_gemm_fused_layernorm_epilogues():
     ops.gemm(h, w2, M=M, N=C, K=C, bias=b2, residual=res, ldr=C, out_f32=x, ldo32=C, out_bf16=xb, ldo16=C,
              row_stats_out=st_again, reverse_tiles=True)
     assert torch.equal(st, st_again)      # plain stores per half-tile: bit-reproducible, whatever the tile order
-    assert st.shape == (M, ops.stats_parts(M, C), 2) and st.shape[1] == 2 * (C // 256)
+    assert st.shape == (M, ops.stats_parts(M, C), 2) and st.shape[1] == 4 * (C // 256)
     parts = st
     st = st.sum(1)
     x_ref = h.float() @ w2.float().t() + b2 + res
@@ -443,6 +443,32 @@ def test_gemm_pair_kernel_split_residual_stream(f16):
         ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_bf16=hi2, ldo16=N,
                  out_lo16=lo2, reverse_tiles=True)
         assert ((hi2.float() + lo2.float()) - z_ref).abs().max() <= tol * z_ref.abs().max()
+        # ... with the row statistics (pio_gemm2_stream_kernel: one slot per 64-column slice), twice, bit-identically
+        st2 = ops.empty_row_stats(M, N, "cuda", parts).fill_(float("nan"))
+        hi3 = torch.empty_like(hi2)
+        lo3 = torch.empty_like(lo2)
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_bf16=hi3, ldo16=N,
+                 out_lo16=lo3, row_stats_out=st2)
+        assert torch.equal(hi3, hi2) and torch.equal(lo3, lo2)
+        assert torch.equal(hi3, z_ref.to(d16))
+        ssum = st2.sum(1)
+        assert not torch.isnan(ssum).any()
+        assert _rel(ssum[:, 0], z_ref.sum(1)) < 1e-4 and _rel(ssum[:, 1], (z_ref * z_ref).sum(1)) < 1e-4
+        st3 = torch.empty_like(st2)
+        ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_bf16=hi3, ldo16=N,
+                 out_lo16=lo3, row_stats_out=st3, reverse_tiles=True)
+        assert torch.equal(st2, st3)
+        # a column tail (N = 984: the last 64-column slice holds 24 columns, the last chunk 24 of 32) and no bias
+        Nt = 984
+        hi4 = torch.zeros(M, N, device="cuda", dtype=d16)
+        lo4 = torch.zeros(M, N, device="cuda", dtype=d16)
+        st4 = ops.empty_row_stats(M, N, "cuda", parts).fill_(float("nan"))
+        ops.gemm(A, W, M=M, N=Nt, K=K, residual_hi16=hi, residual_lo16=lo, ldr16=N, out_bf16=hi4, ldo16=N, out_lo16=lo4,
+                 row_stats_out=st4)
+        zt = A.float() @ W[:Nt].float().t() + xs[:, :Nt]
+        assert ((hi4.float() + lo4.float())[:, :Nt] - zt).abs().max() <= 4 * tol * zt.abs().max()
+        assert (hi4[:, Nt:] == 0).all() and (lo4[:, Nt:] == 0).all()      # the TMA stores clip the tail
+        assert _rel(st4.sum(1)[:, 0], zt.sum(1)) < 1e-4
         # the single-CTA kernel does not implement the pair stream: it must say so
         with pytest.raises(RuntimeError, match="CTA-pair kernel"):
             ops.gemm(A, W, M=M, N=N, K=K, bias=bias, residual=x, ldr=N, out_bf16=hi, ldo16=N, out_lo16=lo, kernel=1)

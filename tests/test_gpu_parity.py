@@ -431,6 +431,49 @@ def test_ragged_sizes_match_oracle(nk, nq):
     assert rel_err(out.cpu(), out_ref)[0] <= BF16_TOL
 
 
+@pytest.mark.parametrize("n_out,n_post,mode", [(40, 24, "bf16"), (40, 24, "fp16"), (2, 5, "bf16"), (1000, 1000, "bf16"),
+                                               (40, 24, "bf16x3")])
+def test_decoder_absorbs_the_postprocessor_linear(n_out, n_post, mode):
+    """`final_layer` and the postprocessor's own Linear (postprocessors.py:176-187, :200-208)
+    composed into one projection inside the decoder — against the oracle's decoder followed by the Linear in fp32, on
+    the wide head (tensor cores), the narrow head (folded into the MLP's second layer) and the validation mode."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import engine
+    from oracle import perceiver_oracle as O
+    torch.manual_seed(n_out + n_post)
+    C, Cq, Nl, Nq = 128, 96, 40, 300
+    dec = pio.PerceiverDecoder(query_channels=Cq, final_project_out_channels=n_out, num_latent_channels=C,
+                               use_query_residual=True).eval()
+    post = torch.nn.Linear(n_out, n_post)
+    _perturb(dec, 11)
+    with torch.no_grad():
+        post.bias.normal_(0, 0.1)
+    query, latents = torch.randn(2, Nq, Cq), torch.randn(2, Nl, C)
+    sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    ref = O.decoder_forward(sd, "", query=query, latents=latents, query_mask=None, num_heads=1, use_query_residual=True,
+                            final_project=True)
+    ref = torch.nn.functional.linear(ref, post.weight.detach(), post.bias.detach())
+    keys_before = list(dec.state_dict().keys())
+    dec, post = dec.cuda(), post.cuda()
+    with torch.inference_mode(), engine.precision_scope(mode):
+        got = dec(query.cuda(), latents.cuda(), post_linear=post)
+        plain = post(dec(query.cuda(), latents.cuda()))
+    assert list(dec.state_dict().keys()) == keys_before       # the composed weights are no part of the module tree
+    assert got.shape == ref.shape == (2, Nq, n_post)
+    tol = 1e-4 if mode == "bf16x3" else BF16_TOL
+    assert rel_err(got.cpu(), ref)[0] <= tol, rel_err(got.cpu(), ref)
+    assert rel_err(plain.cpu(), ref)[0] <= tol
+    # derived weights follow in-place updates of either layer
+    with torch.no_grad():
+        post.weight.mul_(2.0)
+        post.bias.mul_(2.0)
+    with torch.inference_mode(), engine.precision_scope(mode):
+        again = dec(query.cuda(), latents.cuda(), post_linear=post)
+    assert rel_err(again.cpu(), 2.0 * ref)[0] <= tol
+    with pytest.raises(ValueError, match="post_linear"):
+        dec(query.cuda(), latents.cuda(), post_linear=torch.nn.Linear(n_out + 1, 3).cuda())
+
+
 def test_standalone_mlp_matches_oracle():
     """The bare `MLP.forward` (transformer_primitives.py:212-216), as a caller of the module API would use it:
     widening factors 1 and 4, an odd channel count, a 4-D input."""

@@ -84,3 +84,58 @@ def test_key_split_chooser_never_leaves_a_split_empty():
         assert 1 <= s <= 32
         per = (tiles + s - 1) // s
         assert (s - 1) * per < tiles, (B, Nq, Nk, s)
+
+
+def test_postprocessor_linear_composes_with_final_layer():
+    """N3 host algebra: post(final(x)) as one affine map (perceiver._ComposedFinal), in fp64 against the two layers
+    applied in sequence; the composed weights follow in-place parameter updates and stay out of the state_dict."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import inputs as pin_mod
+    torch.manual_seed(5)
+    dec = pio.PerceiverDecoder(query_channels=48, final_project_out_channels=10, num_latent_channels=64).eval()
+    post = torch.nn.Linear(10, 7)
+    with torch.no_grad():
+        dec.final_layer.bias.normal_()
+        post.bias.normal_()
+    keys = list(dec.state_dict().keys())
+    fin, n_out = dec._final(post)
+    assert n_out == 7 and list(dec.state_dict().keys()) == keys
+    x = torch.randn(33, 48, dtype=torch.float64)
+    want = post.double()(dec.final_layer.double()(x)).detach()
+    got = x @ fin.weight.double().t() + fin.bias.double()
+    assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    with torch.no_grad():
+        dec.final_layer.weight.mul_(0.5)
+    want2 = post(dec.final_layer(x)).detach()
+    got2 = x @ fin.weight.double().t() + fin.bias.double()
+    assert float((got2 - want2).abs().max()) <= 1e-6 * float(want2.abs().max())
+    assert dec._final(post)[0] is fin and dec._final(None)[0] is dec.final_layer
+    assert not dec.fuses_post_linear(torch.nn.Linear(11, 3)) and dec.fuses_post_linear(post)
+    no_proj = pio.PerceiverDecoder(query_channels=48, final_project_out_channels=10, num_latent_channels=64,
+                                   final_project=False)
+    assert not no_proj.fuses_post_linear(post)
+
+    # which postprocessors qualify (duck-typed on the reference's class names, postprocessors.py:165-208)
+    class ClassificationPostprocessor(torch.nn.Module):
+        def __init__(self, project):
+            super().__init__()
+            self._project = project
+            if project:
+                self.linear = torch.nn.Linear(10, 7)
+
+    class ProjectionPostprocessor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.projection = torch.nn.Linear(10, 4)
+
+    class FlowPostprocessor(torch.nn.Module):
+        pass
+
+    c = ClassificationPostprocessor(True)
+    assert pin_mod._post_linear({"__default": c}, dec) is c.linear
+    assert pin_mod._post_linear({"__default": ClassificationPostprocessor(False)}, dec) is None
+    pr = ProjectionPostprocessor()
+    assert pin_mod._post_linear({"__default": pr}, dec) is pr.projection
+    assert pin_mod._post_linear({"__default": FlowPostprocessor()}, dec) is None
+    assert pin_mod._post_linear({"a": c, "b": pr}, dec) is None and pin_mod._post_linear(None, dec) is None
+    assert pin_mod._post_linear({"__default": c}, torch.nn.Linear(2, 2)) is None      # a decoder that is not ours

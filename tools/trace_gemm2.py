@@ -50,7 +50,14 @@ if __name__ == "__main__":
         launch()
         torch.cuda.synchronize()
         lib.pio_debug_gemm2_trace(buf)
-    ev = [(buf[2 * i], buf[2 * i + 1]) for i in range(1024) if buf[2 * i]]
+    mma = [(buf[2 * i], buf[2 * i + 1]) for i in range(512, 1024) if buf[2 * i]]
+    if mma:
+        print("MMA issuer of CTA 0 (500 waits for a free accumulator, 501 has it, 502 tile issued): tag, clk, delta")
+        prev = mma[0][1]
+        for tag, clk in mma[:40]:
+            print(f"  {tag:4d} {clk - mma[0][1]:9d} {clk - prev:7d}")
+            prev = clk
+    ev = [(buf[2 * i], buf[2 * i + 1]) for i in range(512) if buf[2 * i]]
     t0 = ev[0][1]
     print(f"producer GEMM {M}x{C}x{C} [{mode}]: epilogue of warp 4, CTA 0 (tag, clk since the first tag, delta)")
     prev = t0
