@@ -113,7 +113,8 @@ typedef struct pio_gemm_args {
    *    half-tile of the row into its own slot: row_stats_out[m][2 * (n / T) + (n % T) / (T / 2)], T = the kernel's tile
    *    width (256 in the CTA-pair kernel, 64 .. 256 in the single-CTA kernel); slots the chosen tile width does not use
    *    are zeroed (plain stores: no atomics, nothing to zero beforehand, bit-reproducible).  The caller sizes the buffer
-   *    with pio_gemm_stats_parts(M, N) (or, with a forced tile width, 2 * ceil(N / T));
+   *    with pio_gemm_stats_parts(M, N) (or, with a forced tile width, 2 * ceil(N / T)); the value for the CTA-pair
+   *    kernel is 4 * ceil(N / 256): the producer of the (hi, lo) stream may split a tile's columns over four warps;
    *  - consumer side (the GEMM that multiplies LN(x) by W): A is that bf16(x), B is W' = W * diag(gamma), and the
    *    epilogue applies the normalisation per output row:
    *        v = rstd_m * (alpha * acc - mean_m * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k],

@@ -1,4 +1,4 @@
-"""ncu target: the fused input LayerNorm, the encoder cross-attend and two latent-tower layers (the LayerNorm-fused path) at the ImageNet-recipe
+"""ncu target: the fused input LayerNorm, the encoder cross-attend and three latent-tower layers (the LayerNorm-fused path) at the ImageNet-recipe
 shapes, launched eagerly twice.  Run plain first, then under `ncu --set full -k regex:pio_`."""
 import os
 import sys
@@ -10,7 +10,7 @@ import perceiverio_pytorch_b200 as pio  # noqa: E402
 
 torch.manual_seed(0)
 B = int(os.environ.get("PIO_PROFILE_BATCH", "64"))
-enc = pio.PerceiverEncoder(num_input_channels=261, num_self_attends_per_block=2, num_blocks=1, num_latents=512,
+enc = pio.PerceiverEncoder(num_input_channels=261, num_self_attends_per_block=int(os.environ.get("PIO_PROFILE_LAYERS", "3")), num_blocks=1, num_latents=512,
                            num_latent_channels=1024).eval().cuda()
 images = torch.randn(B, 3, 224, 224, device="cuda")
 table = pio.fourier_position_table((224, 224), 64, device="cuda")
