@@ -101,28 +101,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// The same as a volatile statement: a run of these keeps its place in the instruction stream.  The softmax loops issue
-// their exponentials in batches of 16 - 32 in front of the instructions that consume them: left to the scheduler, ptxas
-// interleaves each pair of MUFU ops with the conversion and the row-sum add of the previous pair, two scoreboards deep,
-// and a lone softmax warp then waits out the MUFU latency on every pair (~31 clk per pair instead of the 16 the unit
-// needs: profiles/r02o_flash2_flow_tower_clock64_trace.txt).
-__device__ __forceinline__ float ex2_approx_ordered(float x) {
-  float r;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ uint64_t fadd2_ordered(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-template <bool F16>
-__device__ __forceinline__ uint32_t pack16x2_ordered(float lo, float hi) {
-  uint32_t r;
-  if constexpr (F16) asm volatile("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float a = fminf(fabsf(x), 5.9396970f);
   float q = fmaf(a, 0.0005204587359912694f, -0.007397511973977089f);

@@ -453,26 +453,20 @@ pio_flash2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           // one uniform branch per 32 keys selects the 16-bit format; the loop body itself stays select-free
           auto exp_block = [&](auto f16tag) {
             constexpr bool F16 = decltype(f16tag)::value;
-            // all 32 exponentials of the block first (ordered statements: the MUFU unit gets a dense run and its latency
-            // is paid once per block, not once per pair), then the conversions and the row sum
-            float e[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const uint64_t t2 = ffma2(pack_f32x2(__uint_as_float(r[32 * c + 2 * i]), __uint_as_float(r[32 * c + 2 * i + 1])),
                                         sc2, nm2);
               float t0, t1;
               unpack_f32x2(t2, t0, t1);
-              e[2 * i] = ex2_approx_ordered(t0);
-              e[2 * i + 1] = ex2_approx_ordered(t1);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              w[i] = pack16x2_ordered<F16>(e[2 * i], e[2 * i + 1]);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+              w[i] = pack16x2<F16>(e0, e1);
               // the row sum takes the un-rounded exponentials: round-to-nearest is unbiased, so l differs from the sum of
-              // the 16-bit values the tensor core multiplies by ~2^-9 / sqrt(Nk) relative
-              const uint64_t pr = pack_f32x2(e[2 * i], e[2 * i + 1]);
-              if (i & 1) lb = fadd2_ordered(lb, pr);
-              else la = fadd2_ordered(la, pr);
+              // the 16-bit values the tensor core multiplies by ~2^-9 / sqrt(Nk) relative, and rebuilding the rounded
+              // values cost two integer instructions per pair in a loop that is issue-bound (one warp per scheduler)
+              const uint64_t pr = pack_f32x2(e0, e1);
+              if (i & 1) lb = fadd2(lb, pr);
+              else la = fadd2(la, pr);
             }
           };
           if (p.fp16) exp_block(std::true_type{});
