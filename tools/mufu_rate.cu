@@ -26,6 +26,67 @@ __global__ void mufu_kernel(float* out, long long* clk, int iters) {
   if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
 }
 
+// MODE 1: cvt.rn.bf16x2.f32 only; MODE 2: per pair of values two ex2 and one cvt (the softmax loop's mix);
+// MODE 3: two ex2 and the integer form of a truncating bf16 pack (2 x LOP3 + PRMT)
+template <int MODE>
+__global__ void mix_kernel(float* out, long long* clk, int iters) {
+  float v[16];
+  unsigned w[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.001f * (threadIdx.x + i);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE != 1) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[2 * i]));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[2 * i + 1]));
+      }
+      if (MODE == 1 || MODE == 2) {
+        unsigned r;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        w[i] ^= r;
+      }
+      if (MODE == 3) {
+        unsigned a = __float_as_uint(v[2 * i]), b = __float_as_uint(v[2 * i + 1]), r;
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(a), "r"(b));
+        w[i] ^= r;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += __uint_as_float(w[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE>
+void run_mix(int threads, const char* what) {
+  float* out;
+  long long* clk;
+  cudaMalloc(&out, 148 * 1024 * 4);
+  cudaMalloc(&clk, 148 * 8);
+  const int iters = 2000;
+  mix_kernel<MODE><<<148, threads>>>(out, clk, iters);
+  mix_kernel<MODE><<<148, threads>>>(out, clk, iters);
+  cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < 148; ++i) avg += h[i];
+  avg /= 148;
+  printf("%-60s threads/CTA %4d : %6.2f clk per PAIR of values per warp\n", what, threads, avg / (iters * 8.0));
+  cudaFree(out);
+  cudaFree(clk);
+}
+
 template <int CHAINS, int EXTRA>
 void run(int threads, const char* what) {
   float* out;
@@ -56,5 +117,11 @@ int main() {
   run<16, 0>(512, "four warps per scheduler, 16 independent");
   run<16, 8>(128, "one warp per scheduler, 16 + 8 FMA");
   run<16, 8>(256, "two warps per scheduler, 16 + 8 FMA");
+  run_mix<1>(128, "cvt.rn.bf16x2.f32 only, one warp per scheduler");
+  run_mix<1>(256, "cvt.rn.bf16x2.f32 only, two warps per scheduler");
+  run_mix<2>(128, "2 x ex2 + cvt.rn.bf16x2 per pair, one warp per scheduler");
+  run_mix<2>(256, "2 x ex2 + cvt.rn.bf16x2 per pair, two warps per scheduler");
+  run_mix<3>(128, "2 x ex2 + prmt (truncating pack) per pair, one warp");
+  run_mix<3>(256, "2 x ex2 + prmt (truncating pack) per pair, two warps");
   return 0;
 }
