@@ -117,6 +117,13 @@ class PreparedAttention:
         self.scale = 1.0 / math.sqrt(self.dqk)
         self.folded = bool(allow_fold and ENABLE_FOLDING and self.H == 1 and wv.shape[1] == self.Ck
                            and ops.attention_supported(self.Ck, self.Ck) and self.Ck <= 384)
+        # The same key-side fold for single heads the streaming kernels do not cover (the multimodal encoder: 704 channels),
+        # on the explicit S / P path: S = Q' LN(x)^T and O' = P LN(x) take the normalised input array itself as their
+        # operand — K-major for S, MN-major for P.V — so the two projections of the long input array (2 x 52 GF for the
+        # multimodal encoder) disappear.  Chosen per call (use_key_fold_wide): it only pays when the keys far outnumber
+        # the queries; never more work than the unfolded block (Ck <= QK, Ck <= V).
+        self.fold_wide = bool(allow_fold and ENABLE_FOLDING and not self.folded and self.H == 1 and wv.shape[1] == self.Ck
+                              and self.Ck <= self.QK and self.Ck <= self.V and self.Ck % 8 == 0)
         self.wf, self.bf = _bf16_weight(wf), (bf.float().contiguous() if bf is not None else None)
         # Query-side fold for single-head cross-attends with MANY queries and few keys (the decoders):
         #   S_ij = (LN(q_i) Wq^T + bq) . k_j = LN(q_i) . K'_j + b'_j,    K' = k Wq = LN(z) (Wq^T Wk)^T + Wq^T bk,
@@ -143,7 +150,7 @@ class PreparedAttention:
             b_ext[koff:] = wf64 @ bv.double()
             self.qfold = dict(w=_bf16_weight(w_ext.float()), b=b_ext.float().contiguous(), koff=koff, n=n_ext,
                               pair_ok=pair_ok)
-        if self.folded:
+        if self.folded or self.fold_wide:
             # S = (LN(q) Wq^T + bq) Wk . LN(x)^T  (the q.bk term is constant per row and cancels in the softmax)
             # out = (P . LN(x)) (Wf Wv)^T + (Wf bv + bf)          (rows of P sum to one)
             wq64, wk64, wv64, wf64 = (t.double() for t in (wq, wk, wv, wf))
@@ -157,6 +164,8 @@ class PreparedAttention:
             if bf is not None:
                 bo = bo + bf.double()
             self.bo_fold = bo.float().contiguous()
+        if self.folded:
+            pass
         elif self_attention:
             self.wqkv = _bf16_weight(torch.cat([wq, wk, wv], 0))
             self.bqkv = torch.cat([bq, bk, bv], 0).float().contiguous()
@@ -652,10 +661,61 @@ def cross_attention_query_fold(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_b
                                  strideR=(residual.stride(0) if B > 1 else 0) if residual is not None else 0, ln=ln)
 
 
-def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual, row_keep=None):
+# the key-side fold on the explicit path: long input arrays only (the projections it removes scale with Nk)
+KFOLD_WIDE_MIN_KEYS = 4096
+
+
+def use_key_fold_wide(pa: PreparedAttention, Nq: int, Nk: int) -> bool:
+    return pa.fold_wide and Nk >= KFOLD_WIDE_MIN_KEYS and Nk >= 4 * Nq
+
+
+def cross_attention_key_fold_wide(pa: PreparedAttention, qn, kvn, *, B, Nq, Nk, q_bcast, key_mask, row_keep):
+    """Attention of a wide single-head encoder cross-attend through the key-side fold (PreparedAttention.fold_wide):
+    qn 16-bit [(1|B)*Nq, pad8(Cq)], kvn 16-bit [B*Nk, pad8(Ck)] = LN(x).  S = Q' kvn^T on the CTA-pair kernel (kvn is its
+    K-major B operand), row softmax, O' = P kvn with kvn as the MN-major B operand of the single-CTA kernel — no
+    transposed copy, no K / V projection.  Returns (O' 16-bit [B, Nq, pad8(Ck)], Ck) for cross_attention_out(folded=True)."""
+    dev = kvn.device
+    _, qf = ops.linear(qn, pa.Cq, pa.wq_fold, pa.Ck, pa.bq_fold)
+    ldq, ldk = qf.shape[-1], kvn.shape[-1]
+    lds = (Nk + 3) // 4 * 4
+    S = torch.empty((B, Nq, lds), dtype=torch.float32, device=dev)
+    ops.gemm(qf, kvn, M=Nq, N=Nk, K=pa.Ck, batch=B, strideA=0 if q_bcast else Nq * ldq, strideB=Nk * ldk, lda=ldq,
+             ldb=ldk, out_f32=S, ldo32=lds, strideO32=Nq * lds)
+    P = ops.softmax_bf16(S, Nk, pa.scale, key_mask, row_keep)          # [B, Nq, pad8(Nk)], pad columns zero
+    del S
+    ldp, dv = P.shape[-1], pa.Ck
+    tiles = B * ((Nq + 127) // 128) * ((dv + 255) // 256)
+    if B == 1 and tiles * 4 <= 148 and Nk >= 16384:
+        # few query rows, very long key axis: split the contraction over the key axis so that every SM gets a tile, and add
+        # the partial products with the partial-merge kernel (all maxima 0, all sums 1 / splits: a plain sum)
+        splits = min(32, 148 // tiles, Nk // 4096)
+        chunk = -(-Nk // splits) + 63 & ~63          # keys per split, a multiple of the 64-row K chunk
+        splits = -(-Nk // chunk)
+        Op = torch.empty((splits, 1, 1, Nq, dv), dtype=torch.float32, device=dev)
+        full = splits - 1 if splits * chunk != Nk else splits      # the last split is shorter: its own launch
+        if full > 0:
+            ops.gemm(P, kvn, M=Nq, N=dv, K=chunk, batch=full, b_mn_major=True, strideA=chunk, strideB=chunk * ldk,
+                     lda=ldp, ldb=ldk, out_f32=Op, ldo32=dv, strideO32=Nq * dv)
+        if full < splits:
+            k0 = full * chunk
+            ops.gemm(P.view(-1)[k0:], kvn.view(-1)[k0 * ldk:], M=Nq, N=dv, K=Nk - k0, b_mn_major=True, lda=ldp, ldb=ldk,
+                     out_f32=Op[full], ldo32=dv)
+        ml = torch.zeros((2, splits, 1, 1, Nq), dtype=torch.float32, device=dev)
+        ml[1].fill_(1.0 / splits)
+        return ops.attention_combine(Op, ml[0], ml[1]), dv
+    ldo = pad8(dv)
+    O = torch.empty((B, Nq, ldo), dtype=ops.dtype16(), device=dev)
+    ops.gemm(P, kvn, M=Nq, N=dv, K=Nk, batch=B, b_mn_major=True, strideA=Nq * ldp, strideB=Nk * ldk, lda=ldp, ldb=ldk,
+             out_bf16=O, ldo16=ldo, strideO16=Nq * ldo)
+    return O, dv
+
+
+def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B, Nq, residual, row_keep=None,
+                        folded: Optional[bool] = None):
     """Output projection (+ query residual) of a cross-attend: returns fp32 [B*Nq, O].  `row_keep` (u8 [B, Nq]) marks the
     rows the attention kernel did not wipe; it only matters on the folded path (see PreparedAttention.wf_bv)."""
-    if pa.folded:
+    folded = pa.folded if folded is None else folded
+    if folded:
         w, b = pa.wo_fold, pa.bo_fold
     else:
         w, b = pa.wf, pa.bf
@@ -670,7 +730,7 @@ def cross_attention_out(pa: PreparedAttention, o: torch.Tensor, width: int, *, B
         ops.gemm(o2, w, M=Nq, N=pa.O, K=width, batch=B, strideA=Nq * o2.shape[1], strideB=0, bias=b,
                  residual=residual, ldr=residual.stride(1), strideR=residual.stride(0) if B > 1 else 0,
                  out_f32=y, ldo32=ldy, strideO32=Nq * ldy)
-    if pa.folded and row_keep is not None:
+    if folded and row_keep is not None:
         wiped = (row_keep.reshape(B * Nq, 1) == 0).to(torch.float32)
         y.addcmul_(wiped, pa.wf_bv[None, :], value=-1.0)
     return y
@@ -726,10 +786,15 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
         y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, xn=xn,
                              tail=tail)
         return y32.view(B, Nq, -1), y16
+    folded = None
     if general is not None:
         assert shard is None and not pa.folded
         o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk,
                                         general=general)
+    elif shard is None and use_key_fold_wide(pa, Nq, Nk):
+        o, width = cross_attention_key_fold_wide(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km,
+                                                 row_keep=rk)
+        folded = True
     elif shard is None:
         o, width = cross_attention_core(pa, qn, kvn, B=B, Nq=Nq, Nk=Nk, q_bcast=q_bcast, key_mask=km, row_keep=rk)
     else:
@@ -738,6 +803,6 @@ def cross_attention_block(pa: PreparedAttention, pm: PreparedMLP, inputs_q: torc
                                             num_splits=shard.local_splits if shard.local_splits > 0 else None)
         # the wipe of rows without any valid key (on any rank) comes out of the merged sums: no reduction of the mask
         o, rk = shard.combine(parts, row_keep=rk, want_alive=True)
-    x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk)
+    x = cross_attention_out(pa, o, width, B=B, Nq=Nq, residual=res, row_keep=rk, folded=folded)
     y32, y16 = mlp_block(pm, x, ln2.weight, ln2.bias, want_bf16_out=want_bf16_out, stats_out=stats_out, tail=tail)
     return y32.view(B, Nq, -1), y16

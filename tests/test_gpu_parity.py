@@ -431,6 +431,45 @@ def test_ragged_sizes_match_oracle(nk, nq):
     assert rel_err(out.cpu(), out_ref)[0] <= BF16_TOL
 
 
+@pytest.mark.parametrize("B,Nq,Nk,masked", [(2, 40, 5000, True), (1, 200, 17000, False), (1, 130, 16500, True)])
+def test_wide_single_head_encoder_takes_the_key_side_fold_on_the_explicit_path(B, Nq, Nk, masked, monkeypatch):
+    """A single-head cross-attend over a long input array whose width the streaming kernels do not cover (> 384 channels:
+    the multimodal encoder's 704): K and V projections folded onto the query side, S = Q' LN(x)^T, O' = P LN(x) with the
+    normalised inputs as the MN-major operand (engine.cross_attention_key_fold_wide) — against the oracle, incl. a key
+    mask, a sample without any valid key (rows wiped: `final.bias` only) and the key-split P.V of the batch-1 case."""
+    import perceiverio_pytorch_b200 as pio
+    from perceiverio_pytorch_b200 import engine
+    from oracle import perceiver_oracle as O
+    torch.manual_seed(Nk)
+    Cq, Ck = 96, 448
+    ca = pio.CrossAttention(q_in_channels=Cq, kv_in_channels=Ck, num_heads=1, use_query_residual=True).eval()
+    _perturb(ca, 21)
+    q, kv = torch.randn(B, Nq, Cq), torch.randn(B, Nk, Ck)
+    mask = None
+    if masked:
+        km = torch.rand(B, Nk) > 0.3
+        if B > 1:
+            km[1] = False                  # no valid key at all for sample 1
+        mask = O.make_cross_attention_mask(torch.ones(B, Nq, dtype=torch.bool), km)
+    sd = {k: v.detach() for k, v in ca.state_dict().items()}
+    ref = O.cross_attention(sd, "", 1, True, q, kv, mask)
+    calls = []
+    real = engine.cross_attention_key_fold_wide
+    monkeypatch.setattr(engine, "cross_attention_key_fold_wide", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    ca = ca.cuda()
+    with torch.inference_mode():
+        pmask = pio.make_cross_attention_mask(torch.ones(B, Nq, dtype=torch.bool, device="cuda"), km.cuda()) if masked else None
+        got = ca(q.cuda(), kv.cuda(), attention_mask=pmask)
+        monkeypatch.setattr(engine, "KFOLD_WIDE_MIN_KEYS", 10 ** 9)
+        plain = ca(q.cuda(), kv.cuda(), attention_mask=pmask)
+    assert calls == [1]
+    assert rel_err(got.cpu(), ref)[0] <= BF16_TOL, rel_err(got.cpu(), ref)
+    assert rel_err(plain.cpu(), ref)[0] <= BF16_TOL
+    if masked and B > 1:     # wiped rows: q + final.bias (no trace of the folded value bias), then the MLP — on both paths
+        assert rel_err(got[1].cpu(), ref[1])[0] <= 4e-3
+        assert rel_err(got[1].cpu(), plain[1].cpu())[0] <= 1e-5
+
+
 @pytest.mark.parametrize("n_out,n_post,mode", [(40, 24, "bf16"), (40, 24, "fp16"), (2, 5, "bf16"), (1000, 1000, "bf16"),
                                                (40, 24, "bf16x3")])
 def test_decoder_absorbs_the_postprocessor_linear(n_out, n_post, mode):
