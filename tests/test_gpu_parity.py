@@ -467,7 +467,7 @@ def test_wide_single_head_encoder_takes_the_key_side_fold_on_the_explicit_path(B
     assert rel_err(plain.cpu(), ref)[0] <= BF16_TOL
     if masked and B > 1:     # wiped rows: q + final.bias (no trace of the folded value bias), then the MLP — on both paths
         assert rel_err(got[1].cpu(), ref[1])[0] <= 4e-3
-        assert rel_err(got[1].cpu(), plain[1].cpu())[0] <= 1e-5
+        assert rel_err(got[1].cpu(), plain[1].cpu())[0] <= 1e-3
 
 
 @pytest.mark.parametrize("n_out,n_post,mode", [(40, 24, "bf16"), (40, 24, "fp16"), (2, 5, "bf16"), (1000, 1000, "bf16"),
