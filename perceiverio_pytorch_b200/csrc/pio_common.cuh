@@ -112,6 +112,28 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, copysignf(erf_abs, x), hx);
 }
 
+// Two values at a time (the epilogues that apply GELU to a whole accumulator tile are bound by instruction issue): the
+// polynomial, the products and the final blend as packed fp32x2 operations, 7 instead of 11 instructions per element.
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const uint64_t a = pack_f32x2(fminf(fabsf(x0), 5.9396970f), fminf(fabsf(x1), 5.9396970f));
+  uint64_t q = ffma2(a, pack_f32x2(0.0005204587359912694f, 0.0005204587359912694f),
+                     pack_f32x2(-0.007397511973977089f, -0.007397511973977089f));
+  q = ffma2(q, a, pack_f32x2(0.052561238408088684f, 0.052561238408088684f));
+  q = ffma2(q, a, pack_f32x2(0.4592546820640564f, 0.4592546820640564f));
+  q = ffma2(q, a, pack_f32x2(1.1510913372039795f, 1.1510913372039795f));
+  float t0, t1;
+  unpack_f32x2(ffma2(q, a, pack_f32x2(0.f, 0.f)), t0, t1);
+  const float e0 = ex2_approx(-t0), e1 = ex2_approx(-t1);
+  // erf(|x|) = 1 - e, with the sign of x
+  float r0, r1;
+  unpack_f32x2(ffma2(pack_f32x2(e0, e1), pack_f32x2(-1.f, -1.f), pack_f32x2(1.f, 1.f)), r0, r1);
+  const uint64_t s = pack_f32x2(copysignf(r0, x0), copysignf(r1, x1));
+  const uint64_t hx = ffma2(x2, pack_f32x2(0.5f, 0.5f), pack_f32x2(0.f, 0.f));
+  return ffma2(hx, s, hx);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Programmatic dependent launch: every kernel lets the next grid in the stream start its prologue early
 // (launch_dependents) and then waits for the previous grid's results before touching global memory (wait).

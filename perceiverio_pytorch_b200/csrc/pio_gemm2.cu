@@ -77,10 +77,13 @@ enum { G2_BF16 = 0, G2_F32 = 1 };
 // Developer aid (compiled out unless -DPIO_GEMM2_TRACE): warp 4 of CTA 0 records (tag, clock64) pairs of its epilogue;
 // pio_debug_gemm2_trace() copies them out (tools/trace_gemm2.py).
 #ifdef PIO_GEMM2_TRACE
+#ifndef PIO_G2T_WARP
+#define PIO_G2T_WARP 4      // which epilogue warp records (4 .. 11; -DPIO_G2T_WARP=6: one that shares its scheduler with no role warp)
+#endif
 __device__ unsigned long long g_gemm2_trace[1024 * 2];
 #define G2T(tag)                                                                       \
   do {                                                                                 \
-    if (blockIdx.x == 0 && warp == 4 && lane == 0 && g2n < 512) {                     \
+    if (blockIdx.x == 0 && warp == PIO_G2T_WARP && lane == 0 && g2n < 512) {          \
       g_gemm2_trace[g2n * 2] = (unsigned long long)(tag);                              \
       g_gemm2_trace[g2n * 2 + 1] = (unsigned long long)clock64();                      \
       ++g2n;                                                                           \
@@ -233,7 +236,9 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        G2TM(500);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        G2TM(501);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
         for (int kc = 0; kc < num_k_chunks; ++kc) {
@@ -250,6 +255,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) umma_commit_2cta_mcast(&tmem_full[acc], 0x3);       // accumulator halves complete in both CTAs
+        G2TM(502);
       }
     }
   } else if (warp >= 4) {
@@ -330,6 +336,29 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;   // producer side: this row's partial statistics over the tile
+      // 16-bit-output kind: the per-column epilogue parameters (bias, LayerNorm column sums) of this warp's 128 columns
+      // are fetched ONCE per tile, four columns per lane, before the accumulator wait, and handed round by shuffles.
+      // (Loaded per chunk — 32 broadcast float4 loads, in as many batches as the register file allows — they put
+      // several global-memory round trips into every chunk: 2900 - 3400 clk per 64 columns in a clock64 trace of fc1,
+      // and the MMA issuer waited 5000 clk per tile for a free accumulator.)
+      float4 col_cs = make_float4(0.f, 0.f, 0.f, 0.f), col_b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (KIND == G2_BF16) {
+        const int cb = nt * Cfg::BN + half * 128 + 4 * lane;
+        auto fetch4 = [&](const float* src) {
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cb + 3 < p.N && ((reinterpret_cast<uintptr_t>(src + cb) & 15u) == 0)) {
+            r = __ldg(reinterpret_cast<const float4*>(src + cb));
+          } else {
+            if (cb < p.N) r.x = __ldg(src + cb);
+            if (cb + 1 < p.N) r.y = __ldg(src + cb + 1);
+            if (cb + 2 < p.N) r.z = __ldg(src + cb + 2);
+            if (cb + 3 < p.N) r.w = __ldg(src + cb + 3);
+          }
+          return r;
+        };
+        if (p.bias_mode == 1) col_b = fetch4(p.bias);
+        if (p.row_stats_in != nullptr) col_cs = fetch4(p.ln_colsum);
+      }
       G2T(100);
       mbar_wait(&tmem_full[acc], acc_phase);
       G2T(101);
@@ -371,44 +400,30 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         bool bias_done = false;
         if constexpr (KIND == G2_BF16) {
-          if (p.row_stats_in != nullptr) {
-            // v = rstd * (acc - mean * colsum[n])   (bias, which already holds W.beta, is added below)
-            const float nm = -ln_mean;
-            if (p.bias_mode == 1 && col0 + CHUNK_COLS <= p.N &&
-                (((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) | reinterpret_cast<uintptr_t>(p.bias + col0)) & 15u) == 0)) {
-              // the usual case, one instruction per element: v = acc * rstd + ((-mean * rstd) * colsum[n] + bias[n]) as two
-              // packed fp32x2 FMAs per column pair (this epilogue runs next to the mainloop's issue stream; the three
-              // scalar operations per element it replaces cost 8 % of the kernel)
-              const float nmr = nm * ln_rstd;
-              const uint64_t nmr2 = pack_f32x2(nmr, nmr), rstd2 = pack_f32x2(ln_rstd, ln_rstd);
+          // v = acc * rstd + ((-mean * rstd) * colsum[n] + bias[n])  (bias already holds W.beta), or v = acc + bias[n]:
+          // two packed fp32x2 FMAs per column pair, the column parameters out of the lanes that hold them
+          const bool ln = p.row_stats_in != nullptr;
+          if (ln || p.bias_mode == 1) {
+            const float nmr = -ln_mean * ln_rstd;
+            const uint64_t nmr2 = pack_f32x2(nmr, nmr), rstd2 = pack_f32x2(ln_rstd, ln_rstd);
 #pragma unroll
-              for (int j = 0; j < CHUNK_COLS / 4; ++j) {
-                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                const uint64_t lo = ffma2(pack_f32x2(v[4 * j], v[4 * j + 1]), rstd2,
-                                          ffma2(nmr2, pack_f32x2(cs.x, cs.y), pack_f32x2(bq.x, bq.y)));
-                const uint64_t hi = ffma2(pack_f32x2(v[4 * j + 2], v[4 * j + 3]), rstd2,
-                                          ffma2(nmr2, pack_f32x2(cs.z, cs.w), pack_f32x2(bq.z, bq.w)));
-                unpack_f32x2(lo, v[4 * j], v[4 * j + 1]);
-                unpack_f32x2(hi, v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+              const int src = c * (CHUNK_COLS / 4) + j;      // the lane that holds columns 4 src .. 4 src + 3 of the warp's 128
+              const float b0 = __shfl_sync(0xffffffffu, col_b.x, src), b1 = __shfl_sync(0xffffffffu, col_b.y, src);
+              const float b2 = __shfl_sync(0xffffffffu, col_b.z, src), b3 = __shfl_sync(0xffffffffu, col_b.w, src);
+              uint64_t add_lo = pack_f32x2(b0, b1), add_hi = pack_f32x2(b2, b3);
+              if (ln) {
+                const float c0 = __shfl_sync(0xffffffffu, col_cs.x, src), c1 = __shfl_sync(0xffffffffu, col_cs.y, src);
+                const float c2 = __shfl_sync(0xffffffffu, col_cs.z, src), c3 = __shfl_sync(0xffffffffu, col_cs.w, src);
+                add_lo = ffma2(nmr2, pack_f32x2(c0, c1), add_lo);
+                add_hi = ffma2(nmr2, pack_f32x2(c2, c3), add_hi);
               }
-              bias_done = true;
-            } else if (col0 + CHUNK_COLS <= p.N && ((reinterpret_cast<uintptr_t>(p.ln_colsum + col0) & 15u) == 0)) {
-#pragma unroll
-              for (int j = 0; j < CHUNK_COLS / 4; ++j) {
-                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
-                v[4 * j] = ln_rstd * fmaf(nm, cs.x, v[4 * j]);
-                v[4 * j + 1] = ln_rstd * fmaf(nm, cs.y, v[4 * j + 1]);
-                v[4 * j + 2] = ln_rstd * fmaf(nm, cs.z, v[4 * j + 2]);
-                v[4 * j + 3] = ln_rstd * fmaf(nm, cs.w, v[4 * j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < CHUNK_COLS; ++j) {
-                const float cs = (col0 + j < p.N) ? __ldg(p.ln_colsum + col0 + j) : 0.f;
-                v[j] = ln_rstd * fmaf(nm, cs, v[j]);
-              }
+              const uint64_t lo = ffma2(pack_f32x2(v[4 * j], v[4 * j + 1]), rstd2, add_lo);
+              const uint64_t hi = ffma2(pack_f32x2(v[4 * j + 2], v[4 * j + 3]), rstd2, add_hi);
+              unpack_f32x2(lo, v[4 * j], v[4 * j + 1]);
+              unpack_f32x2(hi, v[4 * j + 2], v[4 * j + 3]);
             }
+            bias_done = true;
           }
         }
         if (p.bias_mode == 1 && !bias_done) {
@@ -426,7 +441,10 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < CHUNK_COLS; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < CHUNK_COLS / 2; ++j) {
+            const uint64_t g2 = gelu_erf2(pack_f32x2(v[2 * j], v[2 * j + 1]));
+            unpack_f32x2(g2, v[2 * j], v[2 * j + 1]);
+          }
         }
         G2T(320 + c);
         if constexpr (KIND == G2_F32) {
@@ -542,6 +560,7 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* slot_out = my_out + (use_idx & 1u) * Cfg::SLOT_BYTES;
           if (elect_one()) bulk_wait_read<1>();   // the store issued two chunks ago used this slot
           __syncwarp();
+          G2T(350 + c);
           // one uniform branch per 64-value chunk picks the conversion (no per-element select in the issue stream)
           auto stage_out = [&](auto f16tag) {
             constexpr bool F16 = decltype(f16tag)::value;
@@ -559,11 +578,13 @@ pio_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           else stage_out(std::false_type{});
           fence_proxy_async_smem();
           __syncwarp();
+          G2T(360 + c);
           if (elect_one()) {
             tma_store_3d_hint(&tmap_out, slot_out, col0, row0, z, p.hint_out);
             bulk_commit();
           }
           __syncwarp();
+          G2T(380 + c);
           ++use_idx;
         }
       }
@@ -949,6 +970,7 @@ static int launch_gemm2_stream(const CUtensorMap& ta, const CUtensorMap& tb, con
   PIO_CUDA_OK(cudaGetLastError());
   return PIO_OK;
 }
+
 
 template <int KIND>
 static int launch_gemm2_kind(const pio_gemm_args* a, const DeviceInfo& dev, cudaStream_t stream) {

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 
 if __name__ == "__main__":
     if os.environ.get("PIO_TRACE_CHILD") != "1":
-        env = dict(os.environ, PIO_NVCC_EXTRA="-DPIO_GEMM2_TRACE", PIO_TRACE_CHILD="1")
+        env = dict(os.environ, PIO_NVCC_EXTRA="-DPIO_GEMM2_TRACE " + os.environ.get("PIO_TRACE_EXTRA", ""), PIO_TRACE_CHILD="1")
         subprocess.run([sys.executable, "-m", "perceiverio_pytorch_b200.build", "--force"], check=True, env=env, cwd=ROOT)
         r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, cwd=ROOT)
         subprocess.run([sys.executable, "-m", "perceiverio_pytorch_b200.build", "--force"], check=True, cwd=ROOT)
@@ -30,13 +30,20 @@ if __name__ == "__main__":
     hi = [torch.randn(M, C, device=dev).to(torch.bfloat16) for _ in range(2)]
     lo = [(0.01 * torch.randn(M, C, device=dev)).to(torch.bfloat16) for _ in range(2)]
     y32 = torch.empty(M, C, device=dev)
-    st = ops.empty_row_stats(M, C, dev)
+    st = ops.empty_row_stats(M, C, dev).zero_()
+    st[:, 0, 1] = C        # unit variance, zero mean for the consumer modes
     lib = _lib.load()
     lib.pio_debug_gemm2_trace.argtypes = [ctypes.c_void_p]
     buf = (ctypes.c_ulonglong * (1024 * 2))()
 
     def launch():
-        if mode == "pair":
+        if mode == "fc1":       # consumer: fused-LayerNorm statistics in, GELU, 16-bit out
+            ops.gemm(hi[0], w, M=M, N=C, K=C, bias=b, act=1, out_bf16=hi[1], ldo16=C, row_stats_in=st, ln_colsum=b,
+                     ln_channels=C, ln_eps=1e-5, reverse_tiles=True)
+        elif mode == "qkv":
+            ops.gemm(hi[0], w, M=M, N=C, K=C, bias=b, out_bf16=hi[1], ldo16=C, row_stats_in=st, ln_colsum=b,
+                     ln_channels=C, ln_eps=1e-5)
+        elif mode == "pair":
             ops.gemm(a, w, M=M, N=C, K=C, bias=b, residual_hi16=hi[0], residual_lo16=lo[0], ldr16=C, out_bf16=hi[1], ldo16=C,
                      out_lo16=lo[1], row_stats_out=st)
         else:
