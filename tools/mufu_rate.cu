@@ -32,6 +32,8 @@ template <int MODE>
 __global__ void mix_kernel(float* out, long long* clk, int iters) {
   float v[16];
   unsigned w[8];
+  unsigned long long acc2 = 0;
+  float accs = 0.001f, accs2 = 0.002f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.001f * (threadIdx.x + i);
 #pragma unroll
@@ -41,7 +43,7 @@ __global__ void mix_kernel(float* out, long long* clk, int iters) {
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (MODE != 1) {
+      if (MODE != 1 && MODE != 6) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[2 * i]));
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[2 * i + 1]));
       }
@@ -49,6 +51,24 @@ __global__ void mix_kernel(float* out, long long* clk, int iters) {
         unsigned r;
         asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
         w[i] ^= r;
+      }
+      if (MODE == 4 || MODE == 5) {      // the softmax loop's full mix: scale-subtract, 2 x ex2, convert, row sum
+        unsigned r;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        w[i] ^= r;
+        if (MODE == 4) {
+          unsigned long long t, u;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(v[2 * i]), "f"(v[2 * i + 1]));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(t) : "l"(acc2));
+          asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2) : "l"(t));
+          asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(v[2 * i]), "=f"(v[2 * i + 1]) : "l"(t));
+          (void)u;
+        } else {
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(v[2 * i]) : "f"(accs));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(v[2 * i + 1]) : "f"(accs));
+          asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(accs) : "f"(v[2 * i]));
+          asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(accs2) : "f"(v[2 * i + 1]));
+        }
       }
       if (MODE == 3) {
         unsigned a = __float_as_uint(v[2 * i]), b = __float_as_uint(v[2 * i + 1]), r;
@@ -63,6 +83,7 @@ __global__ void mix_kernel(float* out, long long* clk, int iters) {
   for (int i = 0; i < 16; ++i) s += v[i];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += __uint_as_float(w[i]);
+  s += accs + accs2 + __uint_as_float((unsigned)acc2);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
 }
@@ -121,6 +142,10 @@ int main() {
   run_mix<1>(256, "cvt.rn.bf16x2.f32 only, two warps per scheduler");
   run_mix<2>(128, "2 x ex2 + cvt.rn.bf16x2 per pair, one warp per scheduler");
   run_mix<2>(256, "2 x ex2 + cvt.rn.bf16x2 per pair, two warps per scheduler");
+  run_mix<4>(128, "2 x ex2 + cvt + fma.f32x2 + add.f32x2 per pair, one warp");
+  run_mix<4>(256, "2 x ex2 + cvt + fma.f32x2 + add.f32x2 per pair, two warps");
+  run_mix<5>(128, "2 x ex2 + cvt + 2 fma.f32 + 2 add.f32 per pair, one warp");
+  run_mix<5>(256, "2 x ex2 + cvt + 2 fma.f32 + 2 add.f32 per pair, two warps");
   run_mix<3>(128, "2 x ex2 + prmt (truncating pack) per pair, one warp");
   run_mix<3>(256, "2 x ex2 + prmt (truncating pack) per pair, two warps");
   return 0;
