@@ -421,16 +421,20 @@ def _pick_splits(B, H, Nq, Nk, dqk, dv, same_kv, sm_count: int = 148) -> int:
     partial last wave otherwise (256 CTAs on 148 SMs waste 14 % of the machine; 4 x 256 waste 1 %)."""
     bn = ops._lib.load().pio_attention_key_tile(dqk, dv, 1 if same_kv else 0)
     tiles = (Nk + bn - 1) // bn
+    ctas = B * H * ((Nq + 127) // 128)
+    # a handful of query tiles over a few thousand keys (the language encoder: 8 heads x 256 latents over 2048 bytes):
+    # unsplit, 8 CTAs of the two-tile kernel walk 32 key tiles each (160 us); split, every SM gets four tiles
+    few = Nk >= 1024 and ctas * 2 <= sm_count
+    min_tiles = 4 if (few and Nk < 4096) else 8
     if ENCODER_KEY_SPLITS > 0:
         cands = [min(ENCODER_KEY_SPLITS, tiles)]
     else:
-        if Nk < 4096:
+        if Nk < 4096 and not few:
             return 1
         cands = range(1, 33)
-    ctas = B * H * ((Nq + 127) // 128)
     best, best_eff = 1, 0.0
     for s in cands:
-        if s > tiles or tiles // s < 8:
+        if s > tiles or tiles // s < min_tiles:
             continue
         if s > 1 and (s - 1) * ((tiles + s - 1) // s) >= tiles:
             continue  # would leave an empty split
