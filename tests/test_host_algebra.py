@@ -86,6 +86,23 @@ def test_key_split_chooser_never_leaves_a_split_empty():
         assert (s - 1) * per < tiles, (B, Nq, Nk, s)
 
 
+def test_key_split_chooser_splits_short_inputs_only_when_the_query_tiles_leave_the_sms_idle():
+    """Inputs of 1024 .. 4095 keys are split only when (batch x heads x query tiles) would occupy less than half of the SMs
+    (the language encoder: 8 heads x 256 latents over 2048 bytes); towers with many query tiles and short self-attends
+    keep the unsplit two-tile kernel."""
+    from perceiverio_pytorch_b200 import _lib
+    lang = engine._pick_splits(1, 8, 256, 2048, 32, 160, False)
+    assert lang > 1
+    bn = _lib.load().pio_attention_key_tile(32, 160, 0)
+    tiles = (2048 + bn - 1) // bn
+    assert tiles // lang >= 4 and (lang - 1) * ((tiles + lang - 1) // lang) < tiles
+    assert engine._pick_splits(1, 16, 2048, 2048, 32, 32, False) == 1      # flow tower: 256 query tiles
+    assert engine._pick_splits(1, 8, 784, 784, 64, 64, False) == 1         # multimodal tower: < 1024 keys
+    assert engine._pick_splits(1, 8, 256, 256, 32, 160, False) == 1        # language tower
+    assert engine._pick_splits(64, 8, 512, 512, 128, 128, False) == 1      # classification tower
+    assert engine._pick_splits(1, 8, 2048, 256, 32, 96, False) == 1        # language decoder
+
+
 def test_postprocessor_linear_composes_with_final_layer():
     """N3 host algebra: post(final(x)) as one affine map (perceiver._ComposedFinal), in fp64 against the two layers
     applied in sequence; the composed weights follow in-place parameter updates and stay out of the state_dict."""
